@@ -1,0 +1,402 @@
+// conv_igemm.cu — implicit-GEMM 3x3 / 1x1 convolution and k=1 GEMM on tcgen05 + TMEM.
+//
+// Replaces every nn.Conv2d 3x3/1x1 and nn.Conv1d k=1 of the UNet torso
+// (reference: guided_diffusion/nn.py:22-32 via dynamic_unet.py:194,220,231,303,311,653).
+//
+// GEMM view: rows = output pixels m = (n*H + y)*W + x of a bf16 NHWC tensor, cols = Cout,
+// K = sum over segments of taps*Cin. One CTA computes a 128 x BLOCK_N tile:
+//   warp 0    : TMA producer. The A tile of tap (dy,dx), channel chunk c0 is ONE 4-D tiled
+//               TMA box {64 ch, bw, bh, bn} at (c0, x0+dx, y0+dy, n0); out-of-bounds rows
+//               and columns are zero-filled by the TMA unit = the conv's zero padding.
+//               The B tile is a 2-D box {64, BLOCK_N} of the K-major weight matrix.
+//   warp 1    : allocates TMEM, issues tcgen05.mma (128 x BLOCK_N x 16, bf16 -> fp32).
+//   warps 2-5 : epilogue. tcgen05.ld the accumulator (lane = pixel row), + bias,
+//               + residual (same / 2x2-avg-pooled / nearest-upsampled source), store.
+// Persistent grid (<= #SM CTAs), static round-robin over tiles with n fastest so CTAs that
+// run concurrently share the A tile in L2; smem ring of STAGES stages; two TMEM accumulator
+// stages so the epilogue of tile i overlaps the main loop of tile i+1.
+#include <string.h>
+
+#include "common.cuh"
+
+namespace adb {
+
+namespace {
+
+constexpr int BLOCK_M = 128;
+constexpr int BLOCK_K = 64;  // bf16 elements = one 128-byte swizzle row
+constexpr int UMMA_K = 16;
+constexpr int A_STAGE_BYTES = BLOCK_M * BLOCK_K * 2;  // 16 KiB
+constexpr int NUM_THREADS = 192;
+
+struct ConvKParams {
+  CUtensorMap tmA[3];
+  CUtensorMap tmW;
+  int seg_taps[3];
+  int seg_cin[3];
+  int seg_chunks[3];
+  int seg_kbase[3];
+  int nseg;
+  int M, cout, H, W;
+  int m_tiles, n_tiles;
+  int k_iters;
+  const float* bias;
+  const __nv_bfloat16* residual;
+  int res_mode;
+  void* out;
+  int out_mode;
+};
+
+template <int BLOCK_N>
+struct Cfg {
+  static constexpr int B_STAGE_BYTES = BLOCK_N * BLOCK_K * 2;
+  static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
+  static constexpr int STAGES = (BLOCK_N >= 192) ? 5 : (BLOCK_N >= 128 ? 6 : 8);
+  static constexpr int TMEM_COLS = (2 * BLOCK_N <= 32)    ? 32
+                                   : (2 * BLOCK_N <= 64)  ? 64
+                                   : (2 * BLOCK_N <= 128) ? 128
+                                   : (2 * BLOCK_N <= 256) ? 256
+                                                          : 512;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/;
+};
+
+template <int BLOCK_N>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+conv_igemm_kernel(const __grid_constant__ ConvKParams p) {
+  using C = Cfg<BLOCK_N>;
+  constexpr int STAGES = C::STAGES;
+  extern __shared__ uint8_t smem_raw[];
+  // barriers: full[STAGES], empty[STAGES], tmem_full[2], tmem_empty[2]
+  __shared__ __align__(8) uint64_t bars[2 * STAGES + 4];
+  __shared__ uint32_t tmem_slot_s;
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;  // SWIZZLE_128B atoms
+  const uint32_t bar_base = smem_u32(bars);
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
+  auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * STAGES + s); };
+  auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * STAGES + 2 + s); };
+  const uint32_t tmem_slot = smem_u32(&tmem_slot_s);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < p.nseg; ++s) tma_prefetch_desc(&p.tmA[s]);
+    tma_prefetch_desc(&p.tmW);
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(tfull_bar(s), 1);
+      mbar_init(tempty_bar(s), 4);  // one arrive per epilogue warp
+    }
+    fence_mbar_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, C::TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(&tmem_slot_s);
+
+  const int num_tiles = p.m_tiles * p.n_tiles;
+  const int P = p.H * p.W;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int m_tile = tile / p.n_tiles;
+        const int n_tile = tile - m_tile * p.n_tiles;
+        const int m0 = m_tile * BLOCK_M;
+        const int img = m0 / P;
+        const int rem = m0 - img * P;
+        const int y0 = rem / p.W;
+        const int x0 = rem - y0 * p.W;
+        for (int s = 0; s < p.nseg; ++s) {
+          const int taps = p.seg_taps[s];
+          const int chunks = p.seg_chunks[s];
+          for (int tap = 0; tap < taps; ++tap) {
+            const int dy = (taps == 9) ? (tap / 3 - 1) : 0;
+            const int dx = (taps == 9) ? (tap % 3 - 1) : 0;
+            const int kb = p.seg_kbase[s] + tap * p.seg_cin[s];
+            for (int ch = 0; ch < chunks; ++ch) {
+              mbar_wait(empty_bar(stage), phase ^ 1u);
+              const uint32_t a_dst = smem_base + stage * C::STAGE_BYTES;
+              const uint32_t b_dst = a_dst + A_STAGE_BYTES;
+              mbar_arrive_expect_tx(full_bar(stage), C::STAGE_BYTES);
+              tma_load_4d(a_dst, &p.tmA[s], full_bar(stage), ch * BLOCK_K, x0 + dx, y0 + dy, img);
+              tma_load_2d(b_dst, &p.tmW, full_bar(stage), kb + ch * BLOCK_K, n_tile * BLOCK_N);
+              if (++stage == STAGES) {
+                stage = 0;
+                phase ^= 1u;
+              }
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(BLOCK_M, BLOCK_N, 0, 0);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
+        for (int k = 0; k < p.k_iters; ++k) {
+          mbar_wait(full_bar(stage), phase);
+          tc_fence_after();
+          const uint32_t a_addr = smem_base + stage * C::STAGE_BYTES;
+          const uint64_t a_desc = umma_desc_kmajor_sw128(a_addr);
+          const uint64_t b_desc = umma_desc_kmajor_sw128(a_addr + A_STAGE_BYTES);
+#pragma unroll
+          for (int kk = 0; kk < BLOCK_K / UMMA_K; ++kk) {
+            // advance 16 bf16 = 32 bytes along K inside the swizzle row: +2 in 16-byte units
+            umma_bf16_ss(d_tmem, a_desc + 2u * kk, b_desc + 2u * kk, idesc, (k | kk) != 0);
+          }
+          umma_commit(empty_bar(stage));
+          if (++stage == STAGES) {
+            stage = 0;
+            phase ^= 1u;
+          }
+        }
+        umma_commit(tfull_bar(acc));
+        if (++acc == 2) {
+          acc = 0;
+          acc_phase ^= 1u;
+        }
+      }
+    }
+  } else {
+    // ===================== epilogue (warps 2..5) =====================
+    const int quarter = warp & 3;  // TMEM lane quarter this warp may access
+    const int row = quarter * 32 + lane;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int m_tile = tile / p.n_tiles;
+      const int n_tile = tile - m_tile * p.n_tiles;
+      const int m = m_tile * BLOCK_M + row;
+      const int n0 = n_tile * BLOCK_N;
+      mbar_wait(tfull_bar(acc), acc_phase);
+      tc_fence_after();
+      const bool row_ok = m < p.M;
+      // geometry of this output pixel (for resampled residuals / NCHW stores)
+      const int img = m / P;
+      const int rem = m - img * P;
+      const int y = rem / p.W;
+      const int x = rem - y * p.W;
+#pragma unroll 1
+      for (int c = 0; c < BLOCK_N; c += 32) {
+        uint32_t v[32];
+        const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * BLOCK_N + c;
+        if (BLOCK_N - c >= 32) {
+          tmem_ld_32x32b_x32(taddr, v);
+        } else {
+          tmem_ld_32x32b_x16(taddr, v);
+#pragma unroll
+          for (int i = 16; i < 32; ++i) v[i] = 0;
+        }
+        tmem_wait_ld();
+        const int col0 = n0 + c;
+        if (row_ok && col0 < p.cout) {
+          float f[32];
+#pragma unroll
+          for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]);
+          if (p.bias != nullptr) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+              if (col0 + i < p.cout) f[i] += __ldg(p.bias + col0 + i);
+          }
+          const int ncols = min(32, p.cout - col0);
+          if (p.out_mode == ADB_OUT_BF16_NHWC) {
+            // residual: vector path needs 8-channel groups fully inside cout (cout % 8 == 0)
+            if (p.res_mode != ADB_RES_NONE) {
+              const int nsrc = (p.res_mode == ADB_RES_AVGPOOL2) ? 4 : 1;
+              const float wgt = (p.res_mode == ADB_RES_AVGPOOL2) ? 0.25f : 1.0f;
+              for (int sidx = 0; sidx < nsrc; ++sidx) {
+                size_t pix;
+                if (p.res_mode == ADB_RES_SAME) {
+                  pix = (size_t)m;
+                } else if (p.res_mode == ADB_RES_AVGPOOL2) {
+                  const int sy = 2 * y + (sidx >> 1), sx = 2 * x + (sidx & 1);
+                  pix = ((size_t)img * (2 * p.H) + sy) * (2 * p.W) + sx;
+                } else {  // nearest 2x upsample of a half-resolution source
+                  pix = ((size_t)img * (p.H / 2) + (y >> 1)) * (p.W / 2) + (x >> 1);
+                }
+                const __nv_bfloat16* rp = p.residual + pix * p.cout + col0;
+#pragma unroll
+                for (int g = 0; g < 4; ++g) {
+                  if (g * 8 < ncols) {
+                    const uint4 r = __ldg(reinterpret_cast<const uint4*>(rp) + g);
+                    f[g * 8 + 0] += wgt * bf16_lo(r.x);
+                    f[g * 8 + 1] += wgt * bf16_hi(r.x);
+                    f[g * 8 + 2] += wgt * bf16_lo(r.y);
+                    f[g * 8 + 3] += wgt * bf16_hi(r.y);
+                    f[g * 8 + 4] += wgt * bf16_lo(r.z);
+                    f[g * 8 + 5] += wgt * bf16_hi(r.z);
+                    f[g * 8 + 6] += wgt * bf16_lo(r.w);
+                    f[g * 8 + 7] += wgt * bf16_hi(r.w);
+                  }
+                }
+              }
+            }
+            __nv_bfloat16* op = reinterpret_cast<__nv_bfloat16*>(p.out) + (size_t)m * p.cout + col0;
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+              if (g * 8 < ncols) {
+                uint4 o;
+                o.x = pack_bf16x2(f[g * 8 + 0], f[g * 8 + 1]);
+                o.y = pack_bf16x2(f[g * 8 + 2], f[g * 8 + 3]);
+                o.z = pack_bf16x2(f[g * 8 + 4], f[g * 8 + 5]);
+                o.w = pack_bf16x2(f[g * 8 + 6], f[g * 8 + 7]);
+                reinterpret_cast<uint4*>(op)[g] = o;
+              }
+            }
+          } else {
+            // fp32 NCHW: for a fixed channel, the warp's 32 pixels are contiguous along x
+            float* op = reinterpret_cast<float*>(p.out);
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+              if (i < ncols) op[((size_t)img * p.cout + (col0 + i)) * P + rem] = f[i];
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty_bar(acc));
+      if (++acc == 2) {
+        acc = 0;
+        acc_phase ^= 1u;
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, C::TMEM_COLS);
+  }
+}
+
+template <int BLOCK_N>
+int launch(const ConvKParams& kp, cudaStream_t stream) {
+  using C = Cfg<BLOCK_N>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    ADB_CUDA(cudaFuncSetAttribute(conv_igemm_kernel<BLOCK_N>,
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+    attr_set = true;
+  }
+  const int tiles = kp.m_tiles * kp.n_tiles;
+  const int grid = tiles < num_sms() ? tiles : num_sms();
+  conv_igemm_kernel<BLOCK_N><<<grid, NUM_THREADS, C::SMEM_BYTES, stream>>>(kp);
+  ADB_CUDA(cudaGetLastError());
+  return 1;
+}
+
+}  // namespace
+
+// N tile for a given real Cout; weights are padded to a multiple of it.
+int conv_block_n(int cout) {
+  if (cout % 192 == 0) return 192;
+  if (cout % 128 == 0) return 128;
+  if (cout <= 16) return 16;
+  if (cout <= 64) return 64;
+  if (cout <= 128) return 128;
+  return 192;
+}
+
+namespace {
+
+bool is_pow2(int v) { return v > 0 && (v & (v - 1)) == 0; }
+
+}  // namespace
+
+int conv_igemm_submit(adb_plan* plan, const adb_conv_desc* d, cudaStream_t stream) {
+  ADB_REQUIRE(d != nullptr, "conv_igemm: null descriptor");
+  ADB_REQUIRE(d->n > 0 && is_pow2(d->h) && is_pow2(d->w), "conv_igemm: n>0 and power-of-two h,w required (n=%d h=%d w=%d)", d->n, d->h, d->w);
+  ADB_REQUIRE(d->nseg >= 1 && d->nseg <= 3, "conv_igemm: nseg must be 1..3");
+  ADB_REQUIRE(d->cout > 0 && d->cout_pad >= d->cout && d->cout_pad % 16 == 0, "conv_igemm: cout_pad must be a multiple of 16 and >= cout");
+  ADB_REQUIRE(d->weight && d->out, "conv_igemm: null weight/out");
+  ADB_REQUIRE(d->out_mode == ADB_OUT_BF16_NHWC || d->out_mode == ADB_OUT_F32_NCHW, "conv_igemm: bad out_mode");
+  if (d->out_mode == ADB_OUT_BF16_NHWC)
+    ADB_REQUIRE(d->cout % 8 == 0, "conv_igemm: bf16 NHWC output needs cout %% 8 == 0");
+  ADB_REQUIRE(d->res_mode == ADB_RES_NONE || (d->residual != nullptr && d->out_mode == ADB_OUT_BF16_NHWC),
+              "conv_igemm: residual requires a source and bf16 output");
+  if (d->res_mode == ADB_RES_NEAREST2) ADB_REQUIRE(d->h >= 2 && d->w >= 2, "conv_igemm: nearest2 needs h,w >= 2");
+
+  ConvKParams kp;
+  memset(&kp, 0, sizeof(kp));
+  const long long P = (long long)d->h * d->w;
+  const long long M = P * d->n;
+  ADB_REQUIRE(M < (1ll << 31), "conv_igemm: too many pixels");
+  // box geometry: 128 rows of the GEMM = bn images x bh rows x bw columns
+  const int bw = d->w < BLOCK_M ? d->w : BLOCK_M;
+  const int bh = (P < BLOCK_M) ? d->h : (BLOCK_M / bw);
+  const int bn = (P < BLOCK_M) ? (int)(BLOCK_M / P) : 1;
+  ADB_REQUIRE(bw * bh * bn == BLOCK_M, "conv_igemm: cannot tile %dx%d images into 128-row boxes", d->h, d->w);
+
+  int ktot = 0;
+  for (int s = 0; s < d->nseg; ++s) {
+    const adb_conv_seg& sg = d->seg[s];
+    ADB_REQUIRE(sg.act != nullptr && sg.cin > 0 && sg.cin % 8 == 0, "conv_igemm: segment %d needs cin %% 8 == 0", s);
+    ADB_REQUIRE(sg.taps == 1 || sg.taps == 9, "conv_igemm: taps must be 1 or 9");
+    kp.seg_taps[s] = sg.taps;
+    kp.seg_cin[s] = sg.cin;
+    kp.seg_chunks[s] = (sg.cin + BLOCK_K - 1) / BLOCK_K;
+    kp.seg_kbase[s] = ktot;
+    ktot += sg.taps * sg.cin;
+    kp.k_iters += sg.taps * kp.seg_chunks[s];
+    const uint64_t dims[4] = {(uint64_t)sg.cin, (uint64_t)d->w, (uint64_t)d->h, (uint64_t)d->n};
+    const uint64_t strides[3] = {(uint64_t)sg.cin * 2, (uint64_t)d->w * sg.cin * 2,
+                                 (uint64_t)P * sg.cin * 2};
+    const uint32_t box[4] = {(uint32_t)BLOCK_K, (uint32_t)bw, (uint32_t)bh, (uint32_t)bn};
+    int r = make_tmap_bf16(&kp.tmA[s], sg.act, 4, dims, strides, box);
+    if (r != ADB_OK) return r;
+  }
+  const int block_n = conv_block_n(d->cout);
+  ADB_REQUIRE(d->cout_pad % block_n == 0, "conv_igemm: cout_pad (%d) must be a multiple of the N tile %d (adb_conv_block_n)", d->cout_pad, block_n);
+  {
+    const uint64_t dims[2] = {(uint64_t)ktot, (uint64_t)d->cout_pad};
+    const uint64_t strides[1] = {(uint64_t)ktot * 2};
+    const uint32_t box[2] = {(uint32_t)BLOCK_K, (uint32_t)block_n};
+    int r = make_tmap_bf16(&kp.tmW, d->weight, 2, dims, strides, box);
+    if (r != ADB_OK) return r;
+  }
+  kp.nseg = d->nseg;
+  kp.M = (int)M;
+  kp.cout = d->cout;
+  kp.H = d->h;
+  kp.W = d->w;
+  kp.m_tiles = (int)((M + BLOCK_M - 1) / BLOCK_M);
+  kp.n_tiles = (d->cout_pad + block_n - 1) / block_n;
+  kp.bias = d->bias;
+  kp.residual = reinterpret_cast<const __nv_bfloat16*>(d->residual);
+  kp.res_mode = d->res_mode;
+  kp.out = d->out;
+  kp.out_mode = d->out_mode;
+
+  return submit(plan, stream, [kp, block_n](cudaStream_t s) -> int {
+    switch (block_n) {
+      case 192: return launch<192>(kp, s);
+      case 128: return launch<128>(kp, s);
+      case 64: return launch<64>(kp, s);
+      default: return launch<16>(kp, s);
+    }
+  });
+}
+
+}  // namespace adb

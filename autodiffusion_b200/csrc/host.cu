@@ -1,0 +1,218 @@
+// host.cu — host-side runtime of libadb200: error strings, TMA descriptor encoding,
+// plan record/replay and the extern "C" entry points declared in include/adb200.h.
+#include <cudaTypedefs.h>
+#include <stdarg.h>
+#include <string.h>
+
+#include <mutex>
+
+#include "common.cuh"
+
+namespace adb {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+int cuda_fail(cudaError_t e, const char* what) {
+  set_error("CUDA error %d (%s) at %s", (int)e, cudaGetErrorString(e), what);
+  return ADB_ERR_CUDA;
+}
+
+int num_sms() {
+  static int sms = 0;
+  if (sms == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (sms <= 0) sms = 148;
+  }
+  return sms;
+}
+
+// The driver entry point is resolved through the runtime so the library needs no direct
+// libcuda link (nvcc's static cudart dlopens the driver).
+static PFN_cuTensorMapEncodeTiled_v12000 get_encode_fn() {
+  static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(p);
+  });
+  return fn;
+}
+
+int make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims,
+                   const uint64_t* strides_bytes, const uint32_t* box) {
+  auto fn = get_encode_fn();
+  if (!fn) {
+    set_error("cuTensorMapEncodeTiled not available from the driver");
+    return ADB_ERR_CUDA;
+  }
+  if ((reinterpret_cast<uintptr_t>(base) & 15u) != 0) {
+    set_error("TMA base pointer %p is not 16-byte aligned", base);
+    return ADB_ERR_INVALID;
+  }
+  cuuint64_t gdim[5];
+  cuuint64_t gstr[4];
+  cuuint32_t bx[5];
+  cuuint32_t estr[5];
+  for (int i = 0; i < rank; ++i) {
+    gdim[i] = dims[i];
+    bx[i] = box[i];
+    estr[i] = 1;
+    if (box[i] == 0 || box[i] > 256) {
+      set_error("TMA box dim %d = %u out of range", i, box[i]);
+      return ADB_ERR_INVALID;
+    }
+  }
+  for (int i = 0; i + 1 < rank; ++i) {
+    gstr[i] = strides_bytes[i];
+    if (strides_bytes[i] % 16 != 0) {
+      set_error("TMA stride %d = %llu bytes is not a multiple of 16", i,
+                (unsigned long long)strides_bytes[i]);
+      return ADB_ERR_INVALID;
+    }
+  }
+  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base),
+                  gdim, gstr, bx, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed with CUresult %d (rank %d dims %llu,%llu box %u,%u)",
+              (int)r, rank, (unsigned long long)dims[0], (unsigned long long)dims[1], box[0], box[1]);
+    return ADB_ERR_CUDA;
+  }
+  return ADB_OK;
+}
+
+// implemented in the kernel translation units
+int conv_block_n(int cout);
+int conv_igemm_submit(adb_plan*, const adb_conv_desc*, cudaStream_t);
+int attention_submit(adb_plan*, const void*, void*, int, int, int, int, cudaStream_t);
+int groupnorm_submit(adb_plan*, const adb_gn_desc*, cudaStream_t);
+int resample2x_submit(adb_plan*, const void*, void*, int, int, int, int, int, cudaStream_t);
+int stem_conv_submit(adb_plan*, const float*, const float*, const float*, void*, int, int, int, int,
+                     int, cudaStream_t);
+int timestep_embedding_submit(adb_plan*, const int64_t*, float*, int, int, cudaStream_t);
+int linear_submit(adb_plan*, const float*, const float*, const float*, float*, int, int, int, int,
+                  const float*, const int64_t*, cudaStream_t);
+int ddim_step_submit(adb_plan*, const float*, const float*, int, const float*, float*, float*, int,
+                     int, int, const float*, int, cudaStream_t);
+int pack_uint8_submit(adb_plan*, const float*, uint8_t*, int, int, int, cudaStream_t);
+int moments_submit(adb_plan*, const float*, int, int, double*, double*, cudaStream_t);
+
+}  // namespace adb
+
+using namespace adb;
+
+extern "C" {
+
+const char* adb_last_error(void) { return g_err; }
+int adb_version(void) { return 100; }
+
+int adb_device_check(void) {
+  int dev = 0;
+  ADB_CUDA(cudaGetDevice(&dev));
+  int major = 0;
+  ADB_CUDA(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev));
+  if (major != 10) {
+    set_error("device compute capability %d.x is not sm_100 (B200)", major);
+    return ADB_ERR_UNSUPPORTED;
+  }
+  return ADB_OK;
+}
+
+adb_plan* adb_plan_create(void) { return new (std::nothrow) adb_plan(); }
+void adb_plan_destroy(adb_plan* plan) { delete plan; }
+int adb_plan_num_ops(const adb_plan* plan) { return plan ? (int)plan->ops.size() : 0; }
+
+int adb_plan_run(adb_plan* plan, adb_stream stream) {
+  if (!plan) {
+    set_error("adb_plan_run: null plan");
+    return ADB_ERR_INVALID;
+  }
+  int launches = 0;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  for (auto& op : plan->ops) {
+    int r = op(s);
+    if (r < 0) return r;
+    launches += r;
+  }
+  return launches;
+}
+
+int adb_conv_block_n(int cout) { return conv_block_n(cout); }
+
+int adb_conv_igemm(adb_plan* plan, const adb_conv_desc* d, adb_stream stream) {
+  return conv_igemm_submit(plan, d, static_cast<cudaStream_t>(stream));
+}
+
+int adb_attention(adb_plan* plan, const void* qkv, void* out, int b, int t, int heads,
+                  int legacy_order, adb_stream stream) {
+  return attention_submit(plan, qkv, out, b, t, heads, legacy_order, static_cast<cudaStream_t>(stream));
+}
+
+int adb_groupnorm(adb_plan* plan, const adb_gn_desc* d, adb_stream stream) {
+  return groupnorm_submit(plan, d, static_cast<cudaStream_t>(stream));
+}
+
+int adb_resample2x(adb_plan* plan, const void* src, void* dst, int n, int h, int w, int c, int mode,
+                   adb_stream stream) {
+  return resample2x_submit(plan, src, dst, n, h, w, c, mode, static_cast<cudaStream_t>(stream));
+}
+
+int adb_stem_conv(adb_plan* plan, const float* x, const float* weight, const float* bias, void* out,
+                  int n, int cin, int h, int w, int cout, adb_stream stream) {
+  return stem_conv_submit(plan, x, weight, bias, out, n, cin, h, w, cout,
+                          static_cast<cudaStream_t>(stream));
+}
+
+int adb_timestep_embedding(adb_plan* plan, const int64_t* t, float* out, int b, int dim,
+                           adb_stream stream) {
+  return timestep_embedding_submit(plan, t, out, b, dim, static_cast<cudaStream_t>(stream));
+}
+
+int adb_linear(adb_plan* plan, const float* x, const float* w, const float* bias, float* out, int b,
+               int k, int nout, int silu_in, const float* table, const int64_t* idx,
+               adb_stream stream) {
+  return linear_submit(plan, x, w, bias, out, b, k, nout, silu_in, table, idx,
+                       static_cast<cudaStream_t>(stream));
+}
+
+int adb_ddim_step(adb_plan* plan, const float* x, const float* model_out, int eps_channels,
+                  const float* grad, float* x_prev, float* pred_xstart, int n, int c, int hw,
+                  const float coef[5], int clip_denoised, adb_stream stream) {
+  return ddim_step_submit(plan, x, model_out, eps_channels, grad, x_prev, pred_xstart, n, c, hw, coef,
+                          clip_denoised, static_cast<cudaStream_t>(stream));
+}
+
+int adb_pack_uint8(adb_plan* plan, const float* sample, uint8_t* out, int n, int c, int hw,
+                   adb_stream stream) {
+  return pack_uint8_submit(plan, sample, out, n, c, hw, static_cast<cudaStream_t>(stream));
+}
+
+int adb_moments_accumulate(adb_plan* plan, const float* feats, int n, int d, double* sum_x,
+                           double* sum_xx, adb_stream stream) {
+  return moments_submit(plan, feats, n, d, sum_x, sum_xx, static_cast<cudaStream_t>(stream));
+}
+
+int adb_memset0(adb_plan* plan, void* ptr, size_t bytes, adb_stream stream) {
+  if (!ptr && bytes) {
+    set_error("adb_memset0: null pointer");
+    return ADB_ERR_INVALID;
+  }
+  return submit(plan, static_cast<cudaStream_t>(stream), [ptr, bytes](cudaStream_t s) -> int {
+    ADB_CUDA(cudaMemsetAsync(ptr, 0, bytes, s));
+    return 1;
+  });
+}
+
+}  // extern "C"

@@ -1,0 +1,355 @@
+"""Torch-tensor front end of the C-ABI ops (include/adb200.h).
+
+PyTorch is used here only for device memory and the current CUDA stream: every function
+hands raw device pointers to libadb200.so. Tensors must live on a CUDA device; a CPU tensor
+raises — there is no fallback.
+
+Activation layout: bf16 NHWC `[n, h, w, c]` contiguous. Passing `plan=` records the op
+into a `Plan` (replayed with `Plan.run()`, capturable into a CUDA graph) instead of
+launching it.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Sequence
+
+import torch
+
+from . import _lib
+from ._lib import (
+    OUT_BF16_NHWC,
+    OUT_F32_NCHW,
+    RES_AVGPOOL2,
+    RES_NEAREST2,
+    RES_NONE,
+    RES_SAME,
+    RESAMPLE_AVGPOOL2,
+    RESAMPLE_NEAREST2,
+    RESAMPLE_NONE,
+)
+
+__all__ = [
+    "Plan", "conv_block_n", "pack_conv_weight", "conv_igemm", "attention", "groupnorm", "resample2x",
+    "stem_conv", "timestep_embedding", "linear", "ddim_step", "pack_uint8", "moments_accumulate",
+    "memset0", "nchw_to_nhwc_bf16", "nhwc_to_nchw_f32",
+]
+
+
+def _dev(t: torch.Tensor, name: str, dtype=None) -> int:
+    if not isinstance(t, torch.Tensor) or not t.is_cuda:
+        raise RuntimeError(f"{name}: expected a CUDA tensor (autodiffusion_b200 has no CPU path)")
+    if dtype is not None and t.dtype != dtype:
+        raise TypeError(f"{name}: expected dtype {dtype}, got {t.dtype}")
+    if not t.is_contiguous():
+        raise ValueError(f"{name}: tensor must be contiguous")
+    return t.data_ptr()
+
+
+def _opt(t: Optional[torch.Tensor], name: str, dtype=None) -> Optional[int]:
+    return None if t is None else _dev(t, name, dtype)
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+class Plan:
+    """A recorded launch schedule (adb_plan). Holds references to every tensor recorded into it."""
+
+    def __init__(self):
+        self._lib = _lib.lib()
+        self._h = self._lib.adb_plan_create()
+        if not self._h:
+            raise MemoryError("adb_plan_create failed")
+        self._keep = []
+        self.launches_per_run = None
+
+    def keep(self, *tensors):
+        self._keep.extend(t for t in tensors if t is not None)
+
+    @property
+    def handle(self):
+        return self._h
+
+    def num_ops(self) -> int:
+        return self._lib.adb_plan_num_ops(self._h)
+
+    def run(self) -> int:
+        n = _lib.check(self._lib.adb_plan_run(self._h, _stream()), "adb_plan_run")
+        self.launches_per_run = n
+        return n
+
+    def __del__(self):
+        h, self._h = getattr(self, "_h", None), None
+        if h:
+            try:
+                self._lib.adb_plan_destroy(h)
+            except Exception:
+                pass
+
+
+def _ph(plan: Optional[Plan]):
+    return None if plan is None else plan.handle
+
+
+def conv_block_n(cout: int) -> int:
+    return _lib.lib().adb_conv_block_n(int(cout))
+
+
+def pack_conv_weight(weights: Sequence[torch.Tensor], device=None) -> torch.Tensor:
+    """Pack PyTorch conv weights into the implicit-GEMM K-major bf16 matrix.
+
+    Each `[cout, cin, kh, kw]` (or `[cout, cin, 1]`) weight becomes `[cout, kh*kw*cin]` with K
+    ordered (tap, cin); several weights (K-segments) are concatenated along K. Rows are
+    zero-padded up to a multiple of the kernel's N tile.
+    """
+    mats = []
+    cout = weights[0].shape[0]
+    for w in weights:
+        if w.dim() == 3:
+            w = w.unsqueeze(-1)
+        assert w.shape[0] == cout
+        mats.append(w.detach().float().permute(0, 2, 3, 1).reshape(cout, -1))
+    m = torch.cat(mats, dim=1)
+    bn = conv_block_n(cout)
+    pad = (-cout) % bn
+    if pad:
+        m = torch.cat([m, m.new_zeros(pad, m.shape[1])], dim=0)
+    m = m.to(torch.bfloat16).contiguous()
+    return m.to(device) if device is not None else m
+
+
+def conv_igemm(
+    segs: Sequence[tuple],
+    weight: torch.Tensor,
+    bias: Optional[torch.Tensor],
+    cout: int,
+    out: Optional[torch.Tensor] = None,
+    residual: Optional[torch.Tensor] = None,
+    res_mode: int = RES_NONE,
+    out_mode: int = OUT_BF16_NHWC,
+    plan: Optional[Plan] = None,
+) -> torch.Tensor:
+    """segs: [(act[n,h,w,cin] bf16, taps), ...]; weight from `pack_conv_weight`."""
+    act0 = segs[0][0]
+    n, h, w = act0.shape[0], act0.shape[1], act0.shape[2]
+    d = _lib.ConvDesc()
+    d.n, d.h, d.w = n, h, w
+    d.cout = cout
+    d.cout_pad = weight.shape[0]
+    d.nseg = len(segs)
+    ktot = 0
+    for i, (act, taps) in enumerate(segs):
+        assert act.shape[:3] == (n, h, w), "all K-segments share the output geometry"
+        d.seg[i].act = _dev(act, f"seg{i}.act", torch.bfloat16)
+        d.seg[i].cin = act.shape[3]
+        d.seg[i].taps = taps
+        ktot += taps * act.shape[3]
+    if weight.shape[1] != ktot:
+        raise ValueError(f"packed weight K={weight.shape[1]} does not match segments K={ktot}")
+    d.weight = _dev(weight, "weight", torch.bfloat16)
+    d.bias = _opt(bias, "bias", torch.float32)
+    d.residual = _opt(residual, "residual", torch.bfloat16)
+    d.res_mode = res_mode
+    if out is None:
+        if out_mode == OUT_BF16_NHWC:
+            out = torch.empty((n, h, w, cout), dtype=torch.bfloat16, device=act0.device)
+        else:
+            out = torch.empty((n, cout, h, w), dtype=torch.float32, device=act0.device)
+    d.out = _dev(out, "out")
+    d.out_mode = out_mode
+    _lib.check(_lib.lib().adb_conv_igemm(_ph(plan), C.byref(d), _stream()), "adb_conv_igemm")
+    if plan is not None:
+        plan.keep(*[s[0] for s in segs], weight, bias, residual, out)
+    return out
+
+
+def attention(qkv: torch.Tensor, b: int, t: int, heads: int, legacy_order: bool,
+              out: Optional[torch.Tensor] = None, plan: Optional[Plan] = None) -> torch.Tensor:
+    """qkv: bf16 [b*t, 3*heads*64] -> bf16 [b*t, heads*64]."""
+    c = heads * 64
+    assert qkv.numel() == b * t * 3 * c
+    if out is None:
+        out = torch.empty((b * t, c), dtype=torch.bfloat16, device=qkv.device)
+    _lib.check(
+        _lib.lib().adb_attention(_ph(plan), _dev(qkv, "qkv", torch.bfloat16), _dev(out, "out", torch.bfloat16),
+                                 b, t, heads, int(bool(legacy_order)), _stream()),
+        "adb_attention",
+    )
+    if plan is not None:
+        plan.keep(qkv, out)
+    return out
+
+
+def groupnorm(
+    src0: torch.Tensor,
+    gamma: torch.Tensor,
+    beta: torch.Tensor,
+    src1: Optional[torch.Tensor] = None,
+    scale_shift: Optional[torch.Tensor] = None,
+    ss_stride: int = 0,
+    silu: bool = True,
+    resample: int = RESAMPLE_NONE,
+    eps: float = 1e-5,
+    out: Optional[torch.Tensor] = None,
+    stats: Optional[torch.Tensor] = None,
+    plan: Optional[Plan] = None,
+) -> torch.Tensor:
+    n, h, w, c0 = src0.shape
+    c1 = 0 if src1 is None else src1.shape[3]
+    c = c0 + c1
+    ho, wo = (h // 2, w // 2) if resample == RESAMPLE_AVGPOOL2 else ((h * 2, w * 2) if resample == RESAMPLE_NEAREST2 else (h, w))
+    if out is None:
+        out = torch.empty((n, ho, wo, c), dtype=torch.bfloat16, device=src0.device)
+    if stats is None:
+        stats = torch.empty((n, 32, 2), dtype=torch.float64, device=src0.device)
+    d = _lib.GnDesc()
+    d.n, d.h, d.w = n, h, w
+    d.src0, d.c0 = _dev(src0, "src0", torch.bfloat16), c0
+    d.src1, d.c1 = _opt(src1, "src1", torch.bfloat16), c1
+    d.gamma = _dev(gamma, "gamma", torch.float32)
+    d.beta = _dev(beta, "beta", torch.float32)
+    d.eps = eps
+    d.scale_shift = _opt(scale_shift, "scale_shift", torch.float32)
+    d.ss_stride = ss_stride
+    d.silu = int(bool(silu))
+    d.resample = resample
+    d.out = _dev(out, "out", torch.bfloat16)
+    d.stats = _dev(stats, "stats", torch.float64)
+    _lib.check(_lib.lib().adb_groupnorm(_ph(plan), C.byref(d), _stream()), "adb_groupnorm")
+    if plan is not None:
+        plan.keep(src0, src1, gamma, beta, scale_shift, out, stats)
+    return out
+
+
+def resample2x(src: torch.Tensor, mode: int, out: Optional[torch.Tensor] = None,
+               plan: Optional[Plan] = None) -> torch.Tensor:
+    n, h, w, c = src.shape
+    ho, wo = (h // 2, w // 2) if mode == RESAMPLE_AVGPOOL2 else (h * 2, w * 2)
+    if out is None:
+        out = torch.empty((n, ho, wo, c), dtype=torch.bfloat16, device=src.device)
+    _lib.check(
+        _lib.lib().adb_resample2x(_ph(plan), _dev(src, "src", torch.bfloat16), _dev(out, "out", torch.bfloat16),
+                                  n, h, w, c, mode, _stream()),
+        "adb_resample2x",
+    )
+    if plan is not None:
+        plan.keep(src, out)
+    return out
+
+
+def stem_conv(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor],
+              out: Optional[torch.Tensor] = None, plan: Optional[Plan] = None) -> torch.Tensor:
+    """x fp32 NCHW, weight fp32 [cout,cin,3,3] -> bf16 NHWC."""
+    n, cin, h, w = x.shape
+    cout = weight.shape[0]
+    if out is None:
+        out = torch.empty((n, h, w, cout), dtype=torch.bfloat16, device=x.device)
+    _lib.check(
+        _lib.lib().adb_stem_conv(_ph(plan), _dev(x, "x", torch.float32), _dev(weight, "weight", torch.float32),
+                                 _opt(bias, "bias", torch.float32), _dev(out, "out", torch.bfloat16),
+                                 n, cin, h, w, cout, _stream()),
+        "adb_stem_conv",
+    )
+    if plan is not None:
+        plan.keep(x, weight, bias, out)
+    return out
+
+
+def timestep_embedding(t: torch.Tensor, dim: int, out: Optional[torch.Tensor] = None,
+                       plan: Optional[Plan] = None) -> torch.Tensor:
+    b = t.shape[0]
+    if out is None:
+        out = torch.empty((b, dim), dtype=torch.float32, device=t.device)
+    _lib.check(
+        _lib.lib().adb_timestep_embedding(_ph(plan), _dev(t, "t", torch.int64), _dev(out, "out", torch.float32),
+                                          b, dim, _stream()),
+        "adb_timestep_embedding",
+    )
+    if plan is not None:
+        plan.keep(t, out)
+    return out
+
+
+def linear(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor], silu_in: bool = False,
+           table: Optional[torch.Tensor] = None, idx: Optional[torch.Tensor] = None,
+           out: Optional[torch.Tensor] = None, plan: Optional[Plan] = None) -> torch.Tensor:
+    b, k = x.shape
+    nout = weight.shape[0]
+    assert weight.shape[1] == k
+    if out is None:
+        out = torch.empty((b, nout), dtype=torch.float32, device=x.device)
+    _lib.check(
+        _lib.lib().adb_linear(_ph(plan), _dev(x, "x", torch.float32), _dev(weight, "weight", torch.float32),
+                              _opt(bias, "bias", torch.float32), _dev(out, "out", torch.float32), b, k, nout,
+                              int(bool(silu_in)), _opt(table, "table", torch.float32),
+                              _opt(idx, "idx", torch.int64), _stream()),
+        "adb_linear",
+    )
+    if plan is not None:
+        plan.keep(x, weight, bias, table, idx, out)
+    return out
+
+
+def ddim_step(x: torch.Tensor, model_out: torch.Tensor, grad: Optional[torch.Tensor], coef: Sequence[float],
+              clip_denoised: bool = True, x_prev: Optional[torch.Tensor] = None,
+              pred_xstart: Optional[torch.Tensor] = None, plan: Optional[Plan] = None) -> torch.Tensor:
+    """x fp32 [n,c,h,w]; model_out fp32 [n,>=c,h,w] (eps in the first c channels)."""
+    n, c = x.shape[0], x.shape[1]
+    hw = x[0, 0].numel()
+    if x_prev is None:
+        x_prev = torch.empty_like(x)
+    cf = (C.c_float * 5)(*[float(v) for v in coef])
+    _lib.check(
+        _lib.lib().adb_ddim_step(_ph(plan), _dev(x, "x", torch.float32), _dev(model_out, "model_out", torch.float32),
+                                 model_out.shape[1], _opt(grad, "grad", torch.float32),
+                                 _dev(x_prev, "x_prev", torch.float32), _opt(pred_xstart, "pred_xstart", torch.float32),
+                                 n, c, hw, cf, int(bool(clip_denoised)), _stream()),
+        "adb_ddim_step",
+    )
+    if plan is not None:
+        plan.keep(x, model_out, grad, x_prev, pred_xstart)
+    return x_prev
+
+
+def pack_uint8(sample: torch.Tensor, out: Optional[torch.Tensor] = None, plan: Optional[Plan] = None) -> torch.Tensor:
+    n, c, h, w = sample.shape
+    if out is None:
+        out = torch.empty((n, h, w, c), dtype=torch.uint8, device=sample.device)
+    _lib.check(
+        _lib.lib().adb_pack_uint8(_ph(plan), _dev(sample, "sample", torch.float32), _dev(out, "out", torch.uint8),
+                                  n, c, h * w, _stream()),
+        "adb_pack_uint8",
+    )
+    if plan is not None:
+        plan.keep(sample, out)
+    return out
+
+
+def moments_accumulate(feats: torch.Tensor, sum_x: torch.Tensor, sum_xx: torch.Tensor,
+                       plan: Optional[Plan] = None) -> None:
+    n, d = feats.shape
+    assert sum_x.shape == (d,) and sum_xx.shape == (d, d)
+    _lib.check(
+        _lib.lib().adb_moments_accumulate(_ph(plan), _dev(feats, "feats", torch.float32), n, d,
+                                          _dev(sum_x, "sum_x", torch.float64), _dev(sum_xx, "sum_xx", torch.float64),
+                                          _stream()),
+        "adb_moments_accumulate",
+    )
+    if plan is not None:
+        plan.keep(feats, sum_x, sum_xx)
+
+
+def memset0(t: torch.Tensor, plan: Optional[Plan] = None) -> None:
+    _lib.check(_lib.lib().adb_memset0(_ph(plan), _dev(t, "t"), t.numel() * t.element_size(), _stream()), "adb_memset0")
+    if plan is not None:
+        plan.keep(t)
+
+
+# layout helpers for tests / API edges (plain torch data movement, not compute)
+def nchw_to_nhwc_bf16(x: torch.Tensor) -> torch.Tensor:
+    return x.permute(0, 2, 3, 1).contiguous().to(torch.bfloat16)
+
+
+def nhwc_to_nchw_f32(x: torch.Tensor) -> torch.Tensor:
+    return x.float().permute(0, 3, 1, 2).contiguous()

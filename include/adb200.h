@@ -1,0 +1,170 @@
+/*
+ * adb200.h — C-ABI of libadb200.so, the B200 (sm_100a) compute library under the
+ * AutoDiffusion candidate evaluator.
+ *
+ * Plain pointers and sizes only: no torch types cross this boundary. Every device
+ * pointer is borrowed for the duration of the call (or of the plan, for recorded
+ * ops). All functions return 0 on success and a negative adb_status on failure;
+ * adb_last_error() gives the message. Nothing here throws, exits or falls back to
+ * the CPU.
+ *
+ * Layout conventions inside the library:
+ *   - "act" tensors are bf16 NHWC: [n, h, w, c], c contiguous (pixels are GEMM rows).
+ *   - weights for the implicit GEMM are bf16 [cout_pad, ktot], K contiguous, where
+ *     K runs over (segment, tap=kh*3+kw, cin) in that order.
+ *   - API-edge tensors (x_t, eps, samples) are fp32 NCHW exactly as the reference's.
+ *
+ * Every op takes `adb_plan* plan` first: NULL executes immediately on `stream`;
+ * non-NULL records the op (with its TMA descriptors encoded once) for adb_plan_run.
+ *
+ * Each entry point cites the reference interface it replaces
+ * (paths relative to /root/reference/examples/guided_diffusion/).
+ */
+#ifndef ADB200_H
+#define ADB200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* adb_stream;          /* cudaStream_t */
+typedef struct adb_plan adb_plan;  /* opaque recorded op list */
+
+enum adb_status {
+  ADB_OK = 0,
+  ADB_ERR_INVALID = -1,     /* bad argument / unsupported shape */
+  ADB_ERR_CUDA = -2,        /* CUDA runtime / driver error */
+  ADB_ERR_UNSUPPORTED = -3  /* device is not sm_100 */
+};
+
+const char* adb_last_error(void);
+int adb_version(void);
+/* 0 if the current device can run this library (compute capability 10.x). */
+int adb_device_check(void);
+
+/* ---- plans: recorded launch schedules (guided_diffusion/dynamic_unet.py:673-702 is
+ * walked once per (batch, skip-mask); skipped blocks never enter the list) ---- */
+adb_plan* adb_plan_create(void);
+void adb_plan_destroy(adb_plan* plan);
+int adb_plan_num_ops(const adb_plan* plan);
+/* launches every recorded op in order on `stream`; returns #kernels launched (>=0) or <0 */
+int adb_plan_run(adb_plan* plan, adb_stream stream);
+
+/* ---- implicit-GEMM convolution / k=1 GEMM on tcgen05+TMEM, operands by TMA ----
+ * replaces nn.Conv2d 3x3 s1 p1, nn.Conv2d 1x1 and nn.Conv1d k=1
+ * (guided_diffusion/nn.py:22-32 via dynamic_unet.py:194,220,231,303,311,502,653).
+ * out[m, co] = bias[co] + sum_seg sum_tap sum_ci act_seg[n, h+dh, w+dw, ci] * W[co, k]
+ *              (+ residual), zero padding, m = (n*h + y)*w + x.
+ * Up to three K-segments let the ResBlock's second conv absorb the 1x1 skip
+ * connection over the (never materialised) channel concat (dynamic_unet.py:271,699). */
+enum { ADB_RES_NONE = 0, ADB_RES_SAME = 1, ADB_RES_AVGPOOL2 = 2, ADB_RES_NEAREST2 = 3 };
+enum { ADB_OUT_BF16_NHWC = 0, ADB_OUT_F32_NCHW = 1 };
+
+typedef struct {
+  const void* act;  /* bf16 NHWC [n, h, w, cin] */
+  int cin;          /* multiple of 8 */
+  int taps;         /* 1 (1x1) or 9 (3x3, pad 1) */
+} adb_conv_seg;
+
+typedef struct {
+  int n, h, w;          /* output geometry, h and w powers of two */
+  int cout;             /* real output channels */
+  int cout_pad;         /* rows of `weight`: cout rounded up to adb_conv_block_n(cout), zero rows */
+  int nseg;             /* 1..3 */
+  adb_conv_seg seg[3];
+  const void* weight;   /* bf16 [cout_pad, ktot] */
+  const float* bias;    /* fp32 [cout] or NULL */
+  const void* residual; /* bf16 NHWC, geometry per res_mode, cout channels; or NULL */
+  int res_mode;
+  void* out;
+  int out_mode;
+} adb_conv_desc;
+
+/* N tile the kernel uses for `cout` output channels; `cout_pad` must be a multiple of it. */
+int adb_conv_block_n(int cout);
+int adb_conv_igemm(adb_plan* plan, const adb_conv_desc* d, adb_stream stream);
+
+/* ---- fused softmax attention, head dim 64 ----
+ * replaces QKVAttention.forward / QKVAttentionLegacy.forward
+ * (dynamic_unet.py:390-409 / 357-374): softmax_fp32((q*s)^T (k*s)) v, s = 64^-1/4.
+ * qkv: bf16 [b*t, 3*heads*64] (the k=1 conv output, pixels as rows)
+ * out: bf16 [b*t, heads*64]
+ * legacy_order = 0: channels [q(all heads) | k | v]; 1: per head [q k v]. */
+int adb_attention(adb_plan* plan, const void* qkv, void* out, int b, int t, int heads,
+                  int legacy_order, adb_stream stream);
+
+/* ---- GroupNorm(32) (+scale-shift) (+SiLU) (+2x resample) ----
+ * replaces GroupNorm32.forward + nn.SiLU + the FiLM line + Upsample/Downsample on h
+ * (nn.py:17-19, dynamic_unet.py:192-193,216-217,253-254,262-265,302,651-652).
+ * The input may be the channel concat of two NHWC tensors (dynamic_unet.py:699). */
+enum { ADB_RESAMPLE_NONE = 0, ADB_RESAMPLE_AVGPOOL2 = 1, ADB_RESAMPLE_NEAREST2 = 2 };
+
+typedef struct {
+  int n, h, w;              /* input geometry */
+  const void* src0; int c0; /* bf16 NHWC */
+  const void* src1; int c1; /* optional second source (channel concat), c1 = 0 if none */
+  const float* gamma;       /* [c0+c1] */
+  const float* beta;        /* [c0+c1] */
+  float eps;
+  const float* scale_shift; /* optional fp32 rows: scale = row[0:c], shift = row[c:2c] */
+  int ss_stride;            /* floats between consecutive samples' rows */
+  int silu;
+  int resample;
+  void* out;                /* bf16 NHWC at the resampled geometry, c0+c1 channels */
+  double* stats;            /* workspace [n, 32, 2] doubles, zeroed by the call itself */
+} adb_gn_desc;
+
+int adb_groupnorm(adb_plan* plan, const adb_gn_desc* d, adb_stream stream);
+
+/* 2x average pool / nearest upsample of a bf16 NHWC tensor
+ * (x_upd of a *skipped* up/down ResBlock, dynamic_unet.py:246-249). */
+int adb_resample2x(adb_plan* plan, const void* src, void* dst, int n, int h, int w, int c,
+                   int mode, adb_stream stream);
+
+/* ---- input stem: fp32 NCHW [n,cin,h,w] -> conv3x3 -> bf16 NHWC [n,h,w,cout]
+ * (input_blocks.0.0, dynamic_unet.py:501-503, with x.type(dtype) at :693).
+ * weight fp32 [cout, cin, 3, 3] (PyTorch layout), bias fp32 [cout]; cin <= 4. */
+int adb_stem_conv(adb_plan* plan, const float* x, const float* weight, const float* bias,
+                  void* out, int n, int cin, int h, int w, int cout, adb_stream stream);
+
+/* ---- timestep / label embedding path (nn.py:103-121, dynamic_unet.py:490-498,687-691)
+ * sinusoid: out[b, :] = [cos(t_b f_k) | sin(t_b f_k)], f_k = exp(-ln(1e4) k / (dim/2)) */
+int adb_timestep_embedding(adb_plan* plan, const int64_t* t, float* out, int b, int dim,
+                           adb_stream stream);
+/* out[b, j] = bias[j] + sum_k act(x[b,k]) W[j,k] (+ table[idx[b], j]);
+ * act = SiLU if silu_in else identity. fp32 throughout (the reference keeps these fp32,
+ * fp16_util.py:15-22). Covers time_embed.{0,2}, label_emb add and all ResBlock
+ * emb_layers batched into one [b,768]x[768, sum 2*cout] product. */
+int adb_linear(adb_plan* plan, const float* x, const float* w, const float* bias, float* out,
+               int b, int k, int nout, int silu_in, const float* table, const int64_t* idx,
+               adb_stream stream);
+
+/* ---- fused guidance + DDIM update (gaussian_diffusion.py:328-349,371-393,536-584)
+ * coef = {sqrt_recip_acp, sqrt_recipm1_acp, sqrt(1-acp), sqrt(acp_prev), sqrt(1-acp_prev)}
+ * (fp32, as the reference rounds them at gather, :920). eps is read from the first 3 of
+ * eps_channels channels of model_out. grad may be NULL (no cond_fn). eta = 0 only. */
+int adb_ddim_step(adb_plan* plan, const float* x, const float* model_out, int eps_channels,
+                  const float* grad, float* x_prev, float* pred_xstart /* may be NULL */,
+                  int n, int c, int hw, const float coef[5], int clip_denoised,
+                  adb_stream stream);
+
+/* ((s+1)*127.5).clamp(0,255).to(uint8) NCHW -> NHWC
+ * (search_dynamic_unet_imagenet64_classifier_guidance_progressive.py:421-423). */
+int adb_pack_uint8(adb_plan* plan, const float* sample, uint8_t* out, int n, int c, int hw,
+                   adb_stream stream);
+
+/* ---- FID moments (evaluations/evaluator_v1.py:218-221): accumulates
+ * sum_x[d] += sum_i f[i,d], sum_xx[d,e] += sum_i f[i,d] f[i,e] in fp64. */
+int adb_moments_accumulate(adb_plan* plan, const float* feats, int n, int d, double* sum_x,
+                           double* sum_xx, adb_stream stream);
+
+/* zero `bytes` bytes at `ptr` (recorded memset node) */
+int adb_memset0(adb_plan* plan, void* ptr, size_t bytes, adb_stream stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ADB200_H */

@@ -1,0 +1,246 @@
+"""Gaussian diffusion tables and the DDIM sampling loop, B200 edition.
+
+Mirrors the sampling half of guided_diffusion/gaussian_diffusion.py (reference lines cited
+per function). The float64 coefficient tables are built exactly as the reference builds
+them (betas -> cumprod -> derived arrays, :118-169) and stay numpy attributes that callers
+may mutate in place (`reset_diffusion`, …progressive.py:219-274). What changes is the step:
+the ~25 elementwise torch ops and ~8 host->device table uploads per step of
+p_mean_variance + condition_score + ddim_sample collapse into ONE fused CUDA kernel
+(`adb_ddim_step`) fed five fp32 scalars.
+
+Out of scope: training losses, NLL/bpd, ancestral p_sample, DDIM
+reverse; they raise NotImplementedError rather than silently doing something else.
+"""
+from __future__ import annotations
+
+import enum
+import math
+from typing import Sequence
+
+import numpy as np
+import torch as th
+
+from . import ops
+
+
+def get_named_beta_schedule(schedule_name, num_diffusion_timesteps):
+    """gaussian_diffusion.py:18-42."""
+    if schedule_name == "linear":
+        scale = 1000 / num_diffusion_timesteps
+        return np.linspace(scale * 0.0001, scale * 0.02, num_diffusion_timesteps, dtype=np.float64)
+    elif schedule_name == "cosine":
+        return betas_for_alpha_bar(
+            num_diffusion_timesteps,
+            lambda t: math.cos((t + 0.008) / 1.008 * math.pi / 2) ** 2,
+        )
+    raise NotImplementedError(f"unknown beta schedule: {schedule_name}")
+
+
+def betas_for_alpha_bar(num_diffusion_timesteps, alpha_bar, max_beta=0.999):
+    """gaussian_diffusion.py:45-62."""
+    betas = []
+    for i in range(num_diffusion_timesteps):
+        t1 = i / num_diffusion_timesteps
+        t2 = (i + 1) / num_diffusion_timesteps
+        betas.append(min(1 - alpha_bar(t2) / alpha_bar(t1), max_beta))
+    return np.array(betas)
+
+
+class ModelMeanType(enum.Enum):
+    PREVIOUS_X = enum.auto()
+    START_X = enum.auto()
+    EPSILON = enum.auto()
+
+
+class ModelVarType(enum.Enum):
+    LEARNED = enum.auto()
+    FIXED_SMALL = enum.auto()
+    FIXED_LARGE = enum.auto()
+    LEARNED_RANGE = enum.auto()
+
+
+class LossType(enum.Enum):
+    MSE = enum.auto()
+    RESCALED_MSE = enum.auto()
+    KL = enum.auto()
+    RESCALED_KL = enum.auto()
+
+    def is_vb(self):
+        return self == LossType.KL or self == LossType.RESCALED_KL
+
+
+def ddim_coefficients(tables, i: int, eta: float = 0.0) -> Sequence[float]:
+    """The five fp32 scalars of DDIM step `i`, rounded the way the reference rounds them.
+
+    `_extract_into_tensor` (:910-923) gathers the float64 table entry and casts it to fp32;
+    `(1 - alpha_bar).sqrt()` (:384), `th.sqrt(alpha_bar_prev)` and
+    `th.sqrt(1 - alpha_bar_prev - sigma**2)` (:577-578) are then fp32 ops on those casts.
+    `tables` is a diffusion object or a dict of the numpy arrays.
+    """
+    get = (lambda k: tables[k]) if isinstance(tables, dict) else (lambda k: getattr(tables, k))
+    if eta != 0.0:
+        raise NotImplementedError("adb_ddim_step implements the deterministic DDIM update (eta = 0)")
+    f32 = np.float32
+    one = f32(1.0)
+    a = f32(get("sqrt_recip_alphas_cumprod")[i])
+    bm = f32(get("sqrt_recipm1_alphas_cumprod")[i])
+    ab = f32(get("alphas_cumprod")[i])
+    abp = f32(get("alphas_cumprod_prev")[i])
+    sigma = f32(0.0)
+    return [float(a), float(bm), float(np.sqrt(one - ab)), float(np.sqrt(abp)),
+            float(np.sqrt(one - abp - sigma * sigma))]
+
+
+class GaussianDiffusion:
+    """Sampling-side twin of the reference class (gaussian_diffusion.py:101-169)."""
+
+    def __init__(self, *, betas, model_mean_type, model_var_type, loss_type, rescale_timesteps=False):
+        self.model_mean_type = model_mean_type
+        self.model_var_type = model_var_type
+        self.loss_type = loss_type
+        self.rescale_timesteps = rescale_timesteps
+
+        betas = np.array(betas, dtype=np.float64)
+        self.betas = betas
+        assert len(betas.shape) == 1, "betas must be 1-D"
+        assert (betas > 0).all() and (betas <= 1).all()
+        self.num_timesteps = int(betas.shape[0])
+
+        alphas = 1.0 - betas
+        self.alphas_cumprod = np.cumprod(alphas, axis=0)
+        self.alphas_cumprod_prev = np.append(1.0, self.alphas_cumprod[:-1])
+        self.alphas_cumprod_next = np.append(self.alphas_cumprod[1:], 0.0)
+        assert self.alphas_cumprod_prev.shape == (self.num_timesteps,)
+
+        self.sqrt_alphas_cumprod = np.sqrt(self.alphas_cumprod)
+        self.sqrt_one_minus_alphas_cumprod = np.sqrt(1.0 - self.alphas_cumprod)
+        self.log_one_minus_alphas_cumprod = np.log(1.0 - self.alphas_cumprod)
+        self.sqrt_recip_alphas_cumprod = np.sqrt(1.0 / self.alphas_cumprod)
+        self.sqrt_recipm1_alphas_cumprod = np.sqrt(1.0 / self.alphas_cumprod - 1)
+
+        self.posterior_variance = betas * (1.0 - self.alphas_cumprod_prev) / (1.0 - self.alphas_cumprod)
+        # the reference indexes posterior_variance[1] unconditionally (:159-161) and so cannot
+        # build a 1-step process; callers' reset_diffusion special-cases it (…progressive.py:261-266)
+        if len(self.posterior_variance) > 1:
+            self.posterior_log_variance_clipped = np.log(
+                np.append(self.posterior_variance[1], self.posterior_variance[1:])
+            )
+        else:
+            self.posterior_log_variance_clipped = self.posterior_variance
+        self.posterior_mean_coef1 = betas * np.sqrt(self.alphas_cumprod_prev) / (1.0 - self.alphas_cumprod)
+        self.posterior_mean_coef2 = (
+            (1.0 - self.alphas_cumprod_prev) * np.sqrt(alphas) / (1.0 - self.alphas_cumprod)
+        )
+
+    # ---- hooks SpacedDiffusion overrides ----
+    def _wrap_model(self, model):
+        return model
+
+    def _timestep_for_model(self, i: int):
+        """Value the model / cond_fn receive for step index i (int, or float if rescaled)."""
+        if self.rescale_timesteps:
+            return float(i) * (1000.0 / self.num_timesteps)
+        return int(i)
+
+    def _scale_timesteps(self, t):
+        if self.rescale_timesteps:
+            return t.float() * (1000.0 / self.num_timesteps)
+        return t
+
+    # ---- DDIM ----
+    def _check_ddim_supported(self, denoised_fn, eta):
+        if self.model_mean_type != ModelMeanType.EPSILON:
+            raise NotImplementedError("the fused DDIM step covers epsilon-prediction models (all reference configs)")
+        if denoised_fn is not None:
+            raise NotImplementedError("denoised_fn is not supported by the fused DDIM step")
+        if eta != 0.0:
+            raise NotImplementedError("the fused DDIM step is deterministic (eta = 0), as every reference script uses it")
+
+    def ddim_sample(self, model, x, t, clip_denoised=True, denoised_fn=None, cond_fn=None,
+                    model_kwargs=None, eta=0.0):
+        """One DDIM step x_t -> x_{t-1} (gaussian_diffusion.py:536-584 with :232-326 and :371-393).
+
+        `t` is the [B] tensor of step indices (all equal, as the loop builds it, :703). The model and
+        cond_fn are called with the mapped original timesteps exactly as _WrappedModel does
+        (respace.py:122-127); everything after them is one kernel.
+        """
+        self._check_ddim_supported(denoised_fn, eta)
+        if model_kwargs is None:
+            model_kwargs = {}
+        B, C = x.shape[:2]
+        assert t.shape == (B,)
+        i = int(t[0])
+        return self._ddim_step_index(model, x, t, i, clip_denoised, cond_fn, model_kwargs)
+
+    def _ddim_step_index(self, model, x, t, i, clip_denoised, cond_fn, model_kwargs):
+        B, C = x.shape[:2]
+        wrapped = self._wrap_model(model)
+        model_output = wrapped(x, self._scale_timesteps(t), **model_kwargs)
+        if self.model_var_type in (ModelVarType.LEARNED, ModelVarType.LEARNED_RANGE):
+            assert model_output.shape == (B, C * 2, *x.shape[2:])
+        else:
+            assert model_output.shape == x.shape
+        grad = None
+        if cond_fn is not None:
+            grad = self._wrap_model(cond_fn)(x, self._scale_timesteps(t), **model_kwargs)
+            grad = grad.float().contiguous()
+        model_output = model_output.float().contiguous()
+        x = x.float().contiguous()
+        pred_xstart = th.empty_like(x)
+        sample = ops.ddim_step(x, model_output, grad, ddim_coefficients(self, i), clip_denoised,
+                               pred_xstart=pred_xstart)
+        return {"sample": sample, "pred_xstart": pred_xstart}
+
+    def ddim_sample_loop(self, model, shape, noise=None, clip_denoised=True, denoised_fn=None, cond_fn=None,
+                         model_kwargs=None, device=None, progress=False, eta=0.0, return_all_images=False):
+        """gaussian_diffusion.py:624-662."""
+        final = None
+        all_images = []
+        for sample in self.ddim_sample_loop_progressive(
+            model, shape, noise=noise, clip_denoised=clip_denoised, denoised_fn=denoised_fn, cond_fn=cond_fn,
+            model_kwargs=model_kwargs, device=device, progress=progress, eta=eta,
+        ):
+            final = sample
+            if return_all_images:
+                all_images.append(final["sample"])
+        if return_all_images:
+            return all_images
+        return final["sample"]
+
+    def ddim_sample_loop_progressive(self, model, shape, noise=None, clip_denoised=True, denoised_fn=None,
+                                     cond_fn=None, model_kwargs=None, device=None, progress=False, eta=0.0):
+        """gaussian_diffusion.py:664-716 (including the reference-specific initial yield, :698-700)."""
+        self._check_ddim_supported(denoised_fn, eta)
+        if device is None:
+            device = next(model.parameters()).device
+        assert isinstance(shape, (tuple, list))
+        if noise is not None:
+            img = noise
+        else:
+            img = th.randn(*shape, device=device)
+        if not img.is_cuda:
+            raise RuntimeError("ddim_sample_loop: tensors must be on a CUDA device (no CPU path)")
+        indices = list(range(self.num_timesteps))[::-1]
+        if progress:
+            from tqdm.auto import tqdm
+
+            indices = tqdm(indices)
+        if model_kwargs is None:
+            model_kwargs = {}
+        yield {"sample": img}
+        for i in indices:
+            t = th.full((shape[0],), i, device=device, dtype=th.long)
+            with th.no_grad():
+                out = self._ddim_step_index(model, img, t, i, clip_denoised, cond_fn, model_kwargs)
+                # the reference draws (and, with eta = 0, discards) th.randn_like(x) every step
+                # (:575); keep the caller's RNG stream in the same place
+                th.randn_like(img)
+                yield out
+                img = out["sample"]
+
+    # ---- not part of the evaluator path ----
+    def p_sample_loop(self, *a, **k):
+        raise NotImplementedError("ancestral sampling is outside the evaluator hot path (use_ddim=True)")
+
+    def training_losses(self, *a, **k):
+        raise NotImplementedError("training is outside the evaluator hot path")

@@ -210,7 +210,13 @@ def groupnorm(
     d.gamma = _dev(gamma, "gamma", torch.float32)
     d.beta = _dev(beta, "beta", torch.float32)
     d.eps = eps
-    d.scale_shift = _opt(scale_shift, "scale_shift", torch.float32)
+    ss_base = None
+    if isinstance(scale_shift, tuple):  # (base tensor, element offset of this block's columns)
+        ss_base, ss_off = scale_shift
+        d.scale_shift = _dev(ss_base, "scale_shift", torch.float32) + 4 * int(ss_off)
+    else:
+        d.scale_shift = _opt(scale_shift, "scale_shift", torch.float32)
+        ss_base = scale_shift
     d.ss_stride = ss_stride
     d.silu = int(bool(silu))
     d.resample = resample
@@ -218,7 +224,7 @@ def groupnorm(
     d.stats = _dev(stats, "stats", torch.float64)
     _lib.check(_lib.lib().adb_groupnorm(_ph(plan), C.byref(d), _stream()), "adb_groupnorm")
     if plan is not None:
-        plan.keep(src0, src1, gamma, beta, scale_shift, out, stats)
+        plan.keep(src0, src1, gamma, beta, ss_base, out, stats)
     return out
 
 

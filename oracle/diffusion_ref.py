@@ -65,6 +65,16 @@ def respace(base_alphas_cumprod: np.ndarray, use_timesteps) -> (List[int], np.nd
     return tmap, np.array(new_betas, dtype=np.float64)
 
 
+def base_tables(schedule: str = "cosine", steps: int = 1000) -> Dict[str, np.ndarray]:
+    """create_gaussian_diffusion (script_util.py:415-453): the "base" process is itself a
+    SpacedDiffusion over ALL steps, so its betas are re-derived from the cumprod (respace.py:76-84)
+    and differ from the named schedule by an ulp here and there. Callers' reset_diffusion reads
+    base_diffusion.alphas_cumprod of THAT object (…progressive.py:227)."""
+    first = diffusion_tables(get_named_beta_schedule(schedule, steps))
+    _, nb = respace(first["alphas_cumprod"], range(steps))
+    return diffusion_tables(nb)
+
+
 def _extract(arr: np.ndarray, t: torch.Tensor, shape) -> torch.Tensor:
     """_extract_into_tensor (:910-923): float64 table -> gather -> .float()."""
     res = torch.from_numpy(arr).to(t.device)[t].float()

@@ -243,8 +243,7 @@ def test_ddim_step_bit_exact(with_grad, clip):
     ops = _ops()
     from autodiffusion_b200.gaussian_diffusion import ddim_coefficients
 
-    betas = diffusion_ref.get_named_beta_schedule("cosine", 1000)
-    base = diffusion_ref.diffusion_tables(betas)
+    base = diffusion_ref.base_tables("cosine", 1000)
     tmap, nb = diffusion_ref.respace(base["alphas_cumprod"], [153, 424, 926, 690])
     tables = diffusion_ref.diffusion_tables(nb)
     n = 4

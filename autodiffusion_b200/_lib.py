@@ -145,7 +145,7 @@ SYMBOLS = {
     "adb_groupnorm": (_I, [_P, C.POINTER(GnDesc), _P]),
     "adb_resample2x": (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _P]),
     "adb_stem_conv": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P]),
-    "adb_timestep_embedding": (_I, [_P, _P, _P, _I, _I, _P]),
+    "adb_timestep_embedding": (_I, [_P, _P, _P, _P, _I, _I, _P]),
     "adb_linear": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _P, _P, _P]),
     "adb_ddim_step": (_I, [_P, _P, _P, _I, _P, _P, _P, _I, _I, _I, C.POINTER(C.c_float), _I, _P]),
     "adb_pack_uint8": (_I, [_P, _P, _P, _I, _I, _I, _P]),

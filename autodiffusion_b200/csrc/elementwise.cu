@@ -67,17 +67,19 @@ __global__ void __launch_bounds__(256) stem_conv_kernel(const float* __restrict_
 }
 
 // ------------------------------------------------------------------------------------
-// timestep_embedding (guided_diffusion/nn.py:103-121), fp32 exactly as written there:
-// freqs = exp(-ln(max_period) * k / half); args = t * freqs; [cos | sin]
+// timestep_embedding (guided_diffusion/nn.py:103-121), fp32 as written there:
+// args = t * freqs; out = [cos(args) | sin(args)]
 // ------------------------------------------------------------------------------------
-__global__ void timestep_embedding_kernel(const int64_t* __restrict__ t, float* __restrict__ out, int b,
-                                          int dim) {
+__global__ void timestep_embedding_kernel(const int64_t* __restrict__ t, const float* __restrict__ freqs,
+                                          float* __restrict__ out, int b, int dim) {
   const int half = dim / 2;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= b * half) return;
   const int row = i / half, k = i - row * half;
-  const float freq = expf(-9.210340371976184f * (float)k / (float)half);  // ln(10000)
-  const float arg = (float)t[row] * freq;
+  // freqs[k] = exp(-ln(max_period) * k / half) is a per-model constant table built once on the
+  // host: |t * f| reaches ~1e3, so a 1-ulp difference between exp implementations would move
+  // sin/cos by ~1e-4; taking the table as an input keeps this kernel a pure function of it.
+  const float arg = __fmul_rn((float)t[row], freqs[k]);
   out[(size_t)row * dim + k] = cosf(arg);
   out[(size_t)row * dim + half + k] = sinf(arg);
   if ((dim & 1) && k == 0) out[(size_t)row * dim + dim - 1] = 0.f;
@@ -251,12 +253,12 @@ int stem_conv_submit(adb_plan* plan, const float* x, const float* weight, const 
   });
 }
 
-int timestep_embedding_submit(adb_plan* plan, const int64_t* t, float* out, int b, int dim,
-                              cudaStream_t stream) {
-  ADB_REQUIRE(t && out && b > 0 && dim >= 2, "timestep_embedding: bad arguments");
+int timestep_embedding_submit(adb_plan* plan, const int64_t* t, const float* freqs, float* out, int b,
+                              int dim, cudaStream_t stream) {
+  ADB_REQUIRE(t && freqs && out && b > 0 && dim >= 2, "timestep_embedding: bad arguments");
   return submit(plan, stream, [=](cudaStream_t s) -> int {
     const int total = b * (dim / 2);
-    timestep_embedding_kernel<<<(total + 127) / 128, 128, 0, s>>>(t, out, b, dim);
+    timestep_embedding_kernel<<<(total + 127) / 128, 128, 0, s>>>(t, freqs, out, b, dim);
     ADB_CUDA(cudaGetLastError());
     return 1;
   });

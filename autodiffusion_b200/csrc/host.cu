@@ -101,7 +101,7 @@ int groupnorm_submit(adb_plan*, const adb_gn_desc*, cudaStream_t);
 int resample2x_submit(adb_plan*, const void*, void*, int, int, int, int, int, cudaStream_t);
 int stem_conv_submit(adb_plan*, const float*, const float*, const float*, void*, int, int, int, int,
                      int, cudaStream_t);
-int timestep_embedding_submit(adb_plan*, const int64_t*, float*, int, int, cudaStream_t);
+int timestep_embedding_submit(adb_plan*, const int64_t*, const float*, float*, int, int, cudaStream_t);
 int linear_submit(adb_plan*, const float*, const float*, const float*, float*, int, int, int, int,
                   const float*, const int64_t*, cudaStream_t);
 int ddim_step_submit(adb_plan*, const float*, const float*, int, const float*, float*, float*, int,
@@ -175,9 +175,9 @@ int adb_stem_conv(adb_plan* plan, const float* x, const float* weight, const flo
                           static_cast<cudaStream_t>(stream));
 }
 
-int adb_timestep_embedding(adb_plan* plan, const int64_t* t, float* out, int b, int dim,
-                           adb_stream stream) {
-  return timestep_embedding_submit(plan, t, out, b, dim, static_cast<cudaStream_t>(stream));
+int adb_timestep_embedding(adb_plan* plan, const int64_t* t, const float* freqs, float* out, int b,
+                           int dim, adb_stream stream) {
+  return timestep_embedding_submit(plan, t, freqs, out, b, dim, static_cast<cudaStream_t>(stream));
 }
 
 int adb_linear(adb_plan* plan, const float* x, const float* w, const float* bias, float* out, int b,

@@ -53,6 +53,9 @@ class _Seq(_Holder):
         for i, m in children.items():
             self.add_module(str(i), m)
 
+    def __getitem__(self, i: int) -> nn.Module:
+        return getattr(self, str(i))
+
 
 class ResBlock(_Holder):
     """Parameters of dynamic_unet.py ResBlock (:150-231), created in the reference's order."""

@@ -11,6 +11,7 @@ launching it.
 from __future__ import annotations
 
 import ctypes as C
+import math
 from typing import Optional, Sequence
 
 import torch
@@ -262,18 +263,33 @@ def stem_conv(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor
     return out
 
 
+_FREQS = {}
+
+
+def timestep_freqs(dim: int, device, max_period: int = 10000) -> torch.Tensor:
+    """The constant table of nn.py:112-114, evaluated once on the host with the reference's own
+    expression (fp32) so that t * freqs is bit-identical to the reference's `args`."""
+    key = (dim, str(device), max_period)
+    if key not in _FREQS:
+        half = dim // 2
+        f = torch.exp(-math.log(max_period) * torch.arange(start=0, end=half, dtype=torch.float32) / half)
+        _FREQS[key] = f.to(device)
+    return _FREQS[key]
+
+
 def timestep_embedding(t: torch.Tensor, dim: int, out: Optional[torch.Tensor] = None,
                        plan: Optional[Plan] = None) -> torch.Tensor:
     b = t.shape[0]
     if out is None:
         out = torch.empty((b, dim), dtype=torch.float32, device=t.device)
+    freqs = timestep_freqs(dim, t.device)
     _lib.check(
-        _lib.lib().adb_timestep_embedding(_ph(plan), _dev(t, "t", torch.int64), _dev(out, "out", torch.float32),
-                                          b, dim, _stream()),
+        _lib.lib().adb_timestep_embedding(_ph(plan), _dev(t, "t", torch.int64), _dev(freqs, "freqs", torch.float32),
+                                          _dev(out, "out", torch.float32), b, dim, _stream()),
         "adb_timestep_embedding",
     )
     if plan is not None:
-        plan.keep(t, out)
+        plan.keep(t, freqs, out)
     return out
 
 

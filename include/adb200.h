@@ -131,9 +131,10 @@ int adb_stem_conv(adb_plan* plan, const float* x, const float* weight, const flo
                   void* out, int n, int cin, int h, int w, int cout, adb_stream stream);
 
 /* ---- timestep / label embedding path (nn.py:103-121, dynamic_unet.py:490-498,687-691)
- * sinusoid: out[b, :] = [cos(t_b f_k) | sin(t_b f_k)], f_k = exp(-ln(1e4) k / (dim/2)) */
-int adb_timestep_embedding(adb_plan* plan, const int64_t* t, float* out, int b, int dim,
-                           adb_stream stream);
+ * sinusoid: out[b, :] = [cos(t_b f_k) | sin(t_b f_k)]; freqs[k] = exp(-ln(1e4) k / (dim/2)) is a
+ * constant fp32 table of dim/2 entries supplied by the host. */
+int adb_timestep_embedding(adb_plan* plan, const int64_t* t, const float* freqs, float* out, int b,
+                           int dim, adb_stream stream);
 /* out[b, j] = bias[j] + sum_k act(x[b,k]) W[j,k] (+ table[idx[b], j]);
  * act = SiLU if silu_in else identity. fp32 throughout (the reference keeps these fp32,
  * fp16_util.py:15-22). Covers time_embed.{0,2}, label_emb add and all ResBlock

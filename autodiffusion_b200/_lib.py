@@ -139,6 +139,8 @@ SYMBOLS = {
     "adb_plan_destroy": (None, [_P]),
     "adb_plan_num_ops": (_I, [_P]),
     "adb_plan_run": (_I, [_P, _P]),
+    "adb_plan_op_info": (_I, [_P, _I, C.POINTER(C.c_char_p), C.POINTER(C.c_double), C.POINTER(C.c_double)]),
+    "adb_plan_run_profiled": (_I, [_P, _P, C.POINTER(C.c_float), _I]),
     "adb_conv_block_n": (_I, [_I]),
     "adb_conv_igemm": (_I, [_P, C.POINTER(ConvDesc), _P]),
     "adb_attention": (_I, [_P, _P, _P, _I, _I, _I, _I, _P]),

@@ -291,7 +291,8 @@ int attention_submit(adb_plan* plan, const void* qkv, void* out, int b, int t, i
   ap.heads = heads;
   ap.C = C;
   ap.legacy = legacy_order ? 1 : 0;
-  return submit(plan, stream, [ap, b, bn](cudaStream_t s) -> int {
+  const double flops = 4.0 * (double)b * heads * (double)t * (double)t * HD;  // QK^T and PV
+  return submit(plan, stream, "attention", flops, 0.0, [ap, b, bn](cudaStream_t s) -> int {
     return bn == 64 ? launch_attn<64>(ap, b, s) : launch_attn<128>(ap, b, s);
   });
 }

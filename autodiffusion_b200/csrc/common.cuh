@@ -41,16 +41,26 @@ using Op = std::function<int(cudaStream_t)>;
 
 }  // namespace adb
 
+// What a recorded op is and how much algorithmic work it does (for roofline accounting):
+// flops = 2*MACs of GEMM-shaped work, bytes = compulsory HBM traffic of memory-bound work.
+struct adb_op_info {
+  const char* kind;
+  double flops;
+  double bytes;
+};
+
 struct adb_plan {
   std::vector<adb::Op> ops;
+  std::vector<adb_op_info> info;
 };
 
 namespace adb {
 
 // run now (plan == nullptr) or record
-inline int submit(adb_plan* plan, cudaStream_t stream, Op op) {
+inline int submit(adb_plan* plan, cudaStream_t stream, const char* kind, double flops, double bytes, Op op) {
   if (plan) {
     plan->ops.push_back(std::move(op));
+    plan->info.push_back(adb_op_info{kind, flops, bytes});
     return ADB_OK;
   }
   int r = op(stream);

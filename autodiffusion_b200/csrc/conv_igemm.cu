@@ -389,7 +389,8 @@ int conv_igemm_submit(adb_plan* plan, const adb_conv_desc* d, cudaStream_t strea
   kp.out = d->out;
   kp.out_mode = d->out_mode;
 
-  return submit(plan, stream, [kp, block_n](cudaStream_t s) -> int {
+  const double flops = 2.0 * (double)M * (double)d->cout * (double)ktot;
+  return submit(plan, stream, "conv_igemm", flops, 0.0, [kp, block_n](cudaStream_t s) -> int {
     switch (block_n) {
       case 192: return launch<192>(kp, s);
       case 128: return launch<128>(kp, s);

@@ -237,7 +237,7 @@ int stem_conv_submit(adb_plan* plan, const float* x, const float* weight, const 
   ADB_REQUIRE(cout > 0 && cout % 8 == 0, "stem_conv: cout %% 8 != 0");
   const size_t smem = ((size_t)9 * cin * cout + cout) * sizeof(float);
   ADB_REQUIRE(smem <= 48 * 1024, "stem_conv: weights do not fit shared memory");
-  return submit(plan, stream, [=](cudaStream_t s) -> int {
+  return submit(plan, stream, "stem_conv", 0.0, 0.0, [=](cudaStream_t s) -> int {
     const int V = cout / 8;
     const int slots = V < 256 ? V : 256;
     const int lanes = 256 / slots;
@@ -256,7 +256,7 @@ int stem_conv_submit(adb_plan* plan, const float* x, const float* weight, const 
 int timestep_embedding_submit(adb_plan* plan, const int64_t* t, const float* freqs, float* out, int b,
                               int dim, cudaStream_t stream) {
   ADB_REQUIRE(t && freqs && out && b > 0 && dim >= 2, "timestep_embedding: bad arguments");
-  return submit(plan, stream, [=](cudaStream_t s) -> int {
+  return submit(plan, stream, "timestep_embedding", 0.0, 0.0, [=](cudaStream_t s) -> int {
     const int total = b * (dim / 2);
     timestep_embedding_kernel<<<(total + 127) / 128, 128, 0, s>>>(t, freqs, out, b, dim);
     ADB_CUDA(cudaGetLastError());
@@ -269,7 +269,7 @@ int linear_submit(adb_plan* plan, const float* x, const float* w, const float* b
                   cudaStream_t stream) {
   ADB_REQUIRE(x && w && out && b > 0 && k > 0 && nout > 0, "linear: bad arguments");
   ADB_REQUIRE((table == nullptr) == (idx == nullptr), "linear: table and idx go together");
-  return submit(plan, stream, [=](cudaStream_t s) -> int {
+  return submit(plan, stream, "linear", 2.0 * b * (double)k * nout, 0.0, [=](cudaStream_t s) -> int {
     dim3 grid((nout + LT_N - 1) / LT_N, (b + LT_M - 1) / LT_M);
     linear_kernel<<<grid, 256, 0, s>>>(x, w, bias, out, b, k, nout, silu_in, table, idx);
     ADB_CUDA(cudaGetLastError());
@@ -284,7 +284,7 @@ int ddim_step_submit(adb_plan* plan, const float* x, const float* model_out, int
   ADB_REQUIRE(n > 0 && c > 0 && hw > 0 && eps_channels >= c, "ddim_step: bad geometry");
   DdimCoef cf;
   for (int i = 0; i < 5; ++i) cf.v[i] = coef[i];
-  return submit(plan, stream, [=](cudaStream_t s) -> int {
+  return submit(plan, stream, "ddim_step", 0.0, 4.0 * (grad ? 4.0 : 3.0) * (double)n * c * hw, [=](cudaStream_t s) -> int {
     const size_t total = (size_t)n * c * hw;
     size_t blocks = (total + 255) / 256;
     const size_t cap = (size_t)num_sms() * 8;
@@ -299,7 +299,7 @@ int ddim_step_submit(adb_plan* plan, const float* x, const float* model_out, int
 int pack_uint8_submit(adb_plan* plan, const float* sample, uint8_t* out, int n, int c, int hw,
                       cudaStream_t stream) {
   ADB_REQUIRE(sample && out && n > 0 && c > 0 && hw > 0, "pack_uint8: bad arguments");
-  return submit(plan, stream, [=](cudaStream_t s) -> int {
+  return submit(plan, stream, "pack_uint8", 0.0, 0.0, [=](cudaStream_t s) -> int {
     const size_t total = (size_t)n * hw;
     size_t blocks = (total + 255) / 256;
     const size_t cap = (size_t)num_sms() * 8;

@@ -293,7 +293,9 @@ int groupnorm_submit(adb_plan* plan, const adb_gn_desc* d, cudaStream_t stream) 
   if (splits < 1) splits = 1;
   p.splits = splits;
 
-  return submit(plan, stream, [p](cudaStream_t s) -> int {
+  const double in_elems = (double)d->n * P * C;
+  const double out_elems = d->resample == ADB_RESAMPLE_AVGPOOL2 ? in_elems / 4 : (d->resample == ADB_RESAMPLE_NEAREST2 ? in_elems * 4 : in_elems);
+  return submit(plan, stream, "groupnorm", 0.0, 2.0 * (in_elems + out_elems), [p](cudaStream_t s) -> int {
     ADB_CUDA(cudaMemsetAsync(p.stats, 0, (size_t)p.n * GN_GROUPS * 2 * sizeof(double), s));
     dim3 grid(p.splits, p.n);
     gn_stats_kernel<<<grid, GN_THREADS, 0, s>>>(p);
@@ -309,7 +311,7 @@ int resample2x_submit(adb_plan* plan, const void* src, void* dst, int n, int h, 
   ADB_REQUIRE(src && dst && n > 0 && h > 0 && w > 0 && c > 0 && c % 8 == 0, "resample2x: bad arguments");
   ADB_REQUIRE(mode == ADB_RESAMPLE_AVGPOOL2 || mode == ADB_RESAMPLE_NEAREST2, "resample2x: bad mode");
   if (mode == ADB_RESAMPLE_AVGPOOL2) ADB_REQUIRE(h % 2 == 0 && w % 2 == 0, "resample2x: avgpool2 needs even h,w");
-  return submit(plan, stream, [=](cudaStream_t s) -> int {
+  return submit(plan, stream, "resample2x", 0.0, 0.0, [=](cudaStream_t s) -> int {
     const size_t out_pix = (mode == ADB_RESAMPLE_AVGPOOL2) ? (size_t)n * (h / 2) * (w / 2) : (size_t)n * h * w * 4;
     const size_t total = out_pix * (c / 8);
     size_t blocks = (total + 255) / 256;

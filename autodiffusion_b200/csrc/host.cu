@@ -149,6 +149,49 @@ int adb_plan_run(adb_plan* plan, adb_stream stream) {
   return launches;
 }
 
+int adb_plan_op_info(const adb_plan* plan, int i, const char** kind, double* flops, double* bytes) {
+  if (!plan || i < 0 || i >= (int)plan->info.size()) {
+    set_error("adb_plan_op_info: index out of range");
+    return ADB_ERR_INVALID;
+  }
+  if (kind) *kind = plan->info[i].kind;
+  if (flops) *flops = plan->info[i].flops;
+  if (bytes) *bytes = plan->info[i].bytes;
+  return ADB_OK;
+}
+
+// Runs the plan with a CUDA event pair around every op (on `stream`, the stream the kernels are
+// launched on) and returns each op's device time in milliseconds. Synchronises the stream.
+int adb_plan_run_profiled(adb_plan* plan, adb_stream stream, float* ms_out, int capacity) {
+  if (!plan || !ms_out || capacity < (int)plan->ops.size()) {
+    set_error("adb_plan_run_profiled: bad arguments");
+    return ADB_ERR_INVALID;
+  }
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const size_t n = plan->ops.size();
+  std::vector<cudaEvent_t> ev(n + 1);
+  for (auto& e : ev) ADB_CUDA(cudaEventCreate(&e));
+  int rc = ADB_OK;
+  ADB_CUDA(cudaEventRecord(ev[0], s));
+  for (size_t i = 0; i < n; ++i) {
+    int r = plan->ops[i](s);
+    if (r < 0) {
+      rc = r;
+      break;
+    }
+    ADB_CUDA(cudaEventRecord(ev[i + 1], s));
+  }
+  if (rc == ADB_OK) {
+    cudaError_t e = cudaStreamSynchronize(s);
+    if (e != cudaSuccess) rc = cuda_fail(e, "cudaStreamSynchronize");
+  }
+  if (rc == ADB_OK) {
+    for (size_t i = 0; i < n; ++i) cudaEventElapsedTime(&ms_out[i], ev[i], ev[i + 1]);
+  }
+  for (auto& e : ev) cudaEventDestroy(e);
+  return rc == ADB_OK ? (int)n : rc;
+}
+
 int adb_conv_block_n(int cout) { return conv_block_n(cout); }
 
 int adb_conv_igemm(adb_plan* plan, const adb_conv_desc* d, adb_stream stream) {
@@ -209,7 +252,7 @@ int adb_memset0(adb_plan* plan, void* ptr, size_t bytes, adb_stream stream) {
     set_error("adb_memset0: null pointer");
     return ADB_ERR_INVALID;
   }
-  return submit(plan, static_cast<cudaStream_t>(stream), [ptr, bytes](cudaStream_t s) -> int {
+  return submit(plan, static_cast<cudaStream_t>(stream), "memset", 0.0, 0.0, [ptr, bytes](cudaStream_t s) -> int {
     ADB_CUDA(cudaMemsetAsync(ptr, 0, bytes, s));
     return 1;
   });

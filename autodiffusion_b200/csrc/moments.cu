@@ -87,7 +87,7 @@ __global__ void __launch_bounds__(256) moments_kernel(const float* __restrict__ 
 int moments_submit(adb_plan* plan, const float* feats, int n, int d, double* sum_x, double* sum_xx,
                    cudaStream_t stream) {
   ADB_REQUIRE(feats && sum_x && sum_xx && n > 0 && d > 0, "moments_accumulate: bad arguments");
-  return submit(plan, stream, [=](cudaStream_t s) -> int {
+  return submit(plan, stream, "moments", 2.0 * n * (double)d * d, 0.0, [=](cudaStream_t s) -> int {
     const int tiles = (d + MT - 1) / MT;
     const int blocks = tiles * (tiles + 1) / 2;
     moments_kernel<<<blocks, 256, 0, s>>>(feats, n, d, sum_x, sum_xx);

@@ -180,6 +180,14 @@ class _PackedAttn:
     bproj: th.Tensor
 
 
+@dataclass
+class _IO:
+    x_in: th.Tensor
+    t_in: th.Tensor
+    y_in: Optional[th.Tensor]
+    out: th.Tensor
+
+
 class _UNetPlan:
     """One recorded + graph-captured forward for a fixed (batch, H, W, skip set)."""
 
@@ -193,7 +201,7 @@ class _UNetPlan:
         self.plan = ops.Plan()
         self.graph: Optional[th.cuda.CUDAGraph] = None
         self.launches = 0
-        model._record(self, B, H, W, set(skip))
+        model.record_forward(self.plan, self.x_in, self.t_in, self.y_in, self.out, skip)
 
     def finalize(self, use_graph: bool):
         # first run outside capture: sets kernel attributes, validates the schedule
@@ -436,11 +444,22 @@ class Dynamic_UNetModel(nn.Module):
         return cache[key]
 
     # ---- recording: the reference's forward walked once, skipped blocks elided ----
-    def _record(self, up: _UNetPlan, B: int, H: int, W: int, skip: set):
+    def record_forward(self, plan: ops.Plan, x_in: th.Tensor, t_in: th.Tensor, y_in: Optional[th.Tensor],
+                       out: th.Tensor, skip_layer: Sequence[int] = ()):
+        """Record one forward (x_in fp32 NCHW, t_in int64 [B], y_in int64 [B] or None -> out fp32 NCHW)
+        into `plan`. Several forwards — e.g. every step of a searched schedule, each with its own
+        skip set — may be recorded into the same plan; they share this model's activation pool."""
+        if self._device().type != "cuda":
+            raise RuntimeError("Dynamic_UNetModel runs on a CUDA device only: move it with .to('cuda') "
+                               "(autodiffusion_b200 has no CPU path)")
+        if self._packed_generation != self._generation:
+            self._pack()
+        B, _, H, W = x_in.shape
+        skip = set(int(s) for s in skip_layer)
         if self._pool is None or self._pool.device != self._device():
             self._pool = _Pool(self._device())
         P = self._packed
-        plan = up.plan
+        up = _IO(x_in, t_in, y_in, out)
         ctx = _Ctx(self._pool, plan)
         dev = self._device()
         mc, ted = self.model_channels, self.model_channels * 4

@@ -80,6 +80,22 @@ class Plan:
         self.launches_per_run = n
         return n
 
+    def op_info(self):
+        """[(kind, flops, bytes)] per recorded op."""
+        out = []
+        kind, fl, by = C.c_char_p(), C.c_double(), C.c_double()
+        for i in range(self.num_ops()):
+            _lib.check(self._lib.adb_plan_op_info(self._h, i, C.byref(kind), C.byref(fl), C.byref(by)), "adb_plan_op_info")
+            out.append((kind.value.decode(), fl.value, by.value))
+        return out
+
+    def run_profiled(self):
+        """Run with CUDA events around every op; returns per-op milliseconds (syncs the stream)."""
+        n = self.num_ops()
+        ms = (C.c_float * n)()
+        _lib.check(self._lib.adb_plan_run_profiled(self._h, _stream(), ms, n), "adb_plan_run_profiled")
+        return list(ms)
+
     def __del__(self):
         h, self._h = getattr(self, "_h", None), None
         if h:

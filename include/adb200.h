@@ -52,6 +52,12 @@ void adb_plan_destroy(adb_plan* plan);
 int adb_plan_num_ops(const adb_plan* plan);
 /* launches every recorded op in order on `stream`; returns #kernels launched (>=0) or <0 */
 int adb_plan_run(adb_plan* plan, adb_stream stream);
+/* what op i is ("conv_igemm", "groupnorm", ...) and its algorithmic work: flops = 2*MACs of
+ * GEMM-shaped work, bytes = compulsory HBM bytes of memory-bound work (roofline numerators) */
+int adb_plan_op_info(const adb_plan* plan, int i, const char** kind, double* flops, double* bytes);
+/* like adb_plan_run, with a CUDA event pair around each op on `stream`; writes per-op device
+ * milliseconds to ms_out[0..num_ops) and synchronises the stream. Returns num_ops or <0. */
+int adb_plan_run_profiled(adb_plan* plan, adb_stream stream, float* ms_out, int capacity);
 
 /* ---- implicit-GEMM convolution / k=1 GEMM on tcgen05+TMEM, operands by TMA ----
  * replaces nn.Conv2d 3x3 s1 p1, nn.Conv2d 1x1 and nn.Conv1d k=1

@@ -100,6 +100,7 @@ class ConvDesc(C.Structure):
         ("res_mode", C.c_int),
         ("out", C.c_void_p),
         ("out_mode", C.c_int),
+        ("stats_out", C.c_void_p),
     ]
 
 
@@ -121,6 +122,7 @@ class GnDesc(C.Structure):
         ("resample", C.c_int),
         ("out", C.c_void_p),
         ("stats", C.c_void_p),
+        ("stats_ready", C.c_int),
     ]
 
 

@@ -10,7 +10,7 @@
 //               and columns are zero-filled by the TMA unit = the conv's zero padding.
 //               The B tile is a 2-D box {64, BLOCK_N} of the K-major weight matrix.
 //   warp 1    : allocates TMEM, issues tcgen05.mma (128 x BLOCK_N x 16, bf16 -> fp32).
-//   warps 2-5 : epilogue. tcgen05.ld the accumulator (lane = pixel row), + bias,
+//   warps 2-9 : epilogue (two warps per TMEM lane quarter, half of the columns each). tcgen05.ld the accumulator (lane = pixel row), + bias,
 //               + residual (same / 2x2-avg-pooled / nearest-upsampled source), store.
 // Persistent grid (<= #SM CTAs), static round-robin over tiles with n fastest so CTAs that
 // run concurrently share the A tile in L2; smem ring of STAGES stages; two TMEM accumulator
@@ -27,7 +27,8 @@ constexpr int BLOCK_M = 128;
 constexpr int BLOCK_K = 64;  // bf16 elements = one 128-byte swizzle row
 constexpr int UMMA_K = 16;
 constexpr int A_STAGE_BYTES = BLOCK_M * BLOCK_K * 2;  // 16 KiB
-constexpr int NUM_THREADS = 192;
+constexpr int NUM_THREADS = 320;  // TMA warp, MMA warp, 8 epilogue warps
+constexpr int STAT_BINS = 40;      // >= groups one epilogue warp can touch per tile (96 cols / cpg + 2)
 
 struct ConvKParams {
   CUtensorMap tmA[3];
@@ -45,6 +46,8 @@ struct ConvKParams {
   int res_mode;
   void* out;
   int out_mode;
+  double* stats;  // optional [n][32][2] GroupNorm sums of the output, or nullptr
+  int cpg;        // channels per group = cout / 32
 };
 
 template <int BLOCK_N>
@@ -69,6 +72,7 @@ conv_igemm_kernel(const __grid_constant__ ConvKParams p) {
   // barriers: full[STAGES], empty[STAGES], tmem_full[2], tmem_empty[2]
   __shared__ __align__(8) uint64_t bars[2 * STAGES + 4];
   __shared__ uint32_t tmem_slot_s;
+  __shared__ float stat_bins[8][STAT_BINS][2];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;  // SWIZZLE_128B atoms
   const uint32_t bar_base = smem_u32(bars);
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
@@ -89,7 +93,7 @@ conv_igemm_kernel(const __grid_constant__ ConvKParams p) {
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(tfull_bar(s), 1);
-      mbar_init(tempty_bar(s), 4);  // one arrive per epilogue warp
+      mbar_init(tempty_bar(s), 8);  // one arrive per epilogue warp
     }
     fence_mbar_init();
   }
@@ -178,9 +182,22 @@ conv_igemm_kernel(const __grid_constant__ ConvKParams p) {
       }
     }
   } else {
-    // ===================== epilogue (warps 2..5) =====================
-    const int quarter = warp & 3;  // TMEM lane quarter this warp may access
+    // ===================== epilogue (warps 2..9) =====================
+    // Two warps per TMEM lane quarter (warp % 4), each draining half of the tile's columns.
+    const int ew = warp - 2;
+    const int quarter = warp & 3;
+    const int half = ew >> 2;
+    constexpr int CHUNK_COLS = (BLOCK_N >= 32) ? 32 : BLOCK_N;
+    constexpr int CHUNKS = BLOCK_N / CHUNK_COLS;
+    constexpr int CH_HALF = (CHUNKS + 1) / 2;
+    const int cbeg = half * CH_HALF * CHUNK_COLS;
+    const int cend = min(BLOCK_N, cbeg + CH_HALF * CHUNK_COLS);
     const int row = quarter * 32 + lane;
+    float* my_bins = &stat_bins[ew][0][0];
+    if (p.stats != nullptr) {
+      for (int i = lane; i < STAT_BINS * 2; i += 32) my_bins[i] = 0.f;
+      __syncwarp();
+    }
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
@@ -196,11 +213,12 @@ conv_igemm_kernel(const __grid_constant__ ConvKParams p) {
       const int rem = m - img * P;
       const int y = rem / p.W;
       const int x = rem - y * p.W;
+      const int g_lo = (p.stats != nullptr) ? (n0 + cbeg) / p.cpg : 0;
 #pragma unroll 1
-      for (int c = 0; c < BLOCK_N; c += 32) {
+      for (int c = cbeg; c < cend; c += CHUNK_COLS) {
         uint32_t v[32];
         const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * BLOCK_N + c;
-        if (BLOCK_N - c >= 32) {
+        if (CHUNK_COLS == 32) {
           tmem_ld_32x32b_x32(taddr, v);
         } else {
           tmem_ld_32x32b_x16(taddr, v);
@@ -209,67 +227,109 @@ conv_igemm_kernel(const __grid_constant__ ConvKParams p) {
         }
         tmem_wait_ld();
         const int col0 = n0 + c;
-        if (row_ok && col0 < p.cout) {
-          float f[32];
+        if (col0 >= p.cout) continue;  // warp-uniform: padded weight rows of the last N tile
+        const int ncols = min(32, p.cout - col0);
+        float f[32];
 #pragma unroll
-          for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]);
-          if (p.bias != nullptr) {
+        for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]);
+        if (p.bias != nullptr) {
+          if (ncols == 32) {
+            const float4* b4 = reinterpret_cast<const float4*>(p.bias + col0);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float4 bv = __ldg(b4 + j);
+              f[4 * j + 0] += bv.x;
+              f[4 * j + 1] += bv.y;
+              f[4 * j + 2] += bv.z;
+              f[4 * j + 3] += bv.w;
+            }
+          } else {
 #pragma unroll
             for (int i = 0; i < 32; ++i)
-              if (col0 + i < p.cout) f[i] += __ldg(p.bias + col0 + i);
+              if (i < ncols) f[i] += __ldg(p.bias + col0 + i);
           }
-          const int ncols = min(32, p.cout - col0);
-          if (p.out_mode == ADB_OUT_BF16_NHWC) {
-            // residual: vector path needs 8-channel groups fully inside cout (cout % 8 == 0)
-            if (p.res_mode != ADB_RES_NONE) {
-              const int nsrc = (p.res_mode == ADB_RES_AVGPOOL2) ? 4 : 1;
-              const float wgt = (p.res_mode == ADB_RES_AVGPOOL2) ? 0.25f : 1.0f;
-              for (int sidx = 0; sidx < nsrc; ++sidx) {
-                size_t pix;
-                if (p.res_mode == ADB_RES_SAME) {
-                  pix = (size_t)m;
-                } else if (p.res_mode == ADB_RES_AVGPOOL2) {
-                  const int sy = 2 * y + (sidx >> 1), sx = 2 * x + (sidx & 1);
-                  pix = ((size_t)img * (2 * p.H) + sy) * (2 * p.W) + sx;
-                } else {  // nearest 2x upsample of a half-resolution source
-                  pix = ((size_t)img * (p.H / 2) + (y >> 1)) * (p.W / 2) + (x >> 1);
-                }
-                const __nv_bfloat16* rp = p.residual + pix * p.cout + col0;
+        }
+        if (p.out_mode == ADB_OUT_BF16_NHWC) {
+          // residual: vector path needs 8-channel groups fully inside cout (cout % 8 == 0)
+          if (p.res_mode != ADB_RES_NONE && row_ok) {
+            const int nsrc = (p.res_mode == ADB_RES_AVGPOOL2) ? 4 : 1;
+            const float wgt = (p.res_mode == ADB_RES_AVGPOOL2) ? 0.25f : 1.0f;
+            for (int sidx = 0; sidx < nsrc; ++sidx) {
+              size_t pix;
+              if (p.res_mode == ADB_RES_SAME) {
+                pix = (size_t)m;
+              } else if (p.res_mode == ADB_RES_AVGPOOL2) {
+                const int sy = 2 * y + (sidx >> 1), sx = 2 * x + (sidx & 1);
+                pix = ((size_t)img * (2 * p.H) + sy) * (2 * p.W) + sx;
+              } else {  // nearest 2x upsample of a half-resolution source
+                pix = ((size_t)img * (p.H / 2) + (y >> 1)) * (p.W / 2) + (x >> 1);
+              }
+              const __nv_bfloat16* rp = p.residual + pix * p.cout + col0;
 #pragma unroll
-                for (int g = 0; g < 4; ++g) {
-                  if (g * 8 < ncols) {
-                    const uint4 r = __ldg(reinterpret_cast<const uint4*>(rp) + g);
-                    f[g * 8 + 0] += wgt * bf16_lo(r.x);
-                    f[g * 8 + 1] += wgt * bf16_hi(r.x);
-                    f[g * 8 + 2] += wgt * bf16_lo(r.y);
-                    f[g * 8 + 3] += wgt * bf16_hi(r.y);
-                    f[g * 8 + 4] += wgt * bf16_lo(r.z);
-                    f[g * 8 + 5] += wgt * bf16_hi(r.z);
-                    f[g * 8 + 6] += wgt * bf16_lo(r.w);
-                    f[g * 8 + 7] += wgt * bf16_hi(r.w);
-                  }
+              for (int g = 0; g < 4; ++g) {
+                if (g * 8 < ncols) {
+                  const uint4 r = __ldg(reinterpret_cast<const uint4*>(rp) + g);
+                  f[g * 8 + 0] += wgt * bf16_lo(r.x);
+                  f[g * 8 + 1] += wgt * bf16_hi(r.x);
+                  f[g * 8 + 2] += wgt * bf16_lo(r.y);
+                  f[g * 8 + 3] += wgt * bf16_hi(r.y);
+                  f[g * 8 + 4] += wgt * bf16_lo(r.z);
+                  f[g * 8 + 5] += wgt * bf16_hi(r.z);
+                  f[g * 8 + 6] += wgt * bf16_lo(r.w);
+                  f[g * 8 + 7] += wgt * bf16_hi(r.w);
                 }
               }
             }
+          }
+          uint32_t ow[16];  // this row's 32 outputs rounded to bf16, packed in pairs
+#pragma unroll
+          for (int i = 0; i < 16; ++i) ow[i] = pack_bf16x2(f[2 * i], f[2 * i + 1]);
+          if (row_ok) {
             __nv_bfloat16* op = reinterpret_cast<__nv_bfloat16*>(p.out) + (size_t)m * p.cout + col0;
 #pragma unroll
             for (int g = 0; g < 4; ++g) {
-              if (g * 8 < ncols) {
-                uint4 o;
-                o.x = pack_bf16x2(f[g * 8 + 0], f[g * 8 + 1]);
-                o.y = pack_bf16x2(f[g * 8 + 2], f[g * 8 + 3]);
-                o.z = pack_bf16x2(f[g * 8 + 4], f[g * 8 + 5]);
-                o.w = pack_bf16x2(f[g * 8 + 6], f[g * 8 + 7]);
-                reinterpret_cast<uint4*>(op)[g] = o;
-              }
+              if (g * 8 < ncols)
+                reinterpret_cast<uint4*>(op)[g] = make_uint4(ow[4 * g], ow[4 * g + 1], ow[4 * g + 2], ow[4 * g + 3]);
             }
-          } else {
-            // fp32 NCHW: for a fixed channel, the warp's 32 pixels are contiguous along x
-            float* op = reinterpret_cast<float*>(p.out);
+          }
+          if (p.stats != nullptr) {
+            // GroupNorm statistics of the tensor being written, for its consumer (nn.py:17-19): sum and
+            // sum of squares of the STORED (bf16-rounded) values per (image, group of cpg channels).
+            // Column sums over the warp's 32 rows (pixels of one image: P % 32 == 0) by a transposing
+            // butterfly - 31 shuffles per quantity, independent chains - after which lane j owns
+            // column col0 + j and adds it to this warp's shared-memory bin of its group.
+            float sv[32], qv[32];
 #pragma unroll
             for (int i = 0; i < 32; ++i) {
-              if (i < ncols) op[((size_t)img * p.cout + (col0 + i)) * P + rem] = f[i];
+              const float val = (row_ok && i < ncols) ? ((i & 1) ? bf16_hi(ow[i >> 1]) : bf16_lo(ow[i >> 1])) : 0.f;
+              sv[i] = val;
+              qv[i] = val * val;
             }
+#pragma unroll
+            for (int off = 16, cnt = 16; off > 0; off >>= 1, cnt >>= 1) {
+              const bool upper = (lane & off) != 0;
+#pragma unroll
+              for (int i = 0; i < cnt; ++i) {
+                const float s_keep = upper ? sv[i + cnt] : sv[i];
+                const float s_send = upper ? sv[i] : sv[i + cnt];
+                const float q_keep = upper ? qv[i + cnt] : qv[i];
+                const float q_send = upper ? qv[i] : qv[i + cnt];
+                sv[i] = s_keep + __shfl_xor_sync(0xffffffffu, s_send, off);
+                qv[i] = q_keep + __shfl_xor_sync(0xffffffffu, q_send, off);
+              }
+            }
+            if (lane < ncols) {
+              const int gb = (col0 + lane) / p.cpg - g_lo;
+              atomicAdd(my_bins + 2 * gb, sv[0]);
+              atomicAdd(my_bins + 2 * gb + 1, qv[0]);
+            }
+          }
+        } else if (row_ok) {
+          // fp32 NCHW: for a fixed channel, the warp's 32 pixels are contiguous along x
+          float* op = reinterpret_cast<float*>(p.out);
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            if (i < ncols) op[((size_t)img * p.cout + (col0 + i)) * P + rem] = f[i];
           }
         }
       }
@@ -279,6 +339,24 @@ conv_igemm_kernel(const __grid_constant__ ConvKParams p) {
       if (++acc == 2) {
         acc = 0;
         acc_phase ^= 1u;
+      }
+      if (p.stats != nullptr && cbeg < cend) {
+        // flush this warp's bins: one fp64 atomic pair per group touched by this tile half
+        const int col_last = min(n0 + cend, p.cout) - 1;
+        const int ng = (col_last >= n0 + cbeg) ? (col_last / p.cpg - g_lo + 1) : 0;
+        const int img0 = __shfl_sync(0xffffffffu, img, 0);
+        const bool any_row = __shfl_sync(0xffffffffu, (int)row_ok, 0) != 0;  // rows ascend: row 0 invalid => all invalid
+        for (int gb = lane; gb < ng; gb += 32) {
+          const float bs = my_bins[2 * gb], bq = my_bins[2 * gb + 1];
+          my_bins[2 * gb] = 0.f;
+          my_bins[2 * gb + 1] = 0.f;
+          if (any_row) {
+            double* sp = p.stats + ((size_t)img0 * 32 + (g_lo + gb)) * 2;
+            atomicAdd(sp, (double)bs);
+            atomicAdd(sp + 1, (double)bq);
+          }
+        }
+        __syncwarp();
       }
     }
   }
@@ -388,6 +466,12 @@ int conv_igemm_submit(adb_plan* plan, const adb_conv_desc* d, cudaStream_t strea
   kp.res_mode = d->res_mode;
   kp.out = d->out;
   kp.out_mode = d->out_mode;
+  kp.stats = d->stats_out;
+  kp.cpg = d->cout / 32;
+  if (d->stats_out != nullptr) {
+    ADB_REQUIRE(d->out_mode == ADB_OUT_BF16_NHWC && d->cout % 32 == 0 && P % 32 == 0,
+                "conv_igemm: stats_out needs bf16 output, cout %% 32 == 0 and h*w %% 32 == 0");
+  }
 
   const double flops = 2.0 * (double)M * (double)d->cout * (double)ktot;
   return submit(plan, stream, "conv_igemm", flops, 0.0, [kp, block_n](cudaStream_t s) -> int {

@@ -66,6 +66,80 @@ __global__ void __launch_bounds__(256) stem_conv_kernel(const float* __restrict_
   }
 }
 
+// Fast path (cout % 64 == 0, W % 32 == 0): one warp = 32 consecutive pixels of a row x 64 output
+// channels. The 9*cin inputs of a pixel are loaded once (coalesced along x) and kept in registers;
+// weights are read from shared memory as warp-uniform float4 broadcasts; 64 fp32 accumulators.
+__global__ void __launch_bounds__(256) stem_conv64_kernel(const float* __restrict__ x,
+                                                         const float* __restrict__ wgt,
+                                                         const float* __restrict__ bias,
+                                                         __nv_bfloat16* __restrict__ out, int n, int cin,
+                                                         int H, int W, int cout) {
+  extern __shared__ float s_w[];  // [9*cin][cout] then bias[cout]
+  const int K = 9 * cin;
+  float* s_b = s_w + K * cout;
+  for (int i = threadIdx.x; i < K * cout; i += blockDim.x) {
+    const int co = i % cout;
+    const int k = i / cout;
+    const int tap = k / cin, ci = k - tap * cin;
+    s_w[i] = wgt[((size_t)co * cin + ci) * 9 + tap];
+  }
+  for (int i = threadIdx.x; i < cout; i += blockDim.x) s_b[i] = bias ? bias[i] : 0.f;
+  __syncthreads();
+
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  const int ncg = cout / 64;
+  const size_t P = (size_t)H * W;
+  const size_t items = (size_t)n * P / 32 * ncg;
+  for (size_t item = (size_t)blockIdx.x * 8 + warp; item < items; item += (size_t)gridDim.x * 8) {
+    const int cg = (int)(item % ncg);
+    const size_t pix = (item / ncg) * 32 + lane;
+    const int img = (int)(pix / P);
+    const int rem = (int)(pix - (size_t)img * P);
+    const int y = rem / W, xx = rem - y * W;
+    float a[36];
+#pragma unroll
+    for (int tap = 0; tap < 9; ++tap) {
+      const int yy = y + tap / 3 - 1, xs = xx + tap % 3 - 1;
+      const bool ok = yy >= 0 && yy < H && xs >= 0 && xs < W;
+#pragma unroll
+      for (int ci = 0; ci < 4; ++ci)
+        a[tap * 4 + ci] = (ok && ci < cin) ? __ldg(x + ((size_t)img * cin + ci) * P + (size_t)yy * W + xs) : 0.f;
+    }
+    float acc[64];
+#pragma unroll
+    for (int j = 0; j < 64; ++j) acc[j] = s_b[cg * 64 + j];
+#pragma unroll
+    for (int tap = 0; tap < 9; ++tap) {
+#pragma unroll
+      for (int ci = 0; ci < 4; ++ci) {
+        if (ci < cin) {
+          const float av = a[tap * 4 + ci];
+          const float4* wr = reinterpret_cast<const float4*>(s_w + (tap * cin + ci) * cout + cg * 64);
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const float4 w4 = wr[j];
+            acc[4 * j + 0] = fmaf(av, w4.x, acc[4 * j + 0]);
+            acc[4 * j + 1] = fmaf(av, w4.y, acc[4 * j + 1]);
+            acc[4 * j + 2] = fmaf(av, w4.z, acc[4 * j + 2]);
+            acc[4 * j + 3] = fmaf(av, w4.w, acc[4 * j + 3]);
+          }
+        }
+      }
+    }
+    uint4* op = reinterpret_cast<uint4*>(out + pix * cout + cg * 64);
+#pragma unroll
+    for (int g = 0; g < 8; ++g) {
+      uint4 o;
+      o.x = pack_bf16x2(acc[8 * g + 0], acc[8 * g + 1]);
+      o.y = pack_bf16x2(acc[8 * g + 2], acc[8 * g + 3]);
+      o.z = pack_bf16x2(acc[8 * g + 4], acc[8 * g + 5]);
+      o.w = pack_bf16x2(acc[8 * g + 6], acc[8 * g + 7]);
+      op[g] = o;
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------
 // timestep_embedding (guided_diffusion/nn.py:103-121), fp32 as written there:
 // args = t * freqs; out = [cos(args) | sin(args)]
@@ -237,17 +311,25 @@ int stem_conv_submit(adb_plan* plan, const float* x, const float* weight, const 
   ADB_REQUIRE(cout > 0 && cout % 8 == 0, "stem_conv: cout %% 8 != 0");
   const size_t smem = ((size_t)9 * cin * cout + cout) * sizeof(float);
   ADB_REQUIRE(smem <= 48 * 1024, "stem_conv: weights do not fit shared memory");
-  return submit(plan, stream, "stem_conv", 0.0, 0.0, [=](cudaStream_t s) -> int {
-    const int V = cout / 8;
-    const int slots = V < 256 ? V : 256;
-    const int lanes = 256 / slots;
+  return submit(plan, stream, "stem_conv", 2.0 * 9 * cin * (double)cout * n * h * w, 0.0, [=](cudaStream_t s) -> int {
     const size_t total = (size_t)n * h * w;
-    size_t blocks = (total + lanes - 1) / lanes;
-    const size_t cap = (size_t)num_sms() * 8;
-    if (blocks > cap) blocks = cap;
-    stem_conv_kernel<<<(unsigned)blocks, 256, smem, s>>>(x, weight, bias,
-                                                         reinterpret_cast<__nv_bfloat16*>(out), n, cin, h,
-                                                         w, cout);
+    if (cout % 64 == 0 && w % 32 == 0) {
+      const size_t items = total / 32 * (cout / 64);
+      size_t blocks = (items + 7) / 8;
+      const size_t cap = (size_t)num_sms() * 16;
+      if (blocks > cap) blocks = cap;
+      stem_conv64_kernel<<<(unsigned)blocks, 256, smem, s>>>(x, weight, bias, reinterpret_cast<__nv_bfloat16*>(out),
+                                                             n, cin, h, w, cout);
+    } else {
+      const int V = cout / 8;
+      const int slots = V < 256 ? V : 256;
+      const int lanes = 256 / slots;
+      size_t blocks = (total + lanes - 1) / lanes;
+      const size_t cap = (size_t)num_sms() * 8;
+      if (blocks > cap) blocks = cap;
+      stem_conv_kernel<<<(unsigned)blocks, 256, smem, s>>>(x, weight, bias, reinterpret_cast<__nv_bfloat16*>(out), n,
+                                                           cin, h, w, cout);
+    }
     ADB_CUDA(cudaGetLastError());
     return 1;
   });

@@ -33,6 +33,7 @@ struct GnParams {
   int resample;
   __nv_bfloat16* out;
   double* stats;  // [n][32][2]
+  int stats_ready;
   int splits;
 };
 
@@ -72,7 +73,24 @@ __global__ void __launch_bounds__(GN_THREADS) gn_stats_kernel(const GnParams p) 
     float s[8], q[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) s[i] = q[i] = 0.f;
-    for (int pix = p_begin + pl; pix < p_end; pix += lanes) {
+    int pix = p_begin + pl;
+    // 4 independent 16-byte loads in flight per thread
+    for (; pix + 3 * lanes < p_end; pix += 4 * lanes) {
+      uint4 r[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) r[u] = load_vec(p, (size_t)n * P + pix + u * lanes, v);
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        float f[8];
+        unpack8(r[u], f);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          s[i] += f[i];
+          q[i] = fmaf(f[i], f[i], q[i]);
+        }
+      }
+    }
+    for (; pix < p_end; pix += lanes) {
       float f[8];
       unpack8(load_vec(p, (size_t)n * P + pix, v), f);
 #pragma unroll
@@ -174,7 +192,22 @@ __global__ void __launch_bounds__(GN_THREADS) gn_apply_kernel(const GnParams p) 
       a[i] = s_a[v * 8 + i];
       b[i] = s_b[v * 8 + i];
     }
-    for (int pix = p_begin + pl; pix < p_end; pix += lanes) {
+    int pix = p_begin + pl;
+    if (p.resample == ADB_RESAMPLE_NONE) {
+      for (; pix + 3 * lanes < p_end; pix += 4 * lanes) {
+        uint4 r[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) r[u] = load_vec(p, (size_t)n * P + pix + u * lanes, v);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          float f[8], o[8];
+          unpack8(r[u], f);
+          affine_act8(f, a, b, p.silu, o);
+          *reinterpret_cast<uint4*>(p.out + ((size_t)n * P + pix + u * lanes) * p.C + v * 8) = pack8(o);
+        }
+      }
+    }
+    for (; pix < p_end; pix += lanes) {
       float f[8], o[8];
       if (p.resample == ADB_RESAMPLE_NONE) {
         unpack8(load_vec(p, (size_t)n * P + pix, v), f);
@@ -286,23 +319,28 @@ int groupnorm_submit(adb_plan* plan, const adb_gn_desc* d, cudaStream_t stream) 
   p.resample = d->resample;
   p.out = reinterpret_cast<__nv_bfloat16*>(d->out);
   p.stats = d->stats;
+  p.stats_ready = d->stats_ready;
   const int P = d->h * d->w;
-  int splits = (4 * num_sms() + d->n - 1) / d->n;
-  const int max_splits = (P / 32) > 1 ? (P / 32) : 1;
+  int splits = (8 * num_sms() + d->n - 1) / d->n;
+  const int max_splits = (P / 64) > 1 ? (P / 64) : 1;
   if (splits > max_splits) splits = max_splits;
   if (splits < 1) splits = 1;
   p.splits = splits;
 
   const double in_elems = (double)d->n * P * C;
   const double out_elems = d->resample == ADB_RESAMPLE_AVGPOOL2 ? in_elems / 4 : (d->resample == ADB_RESAMPLE_NEAREST2 ? in_elems * 4 : in_elems);
-  return submit(plan, stream, "groupnorm", 0.0, 2.0 * (in_elems + out_elems), [p](cudaStream_t s) -> int {
-    ADB_CUDA(cudaMemsetAsync(p.stats, 0, (size_t)p.n * GN_GROUPS * 2 * sizeof(double), s));
+  return submit(plan, stream, p.stats_ready ? "groupnorm_apply" : "groupnorm", 0.0, 2.0 * (in_elems + out_elems), [p](cudaStream_t s) -> int {
     dim3 grid(p.splits, p.n);
-    gn_stats_kernel<<<grid, GN_THREADS, 0, s>>>(p);
-    ADB_CUDA(cudaGetLastError());
+    int launches = 1;
+    if (!p.stats_ready) {
+      ADB_CUDA(cudaMemsetAsync(p.stats, 0, (size_t)p.n * GN_GROUPS * 2 * sizeof(double), s));
+      gn_stats_kernel<<<grid, GN_THREADS, 0, s>>>(p);
+      ADB_CUDA(cudaGetLastError());
+      launches = 3;
+    }
     gn_apply_kernel<<<grid, GN_THREADS, 2 * p.C * sizeof(float), s>>>(p);
     ADB_CUDA(cudaGetLastError());
-    return 3;
+    return launches;
   });
 }
 

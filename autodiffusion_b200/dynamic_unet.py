@@ -127,6 +127,7 @@ class _Ctx:
         self.plan = plan
         self.raw: Dict[int, th.Tensor] = {}   # data_ptr -> raw buffer
         self.refs: Dict[int, int] = {}
+        self.on_alloc = None  # hook(t): called for every fresh (possibly recycled) buffer
 
     def alloc(self, shape, dtype=th.bfloat16) -> th.Tensor:
         n = 1
@@ -139,6 +140,8 @@ class _Ctx:
         self.raw[t.data_ptr()] = raw
         self.refs[t.data_ptr()] = 1
         self.plan.keep(raw)
+        if self.on_alloc is not None:
+            self.on_alloc(t)
         return t
 
     def retain(self, t: th.Tensor):
@@ -463,8 +466,33 @@ class Dynamic_UNetModel(nn.Module):
         ctx = _Ctx(self._pool, plan)
         dev = self._device()
         mc, ted = self.model_channels, self.model_channels * 4
-        stats = th.empty((B, 32, 2), dtype=th.float64, device=dev)
+        stats = th.empty((B, 32, 2), dtype=th.float64, device=dev)  # scratch of the stand-alone stats pass
         plan.keep(stats, up.x_in, up.t_in, up.y_in, up.out)
+        # GroupNorm sums accumulated by the PRODUCING conv's epilogue (one slot per conv output that a
+        # single-source GroupNorm will read); the whole arena is zeroed by one memset per forward.
+        fuse_stats = os.environ.get("ADB_NO_FUSED_STATS", "0") != "1" and (H * W) % 32 == 0
+        arena = th.empty((2 * self.layer_num + 4, B, 32, 2), dtype=th.float64, device=dev)
+        slot = [0]
+        produced: Dict[int, th.Tensor] = {}  # data_ptr of an activation -> its producer-filled stats
+        ctx.on_alloc = lambda t: produced.pop(t.data_ptr(), None)  # a recycled buffer has no stats yet
+        if fuse_stats:
+            ops.memset0(arena, plan=plan)
+
+        def new_stats(t: th.Tensor):
+            """Stats slot for conv output `t` (None when fusion is off or the geometry does not allow it)."""
+            if not fuse_stats or t.shape[3] % 32 != 0 or (t.shape[1] * t.shape[2]) % 32 != 0:
+                produced.pop(t.data_ptr(), None)
+                return None
+            st = arena[slot[0]]
+            slot[0] += 1
+            produced[t.data_ptr()] = st
+            return st
+
+        def gn(srcs, gamma, beta, out_t, **kw):
+            """GroupNorm reading producer-filled sums when its single source has them."""
+            st = produced.get(srcs[0].data_ptr()) if len(srcs) == 1 else None
+            ops.groupnorm(srcs[0], gamma, beta, src1=srcs[1] if len(srcs) > 1 else None, out=out_t,
+                          stats=st if st is not None else stats, stats_ready=st is not None, plan=plan, **kw)
 
         # timestep / label embedding (dynamic_unet.py:687-691) and every emb_layers product (:259)
         te = ops.timestep_embedding(up.t_in, mc, plan=plan)
@@ -480,36 +508,38 @@ class Dynamic_UNetModel(nn.Module):
             updown = layer.up or layer.down
             if layer.layer_id in skip:  # dynamic_unet.py:246-249
                 if updown:
-                    return ops.resample2x(
-                        srcs[0], ops.RESAMPLE_NEAREST2 if layer.up else ops.RESAMPLE_AVGPOOL2,
-                        out=ctx.alloc((n, h * 2, w * 2, cout) if layer.up else (n, h // 2, w // 2, cout)), plan=plan)
+                    o = ctx.alloc((n, h * 2, w * 2, cout) if layer.up else (n, h // 2, w // 2, cout))
+                    produced.pop(o.data_ptr(), None)
+                    return ops.resample2x(srcs[0], ops.RESAMPLE_NEAREST2 if layer.up else ops.RESAMPLE_AVGPOOL2,
+                                          out=o, plan=plan)
                 if pk.ws_raw is None:
                     ctx.retain(srcs[0])
                     return srcs[0]
                 wsk = self._w2_skip_only(layer, tuple(s.shape[3] for s in srcs))
-                return ops.conv_igemm([(s, 1) for s in srcs], wsk, pk.bskip, cout,
-                                      out=ctx.alloc((n, h, w, cout)), plan=plan)
+                o = ctx.alloc((n, h, w, cout))
+                return ops.conv_igemm([(s, 1) for s in srcs], wsk, pk.bskip, cout, out=o, plan=plan,
+                                      stats_out=new_stats(o))
             ho, wo = (h * 2, w * 2) if layer.up else ((h // 2, w // 2) if layer.down else (h, w))
             mode = ops.RESAMPLE_NEAREST2 if layer.up else (ops.RESAMPLE_AVGPOOL2 if layer.down else ops.RESAMPLE_NONE)
             cin = sum(s.shape[3] for s in srcs)
             g1 = ctx.alloc((n, ho, wo, cin))
-            ops.groupnorm(srcs[0], pk.g1, pk.be1, src1=srcs[1] if len(srcs) > 1 else None, silu=True,
-                          resample=mode, out=g1, stats=stats, plan=plan)
+            gn(srcs, pk.g1, pk.be1, g1, silu=True, resample=mode)
             c1 = ctx.alloc((n, ho, wo, cout))
-            ops.conv_igemm([(g1, 9)], pk.w1, pk.b1, cout, out=c1, plan=plan)
+            ops.conv_igemm([(g1, 9)], pk.w1, pk.b1, cout, out=c1, plan=plan, stats_out=new_stats(c1))
             ctx.release(g1)
             g2 = ctx.alloc((n, ho, wo, cout))
-            ops.groupnorm(c1, pk.g2, pk.be2, scale_shift=(ss_all, pk.ss_off), ss_stride=ss_total, silu=True,
-                          out=g2, stats=stats, plan=plan)
+            gn([c1], pk.g2, pk.be2, g2, scale_shift=(ss_all, pk.ss_off), ss_stride=ss_total, silu=True)
             ctx.release(c1)
             out = ctx.alloc((n, ho, wo, cout))
             if pk.ws_raw is not None:
                 w2 = self._w2_for(layer, tuple(s.shape[3] for s in srcs))
-                ops.conv_igemm([(g2, 9)] + [(s, 1) for s in srcs], w2, pk.b2, cout, out=out, plan=plan)
+                ops.conv_igemm([(g2, 9)] + [(s, 1) for s in srcs], w2, pk.b2, cout, out=out, plan=plan,
+                               stats_out=new_stats(out))
             else:
                 w2 = self._w2_for(layer, ())
                 rm = ops.RES_NEAREST2 if layer.up else (ops.RES_AVGPOOL2 if layer.down else ops.RES_SAME)
-                ops.conv_igemm([(g2, 9)], w2, pk.b2, cout, out=out, residual=srcs[0], res_mode=rm, plan=plan)
+                ops.conv_igemm([(g2, 9)], w2, pk.b2, cout, out=out, residual=srcs[0], res_mode=rm, plan=plan,
+                               stats_out=new_stats(out))
             ctx.release(g2)
             return out
 
@@ -521,7 +551,7 @@ class Dynamic_UNetModel(nn.Module):
             n, h, w, c = x.shape
             t = h * w
             g = ctx.alloc((n, h, w, c))
-            ops.groupnorm(x, pk.g, pk.be, silu=False, out=g, stats=stats, plan=plan)
+            gn([x], pk.g, pk.be, g, silu=False)
             qkv = ctx.alloc((n, h, w, 3 * c))
             ops.conv_igemm([(g, 1)], pk.wqkv, pk.bqkv, 3 * c, out=qkv, plan=plan)
             ctx.release(g)
@@ -530,7 +560,8 @@ class Dynamic_UNetModel(nn.Module):
                           out=a.view(n * t, c), plan=plan)
             ctx.release(qkv)
             out = ctx.alloc((n, h, w, c))
-            ops.conv_igemm([(a, 1)], pk.wproj, pk.bproj, c, out=out, residual=x, res_mode=ops.RES_SAME, plan=plan)
+            ops.conv_igemm([(a, 1)], pk.wproj, pk.bproj, c, out=out, residual=x, res_mode=ops.RES_SAME, plan=plan,
+                           stats_out=new_stats(out))
             ctx.release(a)
             return out
 
@@ -544,7 +575,9 @@ class Dynamic_UNetModel(nn.Module):
             return srcs[0]
 
         ch0 = int(self.channel_mult[0] * mc)
-        h = ops.stem_conv(up.x_in, P["stem_w"], P["stem_b"], out=ctx.alloc((B, H, W, ch0)), plan=plan)
+        h = ctx.alloc((B, H, W, ch0))
+        produced.pop(h.data_ptr(), None)
+        ops.stem_conv(up.x_in, P["stem_w"], P["stem_b"], out=h, plan=plan)
         hs = [h]
         ctx.retain(h)  # one reference for hs, one for the running h
         for blk in list(self.input_blocks)[1:]:
@@ -555,7 +588,7 @@ class Dynamic_UNetModel(nn.Module):
         for blk in self.output_blocks:
             h = run_block(blk, [h, hs.pop()])  # th.cat([h, hs.pop()], dim=1), dynamic_unet.py:699
         g = ctx.alloc(tuple(h.shape))
-        ops.groupnorm(h, P["out_g"], P["out_be"], silu=True, out=g, stats=stats, plan=plan)
+        gn([h], P["out_g"], P["out_be"], g, silu=True)
         ctx.release(h)
         ops.conv_igemm([(g, 9)], P["out_w"], P["out_b"], self.out_channels, out=up.out,
                        out_mode=ops.OUT_F32_NCHW, plan=plan)

@@ -146,8 +146,10 @@ def conv_igemm(
     res_mode: int = RES_NONE,
     out_mode: int = OUT_BF16_NHWC,
     plan: Optional[Plan] = None,
+    stats_out: Optional[torch.Tensor] = None,
 ) -> torch.Tensor:
-    """segs: [(act[n,h,w,cin] bf16, taps), ...]; weight from `pack_conv_weight`."""
+    """segs: [(act[n,h,w,cin] bf16, taps), ...]; weight from `pack_conv_weight`.
+    stats_out: optional zeroed fp64 [n,32,2]; the epilogue adds the output's GroupNorm sums to it."""
     act0 = segs[0][0]
     n, h, w = act0.shape[0], act0.shape[1], act0.shape[2]
     d = _lib.ConvDesc()
@@ -175,9 +177,10 @@ def conv_igemm(
             out = torch.empty((n, cout, h, w), dtype=torch.float32, device=act0.device)
     d.out = _dev(out, "out")
     d.out_mode = out_mode
+    d.stats_out = _opt(stats_out, "stats_out", torch.float64)
     _lib.check(_lib.lib().adb_conv_igemm(_ph(plan), C.byref(d), _stream()), "adb_conv_igemm")
     if plan is not None:
-        plan.keep(*[s[0] for s in segs], weight, bias, residual, out)
+        plan.keep(*[s[0] for s in segs], weight, bias, residual, out, stats_out)
     return out
 
 
@@ -211,7 +214,9 @@ def groupnorm(
     out: Optional[torch.Tensor] = None,
     stats: Optional[torch.Tensor] = None,
     plan: Optional[Plan] = None,
+    stats_ready: bool = False,
 ) -> torch.Tensor:
+    """stats_ready: `stats` already holds the producer-accumulated sums (conv_igemm stats_out)."""
     n, h, w, c0 = src0.shape
     c1 = 0 if src1 is None else src1.shape[3]
     c = c0 + c1
@@ -239,6 +244,7 @@ def groupnorm(
     d.resample = resample
     d.out = _dev(out, "out", torch.bfloat16)
     d.stats = _dev(stats, "stats", torch.float64)
+    d.stats_ready = int(bool(stats_ready))
     _lib.check(_lib.lib().adb_groupnorm(_ph(plan), C.byref(d), _stream()), "adb_groupnorm")
     if plan is not None:
         plan.keep(src0, src1, gamma, beta, ss_base, out, stats)

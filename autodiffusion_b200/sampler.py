@@ -143,6 +143,7 @@ class SchedulePlan:
             self.y.copy_(y, non_blocking=True)
         if self.cond_fn is None:
             self._run_segment(0)
+            self.model.gpu_launches += self.launches
             return self.final
         kwargs = dict(model_kwargs or {})
         if self.class_cond:

@@ -87,6 +87,8 @@ typedef struct {
   int res_mode;
   void* out;
   int out_mode;
+  double* stats_out;    /* optional [n, 32, 2] fp64: the epilogue ADDS sum / sum-of-squares of the stored
+                           output per (image, GroupNorm group of cout/32 channels); caller zeroes it */
 } adb_conv_desc;
 
 /* N tile the kernel uses for `cout` output channels; `cout_pad` must be a multiple of it. */
@@ -120,7 +122,10 @@ typedef struct {
   int silu;
   int resample;
   void* out;                /* bf16 NHWC at the resampled geometry, c0+c1 channels */
-  double* stats;            /* workspace [n, 32, 2] doubles, zeroed by the call itself */
+  double* stats;            /* [n, 32, 2] doubles: (sum, sum of squares) per (image, group) */
+  int stats_ready;          /* 0: zero `stats` and compute them here (one extra read of the input);
+                               1: `stats` were already accumulated by the producer (adb_conv_igemm
+                               stats_out / adb_stem_conv) - only the normalise pass runs */
 } adb_gn_desc;
 
 int adb_groupnorm(adb_plan* plan, const adb_gn_desc* d, adb_stream stream);

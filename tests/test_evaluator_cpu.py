@@ -1,0 +1,107 @@
+"""CPU: host-side logic of the candidate evaluator — candidate resolution (sorted-rank skip indexing,
+dedup), batch sharding, world-size-independent seeds, and the moment all-reduce + FID finalisation over
+gloo with world size 2 (the N>1 path; the CUDA accumulation kernel itself is covered by -m gpu tests)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from oracle import fid_ref
+from tests.util import golden
+
+
+def _diffusion():
+    from autodiffusion_b200 import create_gaussian_diffusion
+
+    return create_gaussian_diffusion(steps=1000, learn_sigma=True, noise_schedule="cosine")
+
+
+def test_resolve_candidate_sorted_rank_and_dedup():
+    from autodiffusion_b200.sampler import resolve_candidate
+
+    base = _diffusion()
+    cand = {"timesteps": [690, 153, 926, 424], "skip_layers": [[], [9, 2], [], [17, 5, 12, 5]]}
+    active, per_step = resolve_candidate(cand, base)
+    assert active.timestep_map == [153, 424, 690, 926]
+    # skip_layers[j] belongs to the j-th SMALLEST timestep (…progressive.py:394-396), not to timesteps[j]
+    assert per_step == [[], [2, 9], [], [5, 12, 17]]
+    g = golden("ddim_small.npz")
+    seen_t = g["guided/seen_t"].tolist()
+    assert [active.timestep_map[i] for i in range(active.num_timesteps)][::-1] == seen_t
+
+    active, per_step = resolve_candidate({"timesteps": [5, 5, 900], "skip_layers": [[1], [2], [3]]}, base)
+    assert active.timestep_map == [5, 900] and per_step == [[1], [2]]  # trailing entry unused after dedup
+    active, per_step = resolve_candidate([94, 834, 217], base)  # timestep-only candidate (list form)
+    assert active.num_timesteps == 3 and per_step == [[], [], []]
+    with pytest.raises(IndexError):
+        resolve_candidate({"timesteps": [1, 2, 3], "skip_layers": [[]]}, base)
+    assert base.num_timesteps == 1000  # base untouched
+
+
+def test_shards_cover_every_batch_once_and_seeds_ignore_world_size():
+    from autodiffusion_b200.evaluator import batch_seed, shard_batches
+
+    for nb in (1, 4, 7, 10):
+        for world in (1, 2, 3, 8):
+            got = sorted(b for r in range(world) for b in shard_batches(nb, r, world))
+            assert got == list(range(nb))
+    s = {batch_seed(0, "cand", b) for b in range(100)}
+    assert len(s) == 100
+    assert batch_seed(0, "cand", 3) != batch_seed(1, "cand", 3) != batch_seed(0, "cand2", 3)
+    assert batch_seed(5, "c", 2) == batch_seed(5, "c", 2)
+
+
+def _reduce_worker(rank, world, port, tmp):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from autodiffusion_b200.evaluator import FIDStatistics, MomentAccumulator
+
+    g = golden("fid.npz")
+    f1, f2 = g["full/f1"].astype(np.float64), g["full/f2"]
+    mine = f1[rank::world]  # this rank's share of the candidate's features
+    acc = MomentAccumulator(f1.shape[1], "cpu")
+    acc.load_partial(mine.shape[0], mine.sum(0), mine.T @ mine)
+    acc.all_reduce()
+    mu, sigma = acc.statistics()
+    fid = FIDStatistics(mu, sigma).frechet_distance(FIDStatistics(*fid_ref.compute_statistics(f2)))
+    np.save(os.path.join(tmp, f"r{rank}.npy"), np.array([fid, float(acc.n.item())]))
+    dist.destroy_process_group()
+
+
+def test_moment_allreduce_world2_matches_reference_fid(tmp_path):
+    world, port = 2, 29500 + (os.getpid() % 500)
+    mp.spawn(_reduce_worker, args=(world, port, str(tmp_path)), nprocs=world, join=True)
+    g = golden("fid.npz")
+    want = float(g["full/fid"])  # produced by the reference's FIDStatistics.frechet_distance
+    for r in range(world):
+        fid, n = np.load(tmp_path / f"r{r}.npy")
+        assert n == g["full/f1"].shape[0]
+        assert abs(fid - want) <= 1e-6 * max(1.0, abs(want)), (fid, want)
+
+
+def test_moment_statistics_match_numpy_cov():
+    from autodiffusion_b200.evaluator import MomentAccumulator
+
+    rng = np.random.RandomState(1)
+    f = rng.randn(300, 48) * 3 + 10  # large mean: checks the fp64 cancellation margin
+    acc = MomentAccumulator(48, "cpu")
+    acc.load_partial(300, f.sum(0), f.T @ f)
+    mu, sigma = acc.statistics()
+    np.testing.assert_allclose(mu, f.mean(0), rtol=1e-12)
+    np.testing.assert_allclose(sigma, np.cov(f, rowvar=False), rtol=1e-9, atol=1e-10)
+    acc.reset()
+    with pytest.raises(ValueError):
+        acc.statistics()
+
+
+def test_fid_statistics_matches_reference_fixture():
+    from autodiffusion_b200.evaluator import FIDStatistics
+
+    g = golden("fid.npz")
+    for name in ("full", "singular"):
+        a = FIDStatistics(*fid_ref.compute_statistics(g[f"{name}/f1"]))
+        b = FIDStatistics(*fid_ref.compute_statistics(g[f"{name}/f2"]))
+        assert abs(a.frechet_distance(b) - float(g[f"{name}/fid"])) <= 1e-6 * float(g[f"{name}/fid"])

@@ -124,3 +124,67 @@ def test_ddim_sample_loop_matches_reference(name):
     u8 = ops.pack_uint8(outs[-1].contiguous()).cpu().numpy().astype(np.int32)
     diff = np.abs(u8 - g[f"{name}/uint8"].astype(np.int32))
     print(f"uint8: max diff {diff.max()} LSB, mean {diff.mean():.3f}")
+
+
+def test_schedule_plan_matches_generic_loop_and_evaluator_fid():
+    """The fused whole-candidate plan (one CUDA graph) vs the generic closure-driven loop, with and
+    without a cond_fn; then CandidateEvaluator.get_cand_fid vs numpy mean/cov + the oracle's Frechet
+    distance on the very same images."""
+    from autodiffusion_b200.evaluator import CandidateEvaluator, FIDStatistics
+    from autodiffusion_b200.respace import reset_diffusion
+    from autodiffusion_b200.sampler import SchedulePlan, resolve_candidate
+    from oracle import fid_ref
+
+    cfg, sd = oracle_weights(SMALL_FLAGS)
+    model, diffusion = build_ours(SMALL_FLAGS, sd)
+    cand = {"timesteps": [690, 153, 926, 424], "skip_layers": [[], [2, 9], [], [5, 12, 17]]}
+    B = 4
+    noise = torch.randn(B, 3, 64, 64, generator=torch.Generator().manual_seed(11)).cuda()
+    y = torch.randint(0, 1000, (B,), generator=torch.Generator().manual_seed(12)).cuda()
+    base = copy.deepcopy(diffusion)
+    active = reset_diffusion(cand["timesteps"], copy.deepcopy(diffusion), base)
+
+    def model_fn(x, t, y=None, skip_layers=None):
+        return model(x, t, y, skip_layer=skip_layers[active.timestep_map.index(t[0])])
+
+    def cond_fn(x, t, y=None, **kw):  # any torch callable; here a cheap analytic "gradient"
+        return 0.05 * torch.tanh(x) * (1.0 + y.float().view(-1, 1, 1, 1) / 1000.0) * (t.float().view(-1, 1, 1, 1) / 1000.0)
+
+    for cf in (None, cond_fn):
+        ref = active.ddim_sample_loop(model_fn, (B, 3, 64, 64), noise=noise, clip_denoised=True, cond_fn=cf,
+                                      model_kwargs={"y": y, "skip_layers": cand["skip_layers"]}, device=torch.device("cuda"))
+        act2, per_step = resolve_candidate(cand, base)
+        assert per_step == [[], [2, 9], [], [5, 12, 17]] and act2.timestep_map == active.timestep_map
+        plan = SchedulePlan(model, act2, per_step, B, cond_fn=cf, pack_uint8=True)
+        out1 = plan.run(noise, y).clone()
+        out2 = plan.run(noise, y).clone()  # second run replays captured graphs
+        torch.cuda.synchronize()
+        p1, p2 = psnr(out1.cpu(), ref.cpu()), psnr(out2.cpu(), out1.cpu())
+        print(f"SchedulePlan vs generic loop (cond_fn={cf is not None}): psnr={p1:.1f} dB; replay vs first run: {p2:.1f} dB")
+        assert p1 >= 55.0 and p2 >= 55.0  # same kernels; only fp64-atomic summation order may differ
+        assert torch.equal(plan.u8.cpu(), diffusion_ref.pack_uint8(plan.final.cpu()))
+
+    # evaluator: 10 samples in batches of 4 (last batch truncated to 2), 64-d random-projection "features"
+    proj = torch.randn(3 * 64 * 64, 64, generator=torch.Generator().manual_seed(13)).cuda() / 255.0
+    feats_seen = []
+
+    def feature_fn(u8):
+        f = u8.reshape(u8.shape[0], -1).float() @ proj
+        feats_seen.append(f.cpu())
+        return f
+
+    rng = np.random.RandomState(0)
+    ref_f = rng.randn(200, 64) * 2 + 5
+    ref_stats = FIDStatistics(*fid_ref.compute_statistics(ref_f))
+    ev = CandidateEvaluator(model, base, feature_fn, ref_stats, batch_size=4, num_samples=10, image_size=64, seed=3)
+    fid = ev.get_cand_fid(cand)
+    allf = torch.cat(feats_seen).double().numpy()
+    assert allf.shape == (10, 64)
+    want = fid_ref.frechet_distance(*fid_ref.compute_statistics(allf), ref_stats.mu, ref_stats.sigma)
+    print(f"get_cand_fid={fid:.6f} numpy/oracle on the same images={want:.6f} times={ev.last_times}")
+    assert abs(fid - want) <= 1e-6 * max(1.0, abs(want))
+    # the same candidate again hits the plan cache and reproduces the images (per-batch seeds)
+    feats_seen.clear()
+    fid2 = ev.get_cand_fid(cand)
+    assert abs(fid2 - fid) <= 1e-3 * max(1.0, abs(fid))
+    assert ev.is_legal(str(cand), log=lambda s: None) and not ev.is_legal(str(cand), log=lambda s: None)

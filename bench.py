@@ -53,6 +53,7 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-roofline", action="store_true")
     ap.add_argument("--ref-batch", type=int, default=8)
+    ap.add_argument("--dump-ops", default=None, help="write every recorded op's kind/flops/bytes/ms of one step to this CSV")
     return ap.parse_args()
 
 
@@ -315,6 +316,11 @@ def run_ours(args):
             a[2] += fl
             a[3] += by
         total_ms = sum(ms_ops)
+        if args.dump_ops:
+            with open(args.dump_ops, "w") as f:
+                f.write("idx,kind,flops,bytes,ms\n")
+                for i, ((kind, fl, by), t) in enumerate(zip(info, ms_ops)):
+                    f.write(f"{i},{kind},{fl:.0f},{by:.0f},{t:.5f}\n")
         conv = agg["conv_igemm"]
         achieved = conv[2] / (conv[1] * 1e-3) / 1e12
         line["roofline"] = {"kernel": "conv_igemm_kernel (tcgen05 implicit GEMM: 3x3/1x1 conv, qkv/proj)", "bound": "tensor",

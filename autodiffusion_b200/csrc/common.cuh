@@ -71,9 +71,9 @@ int num_sms();
 
 // TMA descriptors -------------------------------------------------------------------------
 // bf16 tensor of rank `rank`, dims/strides innermost first (strides in bytes for dims 1..),
-// 128-byte swizzle, zero fill out of bounds.
+// 128-byte (default) or 64-byte swizzle, zero fill out of bounds.
 int make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims,
-                   const uint64_t* strides_bytes, const uint32_t* box);
+                   const uint64_t* strides_bytes, const uint32_t* box, int swizzle_bytes = 128);
 
 // ---------------------------------------------------------------------------------------
 // device-side PTX wrappers
@@ -160,6 +160,16 @@ __device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map
       ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
       : "memory");
 }
+// TMA store smem -> global (bulk async-group completion); rows/columns outside the tensor are clipped
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, uint32_t src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+               ::"l"(map), "r"(src), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+// all committed stores have finished READING their shared-memory source (it may be overwritten)
+__device__ __forceinline__ void tma_store_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_all0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
 }

@@ -38,6 +38,9 @@ constexpr int STAT_BINS = 40;      // >= groups one epilogue warp can touch per 
 struct ConvKParams {
   CUtensorMap tmA[3];
   CUtensorMap tmW;  // box {64, BLOCK_N / NCTA}: in 2-CTA mode each CTA of the pair loads half of the N tile
+  CUtensorMap tmOut;  // bf16 [M, cout] output, box {32 ch, 32 rows}, 64-byte swizzle (epilogue TMA stores)
+  CUtensorMap tmRes;  // same geometry over the same-resolution residual (epilogue TMA loads)
+  int tma_epi;        // 1: epilogue moves output (and RES_SAME residual) by TMA through shared memory
   int seg_taps[3];
   int seg_cin[3];
   int seg_chunks[3];
@@ -59,13 +62,17 @@ template <int BLOCK_N, int NCTA>
 struct Cfg {
   static constexpr int B_STAGE_BYTES = (BLOCK_N / NCTA) * BLOCK_K * 2;
   static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;  // per CTA
-  static constexpr int STAGES = (200 * 1024) / STAGE_BYTES > 8 ? 8 : (200 * 1024) / STAGE_BYTES;
+  // epilogue staging: per epilogue warp two 2 KB residual buffers + one 2 KB output buffer
+  static constexpr int EPI_WARP_BYTES = 3 * 2048;
+  static constexpr int EPI_BYTES = 8 * EPI_WARP_BYTES;
+  static constexpr int RING_BUDGET = 227 * 1024 - EPI_BYTES - 2048;
+  static constexpr int STAGES = RING_BUDGET / STAGE_BYTES > 8 ? 8 : RING_BUDGET / STAGE_BYTES;
   static constexpr int TMEM_COLS = (2 * BLOCK_N <= 32)    ? 32
                                    : (2 * BLOCK_N <= 64)  ? 64
                                    : (2 * BLOCK_N <= 128) ? 128
                                    : (2 * BLOCK_N <= 256) ? 256
                                                           : 512;
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_BYTES + 1024 /*align slack*/;
 };
 
 template <int BLOCK_N, int NCTA>
@@ -87,6 +94,7 @@ conv_igemm_kernel(const __grid_constant__ ConvKParams p) {
   __shared__ uint32_t tmem_slot_s;
   __shared__ float stat_bins[8][STAT_BINS][2];
   __shared__ float stat_cols[8][64];  // per epilogue warp: column sums / sums of squares of one chunk
+  __shared__ __align__(8) uint64_t res_bars[8][2];  // per epilogue warp: residual TMA landed (2 buffers)
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;  // SWIZZLE_128B atoms
   const uint32_t bar_base = smem_u32(bars);
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
@@ -101,6 +109,14 @@ conv_igemm_kernel(const __grid_constant__ ConvKParams p) {
   if (warp == TMA_WARP && lane == 0) {
     for (int s = 0; s < p.nseg; ++s) tma_prefetch_desc(&p.tmA[s]);
     tma_prefetch_desc(&p.tmW);
+    if (p.tma_epi) {
+      tma_prefetch_desc(&p.tmOut);
+      if (p.res_mode == ADB_RES_SAME) tma_prefetch_desc(&p.tmRes);
+    }
+    for (int w = 0; w < 8; ++w) {
+      mbar_init(smem_u32(&res_bars[w][0]), 1);
+      mbar_init(smem_u32(&res_bars[w][1]), 1);
+    }
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(full_bar(s), NCTA);  // one producer arrive per CTA of the pair (on the leader's barrier)
       mbar_init(empty_bar(s), 1);
@@ -230,6 +246,14 @@ conv_igemm_kernel(const __grid_constant__ ConvKParams p) {
     const int row = quarter * 32 + lane;
     float* my_bins = &stat_bins[ew][0][0];
     float* my_cols = &stat_cols[ew][0];
+    // per-warp staging buffers behind the operand ring: [residual 0 | residual 1 | output], 2 KB each
+    const uint32_t epi_base = smem_base + STAGES * C::STAGE_BYTES + ew * C::EPI_WARP_BYTES;
+    uint8_t* epi_gen = smem_raw + (epi_base - smem_u32(smem_raw));
+    const uint32_t epi_out = epi_base + 4096;
+    uint8_t* epi_out_gen = epi_gen + 4096;
+    const uint32_t res_bar0 = smem_u32(&res_bars[ew][0]);
+    uint32_t res_phase = 0u;  // bit b = parity to wait for on residual buffer b
+    int res_buf = 0;
     if (p.stats != nullptr) {
       for (int i = lane; i < STAT_BINS * 2; i += 32) my_bins[i] = 0.f;
       __syncwarp();
@@ -252,7 +276,9 @@ conv_igemm_kernel(const __grid_constant__ ConvKParams p) {
       const int g_lo = (p.stats != nullptr) ? (n0 + cbeg) / p.cpg : 0;
       // single-source residuals (same / nearest-up) are fetched one chunk AHEAD so their HBM
       // latency overlaps the previous chunk's math; the 4-source average-pool variant is not.
-      const bool res_pf = row_ok && (p.res_mode == ADB_RES_SAME || p.res_mode == ADB_RES_NEAREST2);
+      const bool res_tma = p.tma_epi && p.res_mode == ADB_RES_SAME;  // warp-uniform
+      const bool res_pf = !res_tma && row_ok && (p.res_mode == ADB_RES_SAME || p.res_mode == ADB_RES_NEAREST2);
+      const int row0 = m_tile * BLOCK_M + quarter * 32;  // first output row of this warp's 32x32 sub-tiles
       const __nv_bfloat16* res_row = nullptr;
       if (res_pf) {
         const size_t pix = (p.res_mode == ADB_RES_SAME)
@@ -269,6 +295,11 @@ conv_igemm_kernel(const __grid_constant__ ConvKParams p) {
         }
       };
       fetch_res(n0 + cbeg);
+      if (res_tma && lane == 0 && cbeg < cend) {
+        fence_proxy_async_smem();
+        mbar_arrive_expect_tx(res_bar0 + 8u * res_buf, 2048);
+        tma_load_2d(epi_base + 2048u * res_buf, &p.tmRes, res_bar0 + 8u * res_buf, n0 + cbeg, row0);
+      }
 #pragma unroll 1
       for (int c = cbeg; c < cend; c += CHUNK_COLS) {
         uint32_t v[32];
@@ -284,7 +315,15 @@ conv_igemm_kernel(const __grid_constant__ ConvKParams p) {
         uint4 rcur[4];
 #pragma unroll
         for (int g = 0; g < 4; ++g) rcur[g] = rnext[g];
-        if (c + CHUNK_COLS < cend) fetch_res(col0 + CHUNK_COLS);
+        if (c + CHUNK_COLS < cend) {
+          fetch_res(col0 + CHUNK_COLS);
+          if (res_tma && lane == 0) {
+            // the other buffer was last read (generic proxy) one chunk ago, before a __syncwarp
+            fence_proxy_async_smem();
+            mbar_arrive_expect_tx(res_bar0 + 8u * (res_buf ^ 1), 2048);
+            tma_load_2d(epi_base + 2048u * (res_buf ^ 1), &p.tmRes, res_bar0 + 8u * (res_buf ^ 1), col0 + CHUNK_COLS, row0);
+          }
+        }
         float4 bv[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) bv[j] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -298,6 +337,13 @@ conv_igemm_kernel(const __grid_constant__ ConvKParams p) {
 #pragma unroll
           for (int i = 16; i < 32; ++i) v[i] = 0;
         }
+        if (res_tma) {
+          // consume this chunk's residual buffer even when the chunk is padding, to keep phases in step
+          mbar_wait(res_bar0 + 8u * res_buf, (res_phase >> res_buf) & 1u);
+          res_phase ^= 1u << res_buf;
+        }
+        const int cur_buf = res_buf;
+        res_buf ^= (res_tma ? 1 : 0);
         if (ncols <= 0) continue;  // warp-uniform
         float f[32];
 #pragma unroll
@@ -314,7 +360,13 @@ conv_igemm_kernel(const __grid_constant__ ConvKParams p) {
         }
         if (p.out_mode == ADB_OUT_BF16_NHWC) {
           // residual: 8-channel vectors lie fully inside cout (cout % 8 == 0)
-          if (res_pf) {
+          if (res_tma) {
+            // own row of the landed 32x32 residual sub-tile (64-byte swizzle: chunk ^= (row >> 1) & 3)
+            const uint8_t* rrow = epi_gen + 2048 * cur_buf + lane * 64;
+#pragma unroll
+            for (int g = 0; g < 4; ++g) rcur[g] = *reinterpret_cast<const uint4*>(rrow + ((g ^ ((lane >> 1) & 3)) << 4));
+          }
+          if (res_pf || res_tma) {
 #pragma unroll
             for (int g = 0; g < 4; ++g) {
               f[g * 8 + 0] += bf16_lo(rcur[g].x);
@@ -350,7 +402,24 @@ conv_igemm_kernel(const __grid_constant__ ConvKParams p) {
           uint32_t ow[16];  // this row's 32 outputs rounded to bf16, packed in pairs
 #pragma unroll
           for (int i = 0; i < 16; ++i) ow[i] = pack_bf16x2(f[2 * i], f[2 * i + 1]);
-          if (row_ok) {
+          if (p.tma_epi) {
+            // stage the warp's 32x32 bf16 sub-tile in shared memory (conflict-free with the 64-byte
+            // swizzle) and let ONE TMA store write it: row-strided per-thread 16-byte stores cost 32 LSU
+            // wavefronts per instruction and made small-K tiles epilogue-bound.
+            if (lane == 0) tma_store_wait_read0();  // previous store has finished reading the buffer
+            __syncwarp();
+            uint8_t* orow = epi_out_gen + lane * 64;
+#pragma unroll
+            for (int g = 0; g < 4; ++g)
+              *reinterpret_cast<uint4*>(orow + ((g ^ ((lane >> 1) & 3)) << 4)) =
+                  make_uint4(ow[4 * g], ow[4 * g + 1], ow[4 * g + 2], ow[4 * g + 3]);
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) {
+              tma_store_2d(&p.tmOut, epi_out, col0, row0);  // rows >= M and columns >= cout are clipped
+              tma_store_commit();
+            }
+          } else if (row_ok) {
             __nv_bfloat16* op = reinterpret_cast<__nv_bfloat16*>(p.out) + (size_t)m * p.cout + col0;
 #pragma unroll
             for (int g = 0; g < 4; ++g) {
@@ -444,6 +513,7 @@ conv_igemm_kernel(const __grid_constant__ ConvKParams p) {
     }
   }
 
+  if (warp < 8 && lane == 0 && p.tma_epi) tma_store_wait_all0();  // output stores of this warp are complete
   tc_fence_before();
   if (NCTA == 2) cluster_sync_all(); else __syncthreads();  // the peer may still be reading our smem / TMEM
   if (warp == MMA_WARP) {
@@ -561,6 +631,26 @@ int conv_igemm_submit(adb_plan* plan, const adb_conv_desc* d, cudaStream_t strea
     const uint32_t box[2] = {(uint32_t)BLOCK_K, (uint32_t)(block_n / ncta)};
     int r = make_tmap_bf16(&kp.tmW, d->weight, 2, dims, strides, box);
     if (r != ADB_OK) return r;
+  }
+  kp.tma_epi = (d->out_mode == ADB_OUT_BF16_NHWC && block_n >= 32) ? 1 : 0;
+  {
+    static int no_tma_epi = -1;
+    if (no_tma_epi < 0) {
+      const char* e = getenv("ADB_CONV_NO_TMA_EPI");
+      no_tma_epi = (e && e[0] == '1') ? 1 : 0;
+    }
+    if (no_tma_epi) kp.tma_epi = 0;
+  }
+  if (kp.tma_epi) {
+    const uint64_t dims[2] = {(uint64_t)d->cout, (uint64_t)M};
+    const uint64_t strides[1] = {(uint64_t)d->cout * 2};
+    const uint32_t box[2] = {32u, 32u};
+    int r = make_tmap_bf16(&kp.tmOut, d->out, 2, dims, strides, box, 64);
+    if (r != ADB_OK) return r;
+    if (d->res_mode == ADB_RES_SAME) {
+      r = make_tmap_bf16(&kp.tmRes, d->residual, 2, dims, strides, box, 64);
+      if (r != ADB_OK) return r;
+    }
   }
   kp.nseg = d->nseg;
   kp.M = (int)M;

@@ -51,7 +51,7 @@ static PFN_cuTensorMapEncodeTiled_v12000 get_encode_fn() {
 }
 
 int make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims,
-                   const uint64_t* strides_bytes, const uint32_t* box) {
+                   const uint64_t* strides_bytes, const uint32_t* box, int swizzle_bytes) {
   auto fn = get_encode_fn();
   if (!fn) {
     set_error("cuTensorMapEncodeTiled not available from the driver");
@@ -83,7 +83,8 @@ int make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t*
     }
   }
   CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base),
-                  gdim, gstr, bx, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                  gdim, gstr, bx, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B,
                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     set_error("cuTensorMapEncodeTiled failed with CUresult %d (rank %d dims %llu,%llu box %u,%u)",

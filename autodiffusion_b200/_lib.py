@@ -19,7 +19,7 @@ LIB_DIR = _PKG / "lib"
 LIB_PATH = LIB_DIR / "libadb200.so"
 HEADER = _PKG.parent / "include" / "adb200.h"
 
-SOURCES = ["host.cu", "conv_igemm.cu", "attention.cu", "groupnorm.cu", "elementwise.cu", "moments.cu"]
+SOURCES = ["host.cu", "conv_igemm.cu", "attention.cu", "attention2.cu", "groupnorm.cu", "elementwise.cu", "moments.cu"]
 
 NVCC_FLAGS = [
     "-O3",

@@ -270,7 +270,7 @@ int launch_attn(const AttnParams& ap, int b, cudaStream_t stream) {
 
 }  // namespace
 
-int attention_submit(adb_plan* plan, const void* qkv, void* out, int b, int t, int heads, int legacy_order,
+int attention_v1_submit(adb_plan* plan, const void* qkv, void* out, int b, int t, int heads, int legacy_order,
                      cudaStream_t stream) {
   ADB_REQUIRE(qkv && out && b > 0 && heads > 0, "attention: bad arguments");
   ADB_REQUIRE(t == 64 || (t >= 128 && t % 128 == 0), "attention: sequence length %d unsupported (64 or a multiple of 128)", t);

@@ -399,9 +399,10 @@ conv_igemm_kernel(const __grid_constant__ ConvKParams p) {
               }
             }
           }
-          uint32_t ow[16];  // this row's 32 outputs rounded to bf16, packed in pairs
+          uint32_t ow[16];  // this row's 32 outputs rounded to bf16, packed in pairs (zeros past M / cout)
 #pragma unroll
-          for (int i = 0; i < 16; ++i) ow[i] = pack_bf16x2(f[2 * i], f[2 * i + 1]);
+          for (int i = 0; i < 16; ++i)
+            ow[i] = (row_ok && 2 * i < ncols) ? pack_bf16x2(f[2 * i], f[2 * i + 1]) : 0u;
           if (p.tma_epi) {
             // stage the warp's 32x32 bf16 sub-tile in shared memory (conflict-free with the 64-byte
             // swizzle) and let ONE TMA store write it: row-strided per-thread 16-byte stores cost 32 LSU
@@ -430,29 +431,46 @@ conv_igemm_kernel(const __grid_constant__ ConvKParams p) {
           if (p.stats != nullptr) {
             // GroupNorm statistics of the tensor being written, for its consumer (nn.py:17-19): sum and
             // sum of squares of the STORED (bf16-rounded) values per (image, group of cpg channels).
-            // Column sums over the warp's 32 rows (pixels of one image: P % 32 == 0) by a transposing
-            // butterfly - 31 shuffles per quantity, independent chains - after which lane j owns
-            // column col0 + j. The columns go through a per-warp smem buffer and ONE lane per group
+            // Column sums over the warp's 32 rows (pixels of one image: P % 32 == 0): lane j owns column
+            // col0 + j (read back from the staged tile, or by a transposing shuffle butterfly when the
+            // tile is not staged). The columns go through a per-warp smem buffer and ONE lane per group
             // adds its group's columns into the warp's bin (no atomics: shared fp32 atomicAdd is a
             // CAS loop that serialises cpg-fold on these addresses).
             float sv[32], qv[32];
+            if (p.tma_epi) {
+              // the rounded tile is already staged in shared memory for the TMA store: lane j walks
+              // column j down the 32 rows (a row is 64 contiguous bytes: conflict-free)
+              float cs = 0.f, cq = 0.f;
+              const uint32_t cch = (uint32_t)lane >> 3, cin8 = ((uint32_t)lane & 7u) * 2u;
 #pragma unroll
-            for (int i = 0; i < 32; ++i) {
-              const float val = (row_ok && i < ncols) ? ((i & 1) ? bf16_hi(ow[i >> 1]) : bf16_lo(ow[i >> 1])) : 0.f;
-              sv[i] = val;
-              qv[i] = val * val;
-            }
+              for (int r = 0; r < 32; ++r) {
+                const uint16_t hv = *reinterpret_cast<const uint16_t*>(
+                    epi_out_gen + r * 64 + (((cch ^ ((uint32_t)(r >> 1) & 3u)) << 4) + cin8));
+                const float val = __uint_as_float((uint32_t)hv << 16);
+                cs += val;
+                cq = fmaf(val, val, cq);
+              }
+              sv[0] = cs;
+              qv[0] = cq;
+            } else {
 #pragma unroll
-            for (int off = 16, cnt = 16; off > 0; off >>= 1, cnt >>= 1) {
-              const bool upper = (lane & off) != 0;
+              for (int i = 0; i < 32; ++i) {
+                const float val = (i & 1) ? bf16_hi(ow[i >> 1]) : bf16_lo(ow[i >> 1]);
+                sv[i] = val;
+                qv[i] = val * val;
+              }
 #pragma unroll
-              for (int i = 0; i < cnt; ++i) {
-                const float s_keep = upper ? sv[i + cnt] : sv[i];
-                const float s_send = upper ? sv[i] : sv[i + cnt];
-                const float q_keep = upper ? qv[i + cnt] : qv[i];
-                const float q_send = upper ? qv[i] : qv[i + cnt];
-                sv[i] = s_keep + __shfl_xor_sync(0xffffffffu, s_send, off);
-                qv[i] = q_keep + __shfl_xor_sync(0xffffffffu, q_send, off);
+              for (int off = 16, cnt = 16; off > 0; off >>= 1, cnt >>= 1) {
+                const bool upper = (lane & off) != 0;
+#pragma unroll
+                for (int i = 0; i < cnt; ++i) {
+                  const float s_keep = upper ? sv[i + cnt] : sv[i];
+                  const float s_send = upper ? sv[i] : sv[i + cnt];
+                  const float q_keep = upper ? qv[i + cnt] : qv[i];
+                  const float q_send = upper ? qv[i] : qv[i + cnt];
+                  sv[i] = s_keep + __shfl_xor_sync(0xffffffffu, s_send, off);
+                  qv[i] = q_keep + __shfl_xor_sync(0xffffffffu, q_send, off);
+                }
               }
             }
             my_cols[lane] = sv[0];

@@ -10,6 +10,8 @@
 // (sample, group) — fp32 in registers over <= a few hundred values, fp64 across threads and
 // CTAs; pass 2 re-reads it (L2-resident for the per-sample slabs that fit) and writes the
 // normalised bf16 result: 2 B read (+2 B L2 re-read) + 2 B written per element.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace adb {
@@ -34,6 +36,7 @@ struct GnParams {
   __nv_bfloat16* out;
   double* stats;  // [n][32][2]
   int stats_ready;
+  int reverse;
   int splits;
 };
 
@@ -146,7 +149,9 @@ __global__ void __launch_bounds__(GN_THREADS) gn_apply_kernel(const GnParams p) 
   extern __shared__ float s_ab[];  // [2][C]
   float* s_a = s_ab;
   float* s_b = s_ab + p.C;
-  const int n = blockIdx.y;
+  // reverse traversal (last image / last pixels first): the input was just written front-to-back by
+  // its producer, so its tail is what is still resident in the 126 MB L2
+  const int n = p.reverse ? (int)(gridDim.y - 1 - blockIdx.y) : (int)blockIdx.y;
   const int V = p.C / 8;
   const int P = p.H * p.W;
   const int cpg = p.C / GN_GROUPS;
@@ -182,7 +187,7 @@ __global__ void __launch_bounds__(GN_THREADS) gn_apply_kernel(const GnParams p) 
   const int Ho = (p.resample == ADB_RESAMPLE_AVGPOOL2) ? p.H / 2 : p.H;
   const int PI = Ho * Wo;
   const int per = (PI + p.splits - 1) / p.splits;
-  const int p_begin = blockIdx.x * per;
+  const int p_begin = (p.reverse ? (int)(gridDim.x - 1 - blockIdx.x) : (int)blockIdx.x) * per;
   const int p_end = min(PI, p_begin + per);
 
   for (int v = threadIdx.x % slots; v < V; v += GN_THREADS) {
@@ -320,6 +325,14 @@ int groupnorm_submit(adb_plan* plan, const adb_gn_desc* d, cudaStream_t stream) 
   p.out = reinterpret_cast<__nv_bfloat16*>(d->out);
   p.stats = d->stats;
   p.stats_ready = d->stats_ready;
+  {
+    static int rev = -1;
+    if (rev < 0) {
+      const char* e = getenv("ADB_GN_REVERSE");
+      rev = (e && e[0] == '1') ? 1 : 0;
+    }
+    p.reverse = rev;
+  }
   const int P = d->h * d->w;
   int splits = (8 * num_sms() + d->n - 1) / d->n;
   const int max_splits = (P / 64) > 1 ? (P / 64) : 1;

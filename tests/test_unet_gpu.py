@@ -188,3 +188,37 @@ def test_schedule_plan_matches_generic_loop_and_evaluator_fid():
     fid2 = ev.get_cand_fid(cand)
     assert abs(fid2 - fid) <= 1e-3 * max(1.0, abs(fid))
     assert ev.is_legal(str(cand), log=lambda s: None) and not ev.is_legal(str(cand), log=lambda s: None)
+
+
+def test_lsun_style_unconditional_legacy_attention():
+    """Config-4 family (GD/search_lsun_bedroom.sh:1) at reduced width: unconditional, linear schedule,
+    QKVAttentionLegacy channel order (use_new_attention_order=False), channel_mult with repeated widths,
+    through create_model (UNetModel when use_dynamic_unet=False) - vs the CPU oracle."""
+    from autodiffusion_b200 import create_model_and_diffusion, model_and_diffusion_defaults
+    from autodiffusion_b200.dynamic_unet import Dynamic_UNetModel, UNetModel
+
+    flags = dict(attention_resolutions="16,8", class_cond=False, diffusion_steps=1000, dropout=0.1, image_size=64,
+                 learn_sigma=True, noise_schedule="linear", num_channels=64, num_head_channels=64, num_res_blocks=1,
+                 channel_mult="1,1,2,2", resblock_updown=True, use_fp16=True, use_scale_shift_norm=True)
+    cfg = unet_ref.UNetConfig(image_size=64, model_channels=64, num_res_blocks=1, attention_resolutions=(4, 8),
+                              channel_mult=(1, 1, 2, 2), num_classes=None, use_new_attention_order=False)
+    sd = weights.make_state_dict(unet_ref.param_shapes(cfg), seed=4)
+    d = model_and_diffusion_defaults()
+    d.update(flags)
+    x = torch.randn(3, 3, 64, 64, generator=torch.Generator().manual_seed(21))
+    t = torch.tensor([999, 500, 3])
+    for dyn in (False, True):
+        d["use_dynamic_unet"] = dyn
+        model, diffusion = create_model_and_diffusion(**d)
+        assert isinstance(model, Dynamic_UNetModel) and (dyn or isinstance(model, UNetModel))
+        assert {k: tuple(v.shape) for k, v in model.state_dict().items()} == unet_ref.param_shapes(cfg)
+        model.load_state_dict(sd)
+        model.cuda().eval()
+        out = model(x.cuda(), t.cuda()) if not dyn else model(x.cuda(), t.cuda(), None, skip_layer=[1, 4])
+        with torch.no_grad():
+            ref = unet_ref.unet_forward(sd, cfg, x, t, None, [] if not dyn else [1, 4])
+        rel_rms, mx, std = _report(f"lsun-style dyn={dyn}", out.cpu(), ref)
+        assert rel_rms <= 0.02 and mx <= 0.12 * std
+        with pytest.raises(AssertionError):
+            model(x.cuda(), t.cuda(), torch.zeros(3, dtype=torch.long).cuda())  # y given to an unconditional model
+    assert diffusion.num_timesteps == 1000 and abs(diffusion.betas[0] - 1e-4) < 1e-12

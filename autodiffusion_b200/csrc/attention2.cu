@@ -163,9 +163,15 @@ __global__ void __launch_bounds__(AT_THREADS, 2) attention2_kernel(const __grid_
       tmem_ld_32x32b_x32(s_addr, sr);
       tmem_ld_32x32b_x32(s_addr + 32, sr + 32);
       tmem_wait_ld();
-      float mx = -INFINITY;
+      // 8 independent max chains (a single 64-deep dependent chain costs ~250 cycles of latency that
+      // two resident warps per scheduler cannot hide)
+      float mxs[8];
 #pragma unroll
-      for (int i = 0; i < KT; ++i) mx = fmaxf(mx, __uint_as_float(sr[i]));
+      for (int i = 0; i < 8; ++i) mxs[i] = __uint_as_float(sr[i]);
+#pragma unroll
+      for (int i = 8; i < KT; ++i) mxs[i & 7] = fmaxf(mxs[i & 7], __uint_as_float(sr[i]));
+      const float mx = fmaxf(fmaxf(fmaxf(mxs[0], mxs[1]), fmaxf(mxs[2], mxs[3])),
+                             fmaxf(fmaxf(mxs[4], mxs[5]), fmaxf(mxs[6], mxs[7])));
       // Lazy rescaling: the reference maximum m_run only moves when the tile maximum exceeds it by
       // more than 8 (in log2 units), so p = exp2(s*sc - m_run) <= 256 stays comfortably inside
       // fp32/bf16 range while O and l need rescaling only on the rare big jumps (the final O / l
@@ -193,15 +199,19 @@ __global__ void __launch_bounds__(AT_THREADS, 2) attention2_kernel(const __grid_
         }
       }
       // p = exp2(s*sc - m_new) (one FFMA + one MUFU per element), row sum; bf16 P packed in place
-      float ps0 = 0.f, ps1 = 0.f;
+      float ps[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) ps[i] = 0.f;
 #pragma unroll
       for (int i = 0; i < KT / 2; ++i) {
         const float p0 = ex2_approx(fmaf(__uint_as_float(sr[2 * i]), sc, -m_new));
         const float p1 = ex2_approx(fmaf(__uint_as_float(sr[2 * i + 1]), sc, -m_new));
-        ps0 += p0;
-        ps1 += p1;
+        ps[(2 * i) & 7] += p0;
+        ps[(2 * i + 1) & 7] += p1;
         sr[i] = pack_bf16x2(p0, p1);
       }
+      const float ps0 = (ps[0] + ps[1]) + (ps[2] + ps[3]);
+      const float ps1 = (ps[4] + ps[5]) + (ps[6] + ps[7]);
       // P_j overwrites the head of S_j (all of S_j is in registers by now)
       tmem_st_32x32b_x32(s_addr, sr);
       l_run = l_run * alpha + (ps0 + ps1);

@@ -195,12 +195,11 @@ class _UNetPlan:
     """One recorded + graph-captured forward for a fixed (batch, H, W, skip set)."""
 
     def __init__(self, model: "Dynamic_UNetModel", B: int, H: int, W: int, skip: Tuple[int, ...]):
-        dev = model._device()
+        # every plan of one (B, H, W) shares the same input/output buffers, so a searched schedule can
+        # chain the cached per-mask graphs without copies (sampler.SchedulePlan)
+        io = model.io_buffers(B, H, W)
         self.model = model
-        self.x_in = th.zeros((B, model.in_channels, H, W), dtype=th.float32, device=dev)
-        self.t_in = th.zeros((B,), dtype=th.int64, device=dev)
-        self.y_in = th.zeros((B,), dtype=th.int64, device=dev) if model.num_classes is not None else None
-        self.out = th.empty((B, model.out_channels, H, W), dtype=th.float32, device=dev)
+        self.x_in, self.t_in, self.y_in, self.out = io.x_in, io.t_in, io.y_in, io.out
         self.plan = ops.Plan()
         self.graph: Optional[th.cuda.CUDAGraph] = None
         self.launches = 0
@@ -337,6 +336,7 @@ class Dynamic_UNetModel(nn.Module):
         self._packed_generation = -1
         self._packed: Dict[str, object] = {}
         self._plans: Dict[tuple, _UNetPlan] = {}
+        self._io: Dict[tuple, _IO] = {}
         self._pool: Optional[_Pool] = None
         self.gpu_launches = 0  # kernels launched through this model (bench.py reports it)
 
@@ -366,6 +366,19 @@ class Dynamic_UNetModel(nn.Module):
     def _invalidate(self):
         if hasattr(self, "_generation"):
             self._generation += 1
+
+    def io_buffers(self, B: int, H: int, W: int) -> _IO:
+        """Static input/output buffers shared by all plans of this geometry."""
+        key = (B, H, W, str(self._device()))
+        io = self._io.get(key)
+        if io is None:
+            dev = self._device()
+            io = _IO(th.zeros((B, self.in_channels, H, W), dtype=th.float32, device=dev),
+                     th.zeros((B,), dtype=th.int64, device=dev),
+                     th.zeros((B,), dtype=th.int64, device=dev) if self.num_classes is not None else None,
+                     th.empty((B, self.out_channels, H, W), dtype=th.float32, device=dev))
+            self._io[key] = io
+        return io
 
     def _device(self):
         return self.out[0].weight.device

@@ -10,10 +10,10 @@ launches around an ~800-launch eager UNet forward.
   * timesteps -> `set` -> ascending `timestep_map` and float64 tables (respace.reset_diffusion),
   * the skip list of step i is `skip_layers[i]` for the i-th SMALLEST timestep (the evaluator's
     sorted-rank indexing, :394-396), entries beyond K' unused,
-  * every step's UNet forward (skipped blocks elided) + fused guidance/DDIM update is recorded
-    into ONE plan, in sampling order K'-1 .. 0, and captured in ONE CUDA graph when there is no
-    caller-supplied `cond_fn`. With a `cond_fn` (an arbitrary torch callable returning
-    grad log p(y|x) * scale) the graph is cut at each step around that call.
+  * every step's UNet forward (skipped blocks elided; one cached CUDA graph per (batch, skip set)) +
+    fused guidance/DDIM update is chained in sampling order K'-1 .. 0 and captured in ONE CUDA graph
+    when there is no caller-supplied `cond_fn`. With a `cond_fn` (an arbitrary torch callable
+    returning grad log p(y|x) * scale) the chain is run step by step around that call.
   * the final `((x+1)*127.5).clamp(0,255).to(uint8)` NHWC pack (:421-423) is the last node.
 """
 from __future__ import annotations
@@ -52,7 +52,14 @@ def resolve_candidate(cand, base_diffusion, active_diffusion=None):
 
 
 class SchedulePlan:
-    """All K' steps of a candidate for a fixed batch, recorded once and replayed per batch."""
+    """All K' steps of a candidate for a fixed batch: cached per-mask UNet graphs chained into one graph.
+
+    Building one is cheap: a UNet forward is recorded (and graph-captured) once per (batch, skip set)
+    and cached on the model - most steps of most candidates share the empty mask - so a new candidate
+    only costs its K' coefficient sets, K' tiny nodes and the capture of the chain. All forwards use the
+    model's shared input/output buffers: the fused DDIM update writes x_{t-1} in place into the UNet's
+    input buffer.
+    """
 
     def __init__(self, model, active_diffusion, per_step_skips: Sequence[Sequence[int]], batch: int,
                  image_size: Optional[int] = None, clip_denoised: bool = True, cond_fn: Optional[Callable] = None,
@@ -75,90 +82,73 @@ class SchedulePlan:
         self.shape = (batch, model.in_channels, hw, hw)
         self.cond_fn = cond_fn
         self.class_cond = model.num_classes is not None
+        self.clip_denoised = clip_denoised
         if use_graph is None:
             use_graph = os.environ.get("ADB_NO_GRAPH", "0") != "1"
+        self.use_graph = use_graph
 
-        f32 = dict(dtype=th.float32, device=dev)
-        self.x = [th.zeros(self.shape, **f32), th.zeros(self.shape, **f32)]  # ping-pong x_t
-        self.y = th.zeros((batch,), dtype=th.int64, device=dev) if self.class_cond else None
-        self.model_out = th.empty((batch, model.out_channels, hw, hw), **f32)
-        self.grad = th.zeros(self.shape, **f32) if cond_fn is not None else None
-        self.t_tensors = [th.full((batch,), int(t), dtype=th.int64, device=dev) for t in self.timestep_map]
-        self.u8 = th.empty((batch, hw, hw, model.in_channels), dtype=th.uint8, device=dev) if pack_uint8 else None
-
-        # segments: with a cond_fn each step is [unet] -> cond_fn (eager torch) -> [ddim_step]
-        self.segments: List[ops.Plan] = []
-        self.graphs: List[Optional[th.cuda.CUDAGraph]] = []
-        self.launches = 0
-        cur = 0
-        order = list(range(self.K))[::-1]  # sampling runs high -> low (gaussian_diffusion.py:690)
+        self._order = list(range(self.K))[::-1]  # sampling runs high -> low (gaussian_diffusion.py:690)
         with th.no_grad():
-            plan = ops.Plan()
-            for n, i in enumerate(order):
-                model.record_forward(plan, self.x[cur], self.t_tensors[i], self.y, self.model_out,
-                                     self.per_step_skips[i])
-                if cond_fn is not None:
-                    self.segments.append(plan)
-                    plan = ops.Plan()
-                ops.ddim_step(self.x[cur], self.model_out, self.grad, ddim_coefficients(active_diffusion, i),
-                              clip_denoised, x_prev=self.x[1 - cur], plan=plan)
-                cur = 1 - cur
-            self.final = self.x[cur]
-            if self.u8 is not None:
-                ops.pack_uint8(self.final, out=self.u8, plan=plan)
-            self.segments.append(plan)
-            self._order = order
-            # validation run (sets kernel attributes) + capture
-            if cond_fn is None:
-                for seg in self.segments:
-                    self.launches += seg.run()
-                self.graphs = [self._capture(seg) if use_graph else None for seg in self.segments]
-            else:
-                self.graphs = [None] * len(self.segments)
-                self._use_graph = use_graph
-                self._captured = False
+            self.steps = [model.get_plan(batch, hw, hw, self.per_step_skips[i]) for i in self._order]
+        io = model.io_buffers(batch, hw, hw)
+        self.x, self.t_in, self.y, self.model_out = io.x_in, io.t_in, io.y_in, io.out
+        self.final = self.x  # x_0 ends up in the shared input buffer
+        self.coefs = [ddim_coefficients(active_diffusion, i) for i in self._order]
+        self.t_values = [int(self.timestep_map[i]) for i in self._order]
+        self.grad = th.zeros(self.shape, dtype=th.float32, device=dev) if cond_fn is not None else None
+        self.u8 = th.empty((batch, hw, hw, model.in_channels), dtype=th.uint8, device=dev) if pack_uint8 else None
+        self.launches = sum(up.launches for up in self.steps) + self.K + (1 if pack_uint8 else 0)
+        self.graph: Optional[th.cuda.CUDAGraph] = None
+        if cond_fn is None and use_graph:
+            th.cuda.current_stream().synchronize()
+            g = th.cuda.CUDAGraph()
+            with th.cuda.graph(g):
+                self._run_chain()
+            self.graph = g
 
-    @staticmethod
-    def _capture(seg: ops.Plan) -> th.cuda.CUDAGraph:
-        th.cuda.current_stream().synchronize()
-        g = th.cuda.CUDAGraph()
-        with th.cuda.graph(g):
-            seg.run()
-        return g
-
-    def _run_segment(self, k: int):
-        if self.graphs[k] is not None:
-            self.graphs[k].replay()
+    def _step(self, n: int):
+        """UNet forward of the n-th sampled step (cached graph as a child node when capturing)."""
+        self.t_in.fill_(self.t_values[n])  # original timestep, as _WrappedModel maps it (respace.py:122-127)
+        if th.cuda.is_current_stream_capturing():
+            self.steps[n].plan.run()  # re-issue the recorded launches into the schedule's own graph
         else:
-            n = self.segments[k].run()
-            if self.cond_fn is not None and not self._captured:
-                self.launches += n
+            self.steps[n].replay()
+
+    def _update(self, n: int):
+        ops.ddim_step(self.x, self.model_out, self.grad, self.coefs[n], self.clip_denoised, x_prev=self.x)
+
+    def _run_chain(self):
+        for n in range(self.K):
+            self._step(n)
+            self._update(n)
+        if self.u8 is not None:
+            ops.pack_uint8(self.final, out=self.u8)
 
     def run(self, noise: th.Tensor, y: Optional[th.Tensor] = None, model_kwargs: Optional[dict] = None) -> th.Tensor:
-        """x_T = noise (fp32 [B,C,H,W]), labels y -> x_0 (a view of an internal buffer; clone to keep)."""
+        """x_T = noise (fp32 [B,C,H,W]), labels y -> x_0 (a view of the shared buffer; clone to keep)."""
         assert tuple(noise.shape) == self.shape
-        self.x[0].copy_(noise, non_blocking=True)
+        self.x.copy_(noise, non_blocking=True)
         if self.class_cond:
             assert y is not None and y.shape == (self.B,)
             self.y.copy_(y, non_blocking=True)
+        self.model.gpu_launches += self.launches
         if self.cond_fn is None:
-            self._run_segment(0)
-            self.model.gpu_launches += self.launches
+            if self.graph is not None:
+                self.graph.replay()
+            else:
+                self._run_chain()
             return self.final
         kwargs = dict(model_kwargs or {})
         if self.class_cond:
             kwargs.setdefault("y", self.y)
-        cur = 0
-        for n, i in enumerate(self._order):
-            self._run_segment(n)  # UNet forward of step i (and the previous step's DDIM update)
-            g = self.cond_fn(self.x[cur], self.t_tensors[i], **kwargs)  # original timestep, as _WrappedModel passes it
+        for n in range(self.K):
+            self._step(n)
+            # caller-supplied guidance: grad log p(y|x_t) * scale at the ORIGINAL timestep
+            g = self.cond_fn(self.x, self.t_in, **kwargs)
             self.grad.copy_(g)
-            cur = 1 - cur
-        self._run_segment(len(self._order))
-        if not self._captured:
-            self._captured = True
-            if self._use_graph:
-                self.graphs = [self._capture(seg) for seg in self.segments]
+            self._update(n)
+        if self.u8 is not None:
+            ops.pack_uint8(self.final, out=self.u8)
         return self.final
 
 

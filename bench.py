@@ -231,7 +231,14 @@ def run_ours(args):
 
     B = args.batch
     active, per_step = resolve_candidate(CAND10, diffusion)
+    t_build = time.time()
     plan = SchedulePlan(model, active, per_step, B, clip_denoised=True, cond_fn=None, pack_uint8=True)
+    torch.cuda.synchronize()
+    t_build = time.time() - t_build
+    t_rebuild = time.time()
+    plan = SchedulePlan(model, active, per_step, B, clip_denoised=True, cond_fn=None, pack_uint8=True)  # cached masks
+    torch.cuda.synchronize()
+    t_rebuild = time.time() - t_rebuild
     launches_per_step = plan.launches
 
     g = torch.Generator(device=dev).manual_seed(1234 + rank)
@@ -298,16 +305,28 @@ def run_ours(args):
         "e2e": {"value": e2e_value, "unit": "images/s", "h2d_bytes_per_step": noise_host.numel() * 4 + y_host.numel() * 8,
                 "d2h_bytes_per_step": u8_host.numel()},
         "gpu_launches": launches_per_step * args.steps,
+        "plan_build_s": {"first_candidate": round(t_build, 3), "next_candidate_same_masks": round(t_rebuild, 4)},
         "clocks": clocks,
     }
 
     if rank == 0 and not args.no_roofline:
         # per-kernel times: the same recorded ops, eager on the current stream with an event pair around each
         pk = peaks()
-        seg = plan.segments[0]
-        info = seg.op_info()
-        seg.run_profiled()  # warm
-        ms_ops = seg.run_profiled()
+        # one sampled schedule = its K' cached UNet plans (+ the DDIM updates, timed as one event pair each)
+        info, ms_ops = [], []
+        for up in plan.steps:
+            up.plan.run_profiled()  # warm
+        for n, up in enumerate(plan.steps):
+            plan.t_in.fill_(plan.t_values[n])
+            info += up.plan.op_info()
+            ms_ops += up.plan.run_profiled()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            plan._update(n)
+            e1.record()
+            torch.cuda.synchronize()
+            info.append(("ddim_step", 0.0, 4.0 * 3 * plan.x.numel()))
+            ms_ops.append(e0.elapsed_time(e1))
         agg = {}
         for (kind, fl, by), t in zip(info, ms_ops):
             a = agg.setdefault(kind, [0, 0.0, 0.0, 0.0])

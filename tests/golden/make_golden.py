@@ -230,11 +230,63 @@ def gen_fid():
         linalg.sqrtm = real
 
 
+def gen_config1():
+    """BASELINE config 1: full ADM-G 64 + depth-4 classifier, 4-step searched schedule [153,424,926,690],
+    full architecture, classifier_scale 1.0, batch 8 - the reference's own ddim_sample_loop on CPU."""
+    import torch.nn.functional as F
+
+    model, diffusion = build(ADM_FLAGS)
+    cfg = cfg_of(ADM_FLAGS)
+    sd = weights.make_state_dict(unet_ref.param_shapes(cfg), seed=0)
+    model.load_state_dict(sd)
+    cd = classifier_defaults()
+    cd.update(classifier_depth=4)
+    clf = create_classifier(**cd).eval()
+    ccfg = unet_ref.classifier64_config(depth=4, width=128)
+    csd = weights.make_state_dict(unet_ref.param_shapes(ccfg, encoder_only=True), seed=1)
+    clf.load_state_dict(csd)
+    reset_diffusion = load_reset_diffusion()
+    base = copy.deepcopy(diffusion)
+    B = 8
+    noise = torch.randn(B, 3, 64, 64, generator=torch.Generator().manual_seed(2))
+    y = torch.randint(0, 1000, (B,), generator=torch.Generator().manual_seed(3))
+    cand = CANDIDATES["cand4"]
+    active = copy.deepcopy(base)
+    reset_diffusion(cand["timesteps"], active, base)
+
+    def cond_fn(x, t, y=None, skip_layers=None, timesteps=None):
+        with torch.enable_grad():
+            x_in = x.detach().requires_grad_(True)
+            logits = clf(x_in, t)
+            log_probs = F.log_softmax(logits, dim=-1)
+            selected = log_probs[range(len(logits)), y.view(-1)]
+            return torch.autograd.grad(selected.sum(), x_in)[0] * 1.0
+
+    def model_fn(x, t, y=None, skip_layers=None, timesteps=None):
+        t_index = active.timestep_map.index(t[0])
+        return model(x, t, y, skip_layer=skip_layers[t_index])
+
+    import time
+    t0 = time.time()
+    imgs = active.ddim_sample_loop(model_fn, (B, 3, 64, 64), noise=noise, clip_denoised=True,
+                                   model_kwargs={"y": y, "skip_layers": cand["skip_layers"]}, cond_fn=cond_fn,
+                                   device="cpu", return_all_images=True)
+    print(f"config1 reference: {time.time() - t0:.1f} s for {B} images; final std {imgs[-1].std():.4f}")
+    np.savez_compressed(os.path.join(HERE, "config1_admg64_guided.npz"), noise=noise.numpy(), y=y.numpy(),
+                        timesteps=np.array(cand["timesteps"], dtype=np.int64), final=imgs[-1].numpy(),
+                        step1=imgs[1].numpy(),
+                        uint8=((imgs[-1] + 1) * 127.5).clamp(0, 255).to(torch.uint8).permute(0, 2, 3, 1).contiguous().numpy())
+
+
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "config1":
+        gen_config1()
+        sys.exit(0)
     torch.manual_seed(0)
     gen_tables()
     gen_fid()
     gen_unet("small", SMALL_FLAGS, 2, [(676, []), (85, [0, 1, 3, 4, 5, 9, 11, 12, 13, 15]), (971, [2, 6, 7, 8, 10, 14, 16, 17])])
     gen_ddim_small()
     gen_unet("admg64", ADM_FLAGS, 1, [(153, []), (676, [30, 10, 39, 4, 15, 46, 49, 54, 8])])
+    gen_config1()
     print("done")

@@ -222,3 +222,83 @@ def test_lsun_style_unconditional_legacy_attention():
         with pytest.raises(AssertionError):
             model(x.cuda(), t.cuda(), torch.zeros(3, dtype=torch.long).cuda())  # y given to an unconditional model
     assert diffusion.num_timesteps == 1000 and abs(diffusion.betas[0] - 1e-4) < 1e-12
+
+
+def test_config1_full_admg64_guided_matches_reference():
+    """BASELINE.json configs[0]: ADM-G ImageNet-64 (295.9 M params), 4-step searched schedule
+    [153,424,926,690], full architecture, classifier guidance (scale 1.0), batch 8 - final samples vs the
+    reference's own CPU run (tests/golden/config1_admg64_guided.npz). The classifier is the caller's
+    (here: the oracle's EncoderUNetModel restatement executed by torch on the GPU in fp32)."""
+    from autodiffusion_b200.respace import reset_diffusion
+    from autodiffusion_b200.sampler import SchedulePlan, resolve_candidate
+
+    g = golden("config1_admg64_guided.npz")
+    cfg, sd = oracle_weights(ADM_FLAGS)
+    model, diffusion = build_ours(ADM_FLAGS, sd)
+    ccfg = unet_ref.classifier64_config(depth=4, width=128)
+    csd = {k: v.cuda() for k, v in weights.make_state_dict(unet_ref.param_shapes(ccfg, encoder_only=True), seed=1).items()}
+    cond_fn = unet_ref.classifier_cond_fn(csd, ccfg, 1.0)
+    ts = g["timesteps"].tolist()
+    skips = [[] for _ in ts]
+    base = copy.deepcopy(diffusion)
+    active = reset_diffusion(ts, copy.deepcopy(diffusion), base)
+    assert active.timestep_map == [153, 424, 690, 926]
+
+    def model_fn(x, t, y=None, skip_layers=None, timesteps=None):
+        return model(x, t, y, skip_layer=skip_layers[active.timestep_map.index(t[0])])
+
+    noise, y = torch.from_numpy(g["noise"]).cuda(), torch.from_numpy(g["y"]).cuda()
+    outs = active.ddim_sample_loop(model_fn, tuple(noise.shape), noise=noise, clip_denoised=True,
+                                   model_kwargs={"y": y, "skip_layers": skips}, cond_fn=cond_fn,
+                                   device=torch.device("cuda"), return_all_images=True)
+    final, ref = outs[-1].cpu(), torch.from_numpy(g["final"])
+    p = psnr(final, ref)
+    print(f"config1 (generic loop): max_abs={(final - ref).abs().max().item():.4g} psnr={p:.2f} dB; "
+          f"step1 max_abs={(outs[1].cpu() - torch.from_numpy(g['step1'])).abs().max().item():.4g}")
+    assert p >= 30.0
+    act2, per_step = resolve_candidate({"timesteps": ts, "skip_layers": skips}, base)
+    plan = SchedulePlan(model, act2, per_step, noise.shape[0], cond_fn=cond_fn, pack_uint8=True)
+    out2 = plan.run(noise, y).clone().cpu()
+    p2 = psnr(out2, ref)
+    d8 = np.abs(plan.u8.cpu().numpy().astype(np.int32) - g["uint8"].astype(np.int32))
+    print(f"config1 (SchedulePlan): psnr={p2:.2f} dB; uint8 max diff {d8.max()} LSB, mean {d8.mean():.3f}, "
+          f"pixels within 1 LSB: {(d8 <= 1).mean() * 100:.1f}%")
+    assert p2 >= 30.0
+
+
+def test_fid_of_a_fixed_candidate_within_tolerance_of_the_oracle():
+    """North-star bar: FID of a fixed candidate within +-0.1 of the reference. The Inception graph is not
+    available offline, so both sides use the same fixed 64-d random-projection feature extractor: FID of
+    our 64 samples vs FID of the oracle's 64 samples (same noise / labels), against the same reference
+    statistics."""
+    from autodiffusion_b200.evaluator import FIDStatistics, MomentAccumulator
+    from autodiffusion_b200.sampler import sample_candidate
+    from oracle import fid_ref
+
+    cfg, sd = oracle_weights(SMALL_FLAGS)
+    model, diffusion = build_ours(SMALL_FLAGS, sd)
+    cand = {"timesteps": [153, 424, 926, 690], "skip_layers": [[], [4], [], [9, 12]]}
+    N = 64
+    noise = torch.randn(N, 3, 64, 64, generator=torch.Generator().manual_seed(31))
+    y = torch.randint(0, 1000, (N,), generator=torch.Generator().manual_seed(32))
+    ours = sample_candidate(model, diffusion, cand, (N, 3, 64, 64), noise.cuda(), y.cuda()).cpu()
+    base = diffusion_ref.base_tables("cosine", 1000)
+    tmap, nb = diffusion_ref.respace(base["alphas_cumprod"], cand["timesteps"])
+    tb = diffusion_ref.diffusion_tables(nb)
+    unet = lambda x, t, yy, skip: unet_ref.unet_forward(sd, cfg, x, t, yy, skip)
+    ref = diffusion_ref.ddim_sample_loop(diffusion_ref.make_model_fn(unet, tmap), noise.shape, tb, tmap, noise, True,
+                                         model_kwargs={"y": y, "skip_layers": cand["skip_layers"]})
+    proj = torch.randn(3 * 64 * 64, 32, generator=torch.Generator().manual_seed(33)) * (3.0 / (3 * 64 * 64) ** 0.5)
+    feat = lambda s: ((diffusion_ref.pack_uint8(s).reshape(N, -1).float() / 255.0 - 0.5) @ proj)  # O(1) features
+    # reference statistics of a nearby distribution, so the FID is O(1-10) as in a real search
+    ref_stats = fid_ref.compute_statistics(feat(ref).double().numpy() * 1.15 + 0.2)
+    f_ref = feat(ref).double().numpy()
+    fid_ref_side = fid_ref.frechet_distance(*fid_ref.compute_statistics(f_ref), *ref_stats)
+    acc = MomentAccumulator(32, "cuda")
+    acc.add(feat(ours).cuda())
+    mu, sigma = acc.statistics()
+    fid_ours = float(FIDStatistics(mu, sigma).frechet_distance(FIDStatistics(*ref_stats)))
+    rel = abs(fid_ours - fid_ref_side) / abs(fid_ref_side)
+    print(f"FID ours={fid_ours:.4f} oracle={fid_ref_side:.4f} |diff|={abs(fid_ours - fid_ref_side):.4f} ({rel * 100:.3f}%) "
+          f"sample psnr={psnr(ours, ref):.1f} dB")
+    assert abs(fid_ours - fid_ref_side) <= 0.1

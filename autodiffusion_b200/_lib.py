@@ -101,6 +101,9 @@ class ConvDesc(C.Structure):
         ("out", C.c_void_p),
         ("out_mode", C.c_int),
         ("stats_out", C.c_void_p),
+        ("stats2_out", C.c_void_p),
+        ("stats2_cpg", C.c_int),
+        ("stats2_choff", C.c_int),
     ]
 
 

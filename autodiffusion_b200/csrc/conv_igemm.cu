@@ -54,8 +54,13 @@ struct ConvKParams {
   int res_mode;
   void* out;
   int out_mode;
-  double* stats;  // optional [n][32][2] GroupNorm sums of the output, or nullptr
-  int cpg;        // channels per group = cout / 32
+  double* stats;   // optional [n][32][2] GroupNorm sums of the output, or nullptr
+  int cpg;         // channels per group = cout / 32
+  // second, optional target: the GroupNorm of a consumer that reads this tensor as channels
+  // [choff2, choff2 + cout) of a concat (dynamic_unet.py:699) whose groups are cpg2 channels wide
+  double* stats2;
+  int cpg2;
+  int choff2;
 };
 
 template <int BLOCK_N, int NCTA>
@@ -92,7 +97,7 @@ conv_igemm_kernel(const __grid_constant__ ConvKParams p) {
   // barriers: full[STAGES], empty[STAGES], tmem_full[2], tmem_empty[2]
   __shared__ __align__(8) uint64_t bars[2 * STAGES + 4];
   __shared__ uint32_t tmem_slot_s;
-  __shared__ float stat_bins[8][STAT_BINS][2];
+  __shared__ float stat_bins[8][2 * STAT_BINS][2];  // [warp][target 0 | target 1]
   __shared__ float stat_cols[8][64];  // per epilogue warp: column sums / sums of squares of one chunk
   __shared__ __align__(8) uint64_t res_bars[8][2];  // per epilogue warp: residual TMA landed (2 buffers)
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;  // SWIZZLE_128B atoms
@@ -254,8 +259,9 @@ conv_igemm_kernel(const __grid_constant__ ConvKParams p) {
     const uint32_t res_bar0 = smem_u32(&res_bars[ew][0]);
     uint32_t res_phase = 0u;  // bit b = parity to wait for on residual buffer b
     int res_buf = 0;
+    float* my_bins2 = my_bins + 2 * STAT_BINS;
     if (p.stats != nullptr) {
-      for (int i = lane; i < STAT_BINS * 2; i += 32) my_bins[i] = 0.f;
+      for (int i = lane; i < STAT_BINS * 4; i += 32) my_bins[i] = 0.f;
       __syncwarp();
     }
     int acc = 0;
@@ -274,6 +280,7 @@ conv_igemm_kernel(const __grid_constant__ ConvKParams p) {
       const int y = rem / p.W;
       const int x = rem - y * p.W;
       const int g_lo = (p.stats != nullptr) ? (n0 + cbeg) / p.cpg : 0;
+      const int g_lo2 = (p.stats2 != nullptr) ? (p.choff2 + n0 + cbeg) / p.cpg2 : 0;
       // single-source residuals (same / nearest-up) are fetched one chunk AHEAD so their HBM
       // latency overlaps the previous chunk's math; the 4-source average-pool variant is not.
       const bool res_tma = p.tma_epi && p.res_mode == ADB_RES_SAME;  // warp-uniform
@@ -489,6 +496,21 @@ conv_igemm_kernel(const __grid_constant__ ConvKParams p) {
               my_bins[2 * (gmine - g_lo)] += gs;
               my_bins[2 * (gmine - g_lo) + 1] += gq;
             }
+            if (p.stats2 != nullptr) {
+              const int c2 = p.choff2 + col0;  // this chunk's first column in the consumer's concat
+              const int g2 = c2 / p.cpg2 + lane;
+              const int lo2 = max(g2 * p.cpg2, c2) - c2;
+              const int hi2 = min((g2 + 1) * p.cpg2, c2 + ncols) - c2;
+              if (lo2 < hi2) {
+                float gs = 0.f, gq = 0.f;
+                for (int j = lo2; j < hi2; ++j) {
+                  gs += my_cols[j];
+                  gq += my_cols[32 + j];
+                }
+                my_bins2[2 * (g2 - g_lo2)] += gs;
+                my_bins2[2 * (g2 - g_lo2) + 1] += gq;
+              }
+            }
             __syncwarp();
           }
         } else if (row_ok) {
@@ -524,6 +546,19 @@ conv_igemm_kernel(const __grid_constant__ ConvKParams p) {
             double* sp = p.stats + ((size_t)img0 * 32 + (g_lo + gb)) * 2;
             atomicAdd(sp, (double)bs);
             atomicAdd(sp + 1, (double)bq);
+          }
+        }
+        if (p.stats2 != nullptr) {
+          const int ng2 = (col_last >= n0 + cbeg) ? ((p.choff2 + col_last) / p.cpg2 - g_lo2 + 1) : 0;
+          for (int gb = lane; gb < ng2; gb += 32) {
+            const float bs = my_bins2[2 * gb], bq = my_bins2[2 * gb + 1];
+            my_bins2[2 * gb] = 0.f;
+            my_bins2[2 * gb + 1] = 0.f;
+            if (any_row) {
+              double* sp = p.stats2 + ((size_t)img0 * 32 + (g_lo2 + gb)) * 2;
+              atomicAdd(sp, (double)bs);
+              atomicAdd(sp + 1, (double)bq);
+            }
           }
         }
         __syncwarp();
@@ -684,6 +719,14 @@ int conv_igemm_submit(adb_plan* plan, const adb_conv_desc* d, cudaStream_t strea
   kp.out_mode = d->out_mode;
   kp.stats = d->stats_out;
   kp.cpg = d->cout / 32;
+  kp.stats2 = d->stats2_out;
+  kp.cpg2 = d->stats2_cpg;
+  kp.choff2 = d->stats2_choff;
+  if (d->stats2_out != nullptr) {
+    ADB_REQUIRE(d->stats_out != nullptr && d->stats2_cpg > 0 && d->stats2_choff >= 0 &&
+                    d->stats2_choff + d->cout <= 32 * d->stats2_cpg && 96 / d->stats2_cpg + 2 <= STAT_BINS,
+                "conv_igemm: stats2 needs stats_out and a concat grouping that contains this tensor");
+  }
   if (d->stats_out != nullptr) {
     ADB_REQUIRE(d->out_mode == ADB_OUT_BF16_NHWC && d->cout % 32 == 0 && P % 32 == 0,
                 "conv_igemm: stats_out needs bf16 output, cout %% 32 == 0 and h*w %% 32 == 0");

@@ -484,26 +484,53 @@ class Dynamic_UNetModel(nn.Module):
         # GroupNorm sums accumulated by the PRODUCING conv's epilogue (one slot per conv output that a
         # single-source GroupNorm will read); the whole arena is zeroed by one memset per forward.
         fuse_stats = os.environ.get("ADB_NO_FUSED_STATS", "0") != "1" and (H * W) % 32 == 0
-        arena = th.empty((2 * self.layer_num + 4, B, 32, 2), dtype=th.float64, device=dev)
+        # which conv outputs are later read as one half of a channel concat by a GroupNorm: decided by a
+        # symbolic pre-walk, so that producer can also accumulate sums in the concat's group layout
+        cat_uses, n_cat = self._plan_concat_stats(H, W, skip, fuse_stats)
+        n_slots = 2 * self.layer_num + 4
+        arena = th.empty((n_slots + n_cat, B, 32, 2), dtype=th.float64, device=dev)
         slot = [0]
+        prod_idx = [0]
         produced: Dict[int, th.Tensor] = {}  # data_ptr of an activation -> its producer-filled stats
-        ctx.on_alloc = lambda t: produced.pop(t.data_ptr(), None)  # a recycled buffer has no stats yet
+        produced_tag: Dict[int, int] = {}    # data_ptr -> production index (for concat lookups)
+
+        def _forget(t):
+            produced.pop(t.data_ptr(), None)
+            produced_tag.pop(t.data_ptr(), None)
+
+        ctx.on_alloc = _forget  # a recycled buffer has no stats yet
         if fuse_stats:
             ops.memset0(arena, plan=plan)
 
         def new_stats(t: th.Tensor):
-            """Stats slot for conv output `t` (None when fusion is off or the geometry does not allow it)."""
+            """-> kwargs for conv_igemm: stats slot(s) for conv output `t` ({} when fusion is off or the
+            geometry does not allow it). Must be called in the same order as _plan_concat_stats counts."""
             if not fuse_stats or t.shape[3] % 32 != 0 or (t.shape[1] * t.shape[2]) % 32 != 0:
-                produced.pop(t.data_ptr(), None)
-                return None
+                _forget(t)
+                return {}
             st = arena[slot[0]]
             slot[0] += 1
+            p = prod_idx[0]
+            prod_idx[0] += 1
             produced[t.data_ptr()] = st
-            return st
+            produced_tag[t.data_ptr()] = p
+            kw = {"stats_out": st}
+            use = cat_uses.get(p)
+            if use is not None:
+                cslot, choff, cpg = use
+                kw["stats2"] = (arena[n_slots + cslot], cpg, choff)
+            return kw
 
         def gn(srcs, gamma, beta, out_t, **kw):
-            """GroupNorm reading producer-filled sums when its single source has them."""
-            st = produced.get(srcs[0].data_ptr()) if len(srcs) == 1 else None
+            """GroupNorm reading producer-filled sums when its source(s) have them."""
+            st = None
+            if len(srcs) == 1:
+                st = produced.get(srcs[0].data_ptr())
+            else:
+                p0, p1 = produced_tag.get(srcs[0].data_ptr()), produced_tag.get(srcs[1].data_ptr())
+                u0, u1 = cat_uses.get(p0), cat_uses.get(p1)
+                if u0 is not None and u1 is not None and u0[0] == u1[0] and u0[1] == 0 and u1[1] == srcs[0].shape[3]:
+                    st = arena[n_slots + u0[0]]
             ops.groupnorm(srcs[0], gamma, beta, src1=srcs[1] if len(srcs) > 1 else None, out=out_t,
                           stats=st if st is not None else stats, stats_ready=st is not None, plan=plan, **kw)
 
@@ -522,7 +549,7 @@ class Dynamic_UNetModel(nn.Module):
             if layer.layer_id in skip:  # dynamic_unet.py:246-249
                 if updown:
                     o = ctx.alloc((n, h * 2, w * 2, cout) if layer.up else (n, h // 2, w // 2, cout))
-                    produced.pop(o.data_ptr(), None)
+                    _forget(o)
                     return ops.resample2x(srcs[0], ops.RESAMPLE_NEAREST2 if layer.up else ops.RESAMPLE_AVGPOOL2,
                                           out=o, plan=plan)
                 if pk.ws_raw is None:
@@ -530,15 +557,14 @@ class Dynamic_UNetModel(nn.Module):
                     return srcs[0]
                 wsk = self._w2_skip_only(layer, tuple(s.shape[3] for s in srcs))
                 o = ctx.alloc((n, h, w, cout))
-                return ops.conv_igemm([(s, 1) for s in srcs], wsk, pk.bskip, cout, out=o, plan=plan,
-                                      stats_out=new_stats(o))
+                return ops.conv_igemm([(s, 1) for s in srcs], wsk, pk.bskip, cout, out=o, plan=plan, **new_stats(o))
             ho, wo = (h * 2, w * 2) if layer.up else ((h // 2, w // 2) if layer.down else (h, w))
             mode = ops.RESAMPLE_NEAREST2 if layer.up else (ops.RESAMPLE_AVGPOOL2 if layer.down else ops.RESAMPLE_NONE)
             cin = sum(s.shape[3] for s in srcs)
             g1 = ctx.alloc((n, ho, wo, cin))
             gn(srcs, pk.g1, pk.be1, g1, silu=True, resample=mode)
             c1 = ctx.alloc((n, ho, wo, cout))
-            ops.conv_igemm([(g1, 9)], pk.w1, pk.b1, cout, out=c1, plan=plan, stats_out=new_stats(c1))
+            ops.conv_igemm([(g1, 9)], pk.w1, pk.b1, cout, out=c1, plan=plan, **new_stats(c1))
             ctx.release(g1)
             g2 = ctx.alloc((n, ho, wo, cout))
             gn([c1], pk.g2, pk.be2, g2, scale_shift=(ss_all, pk.ss_off), ss_stride=ss_total, silu=True)
@@ -547,12 +573,12 @@ class Dynamic_UNetModel(nn.Module):
             if pk.ws_raw is not None:
                 w2 = self._w2_for(layer, tuple(s.shape[3] for s in srcs))
                 ops.conv_igemm([(g2, 9)] + [(s, 1) for s in srcs], w2, pk.b2, cout, out=out, plan=plan,
-                               stats_out=new_stats(out))
+                               **new_stats(out))
             else:
                 w2 = self._w2_for(layer, ())
                 rm = ops.RES_NEAREST2 if layer.up else (ops.RES_AVGPOOL2 if layer.down else ops.RES_SAME)
                 ops.conv_igemm([(g2, 9)], w2, pk.b2, cout, out=out, residual=srcs[0], res_mode=rm, plan=plan,
-                               stats_out=new_stats(out))
+                               **new_stats(out))
             ctx.release(g2)
             return out
 
@@ -574,7 +600,7 @@ class Dynamic_UNetModel(nn.Module):
             ctx.release(qkv)
             out = ctx.alloc((n, h, w, c))
             ops.conv_igemm([(a, 1)], pk.wproj, pk.bproj, c, out=out, residual=x, res_mode=ops.RES_SAME, plan=plan,
-                           stats_out=new_stats(out))
+                           **new_stats(out))
             ctx.release(a)
             return out
 
@@ -589,7 +615,7 @@ class Dynamic_UNetModel(nn.Module):
 
         ch0 = int(self.channel_mult[0] * mc)
         h = ctx.alloc((B, H, W, ch0))
-        produced.pop(h.data_ptr(), None)
+        _forget(h)
         ops.stem_conv(up.x_in, P["stem_w"], P["stem_b"], out=h, plan=plan)
         hs = [h]
         ctx.retain(h)  # one reference for hs, one for the running h
@@ -606,6 +632,68 @@ class Dynamic_UNetModel(nn.Module):
         ops.conv_igemm([(g, 9)], P["out_w"], P["out_b"], self.out_channels, out=up.out,
                        out_mode=ops.OUT_F32_NCHW, plan=plan)
         ctx.release(g)
+
+    def _plan_concat_stats(self, H: int, W: int, skip: set, fuse_stats: bool):
+        """Symbolic twin of the walk in record_forward: numbers every stats-producing conv output in
+        production order and returns {production index: (concat slot, channel offset, channels per group)}
+        for those later consumed as one half of `th.cat([h, hs.pop()], 1)` by a (non-skipped) ResBlock's
+        first GroupNorm, plus the number of concat slots."""
+        uses: Dict[int, Tuple[int, int, int]] = {}
+        if not fuse_stats:
+            return uses, 0
+        counter = [0]
+        n_cat = [0]
+
+        class T:  # symbolic activation
+            __slots__ = ("tag", "c", "h", "w")
+
+            def __init__(self, tag, c, h, w):
+                self.tag, self.c, self.h, self.w = tag, c, h, w
+
+        def produce(c, h, w):
+            if c % 32 != 0 or (h * w) % 32 != 0:
+                return T(None, c, h, w)
+            t = T(counter[0], c, h, w)
+            counter[0] += 1
+            return t
+
+        def res(layer, srcs):
+            s0 = srcs[0]
+            cout = layer.out_channels
+            if layer.layer_id in skip:
+                if layer.up or layer.down:
+                    return T(None, cout, s0.h * 2 if layer.up else s0.h // 2, s0.w * 2 if layer.up else s0.w // 2)
+                if not isinstance(layer.skip_connection, nn.Conv2d):
+                    return s0
+                return produce(cout, s0.h, s0.w)
+            ho, wo = (s0.h * 2, s0.w * 2) if layer.up else ((s0.h // 2, s0.w // 2) if layer.down else (s0.h, s0.w))
+            if len(srcs) == 2 and srcs[0].tag is not None and srcs[1].tag is not None:
+                cpg = (srcs[0].c + srcs[1].c) // 32
+                if 96 // cpg + 2 <= 40:
+                    k = n_cat[0]
+                    n_cat[0] += 1
+                    uses[srcs[0].tag] = (k, 0, cpg)
+                    uses[srcs[1].tag] = (k, srcs[0].c, cpg)
+            produce(cout, ho, wo)          # conv1 output
+            return produce(cout, ho, wo)   # block output
+
+        def attn(layer, x):
+            return x if layer.layer_id in skip else produce(x.c, x.h, x.w)
+
+        def block(blk, srcs):
+            for layer in blk.children():
+                srcs = [res(layer, srcs) if isinstance(layer, ResBlock) else attn(layer, srcs[0])]
+            return srcs[0]
+
+        h = T(None, int(self.channel_mult[0] * self.model_channels), H, W)  # stem output: no producer stats
+        hs = [h]
+        for blk in list(self.input_blocks)[1:]:
+            h = block(blk, [h])
+            hs.append(h)
+        h = block(self.middle_block, [h])
+        for blk in self.output_blocks:
+            h = block(blk, [h, hs.pop()])
+        return uses, n_cat[0]
 
     def _w2_skip_only(self, layer: ResBlock, split: Tuple[int, ...]) -> th.Tensor:
         key = (id(layer), "skip", split)

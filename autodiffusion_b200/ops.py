@@ -147,9 +147,11 @@ def conv_igemm(
     out_mode: int = OUT_BF16_NHWC,
     plan: Optional[Plan] = None,
     stats_out: Optional[torch.Tensor] = None,
+    stats2: Optional[tuple] = None,
 ) -> torch.Tensor:
     """segs: [(act[n,h,w,cin] bf16, taps), ...]; weight from `pack_conv_weight`.
-    stats_out: optional zeroed fp64 [n,32,2]; the epilogue adds the output's GroupNorm sums to it."""
+    stats_out: optional zeroed fp64 [n,32,2]; the epilogue adds the output's GroupNorm sums to it.
+    stats2: optional (fp64 [n,32,2], cpg, channel offset) - sums for a consumer GroupNorm over a concat."""
     act0 = segs[0][0]
     n, h, w = act0.shape[0], act0.shape[1], act0.shape[2]
     d = _lib.ConvDesc()
@@ -178,9 +180,12 @@ def conv_igemm(
     d.out = _dev(out, "out")
     d.out_mode = out_mode
     d.stats_out = _opt(stats_out, "stats_out", torch.float64)
+    if stats2 is not None:
+        d.stats2_out = _dev(stats2[0], "stats2", torch.float64)
+        d.stats2_cpg, d.stats2_choff = int(stats2[1]), int(stats2[2])
     _lib.check(_lib.lib().adb_conv_igemm(_ph(plan), C.byref(d), _stream()), "adb_conv_igemm")
     if plan is not None:
-        plan.keep(*[s[0] for s in segs], weight, bias, residual, out, stats_out)
+        plan.keep(*[s[0] for s in segs], weight, bias, residual, out, stats_out, stats2[0] if stats2 else None)
     return out
 
 

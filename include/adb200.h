@@ -89,6 +89,11 @@ typedef struct {
   int out_mode;
   double* stats_out;    /* optional [n, 32, 2] fp64: the epilogue ADDS sum / sum-of-squares of the stored
                            output per (image, GroupNorm group of cout/32 channels); caller zeroes it */
+  double* stats2_out;   /* optional second target (requires stats_out): the GroupNorm of a consumer that reads
+                           this tensor as channels [stats2_choff, +cout) of a channel concat
+                           (dynamic_unet.py:699) with groups of stats2_cpg channels */
+  int stats2_cpg;
+  int stats2_choff;
 } adb_conv_desc;
 
 /* N tile the kernel uses for `cout` output channels; `cout_pad` must be a multiple of it. */

@@ -221,7 +221,10 @@ __global__ void __launch_bounds__(AT_THREADS, 2) attention2_kernel(const __grid_
       __syncwarp();
       if (lane == 0) mbar_arrive(bar(B_P_FULL + (j & 1)));
     }
-    // epilogue: O / l -> bf16
+    // epilogue: O / l -> bf16. Only PV_{nkt-3} is known complete here (S_{nkt-1} was issued after it), so
+    // the barrier may still be two phases behind: a parity wait is only unambiguous one phase ahead,
+    // hence wait for phase nkt-2 first, then nkt-1.
+    if (nkt >= 2) mbar_wait(bar(B_PV_DONE), (uint32_t)(nkt - 2) & 1u);
     mbar_wait(bar(B_PV_DONE), (uint32_t)(nkt - 1) & 1u);
     tc_fence_after();
     const float inv = 1.0f / l_run;

@@ -54,8 +54,8 @@ constexpr int B_KV_FULL = 1;                      // [KV_STAGES]
 constexpr int B_KV_EMPTY = B_KV_FULL + KV_STAGES; // [KV_STAGES]
 constexpr int B_S_FULL = B_KV_EMPTY + KV_STAGES;  // [2]
 constexpr int B_P_FULL = B_S_FULL + 2;            // [2]
-constexpr int B_PV_DONE = B_P_FULL + 2;
-constexpr int NUM_BARS = B_PV_DONE + 1;
+constexpr int B_PV_DONE = B_P_FULL + 2;            // [2]: PV_j commits to barrier j&1, phase j>>1
+constexpr int NUM_BARS = B_PV_DONE + 2;
 
 // TMEM columns: S0 [0,64) | S1 [64,128) | O [128,192); P_j (bf16x2, 32 columns) aliases the head of
 // S_(j&1). Double-buffered S lets S_{j+1} = Q K_{j+1}^T run on the tensor pipe while the softmax warps
@@ -144,7 +144,7 @@ __global__ void __launch_bounds__(AT_THREADS, 2) attention2_kernel(const __grid_
           umma_bf16_ts(tmem_base + O_COL, tmem_base + (j & 1) * KT + 8 * kk, b_desc, idesc_o, (j | kk) != 0);
         }
         umma_commit(bar(B_KV_EMPTY + st));  // K/V stage free
-        umma_commit(bar(B_PV_DONE));        // O stable up to tile j
+        umma_commit(bar(B_PV_DONE + (j & 1)));  // O stable up to tile j
       }
     }
   } else {
@@ -184,8 +184,10 @@ __global__ void __launch_bounds__(AT_THREADS, 2) attention2_kernel(const __grid_
         m_new = fmaxf(m_run, m_tile);
         alpha = ex2_approx(m_run - m_new);  // 0 on the first tile
         if (j > 0) {
-          // O may only be touched once PV_{j-1} has completed (S_j was issued before it)
-          mbar_wait(bar(B_PV_DONE), (uint32_t)(j - 1) & 1u);
+          // O may only be touched once PV_{j-1} has completed (S_j was issued before it). S_j being
+          // complete implies PV_{j-2} and everything before it is (one in-order pipe), so barrier
+          // (j-1)&1 is at most one phase behind the one waited for: the parity wait is unambiguous.
+          mbar_wait(bar(B_PV_DONE + ((j - 1) & 1)), (uint32_t)((j - 1) >> 1) & 1u);
           tc_fence_after();
 #pragma unroll 1
           for (int c = 0; c < HD; c += 32) {
@@ -221,11 +223,10 @@ __global__ void __launch_bounds__(AT_THREADS, 2) attention2_kernel(const __grid_
       __syncwarp();
       if (lane == 0) mbar_arrive(bar(B_P_FULL + (j & 1)));
     }
-    // epilogue: O / l -> bf16. Only PV_{nkt-3} is known complete here (S_{nkt-1} was issued after it), so
-    // the barrier may still be two phases behind: a parity wait is only unambiguous one phase ahead,
-    // hence wait for phase nkt-2 first, then nkt-1.
-    if (nkt >= 2) mbar_wait(bar(B_PV_DONE), (uint32_t)(nkt - 2) & 1u);
-    mbar_wait(bar(B_PV_DONE), (uint32_t)(nkt - 1) & 1u);
+    // epilogue: O / l -> bf16. PV_{nkt-3} is known complete here (S_{nkt-1} was issued after it); it is
+    // the previous phase of the barrier PV_{nkt-1} commits to, so this parity wait cannot alias: it
+    // neither passes early (barrier one phase behind) nor hangs (all PVs already complete).
+    mbar_wait(bar(B_PV_DONE + ((nkt - 1) & 1)), (uint32_t)((nkt - 1) >> 1) & 1u);
     tc_fence_after();
     const float inv = 1.0f / l_run;
     const bool ok = (q0 + row) < p.T;

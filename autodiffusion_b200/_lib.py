@@ -19,7 +19,8 @@ LIB_DIR = _PKG / "lib"
 LIB_PATH = LIB_DIR / "libadb200.so"
 HEADER = _PKG.parent / "include" / "adb200.h"
 
-SOURCES = ["host.cu", "conv_igemm.cu", "attention.cu", "attention2.cu", "groupnorm.cu", "elementwise.cu", "moments.cu"]
+SOURCES = ["host.cu", "conv_igemm.cu", "attention.cu", "attention2.cu", "groupnorm.cu", "elementwise.cu", "moments.cu",
+           "attention_bwd.cu", "backward.cu"]
 
 NVCC_FLAGS = [
     "-O3",
@@ -129,6 +130,29 @@ class GnDesc(C.Structure):
     ]
 
 
+class GnBwdDesc(C.Structure):
+    _fields_ = [
+        ("n", C.c_int),
+        ("h", C.c_int),
+        ("w", C.c_int),
+        ("c", C.c_int),
+        ("x", C.c_void_p),
+        ("stats", C.c_void_p),
+        ("gamma", C.c_void_p),
+        ("beta", C.c_void_p),
+        ("eps", C.c_float),
+        ("scale_shift", C.c_void_p),
+        ("ss_stride", C.c_int),
+        ("silu", C.c_int),
+        ("resample", C.c_int),
+        ("dout", C.c_void_p),
+        ("add", C.c_void_p),
+        ("add_mode", C.c_int),
+        ("dx", C.c_void_p),
+        ("bstats", C.c_void_p),
+    ]
+
+
 RES_NONE, RES_SAME, RES_AVGPOOL2, RES_NEAREST2 = 0, 1, 2, 3
 OUT_BF16_NHWC, OUT_F32_NCHW = 0, 1
 RESAMPLE_NONE, RESAMPLE_AVGPOOL2, RESAMPLE_NEAREST2 = 0, 1, 2
@@ -158,6 +182,14 @@ SYMBOLS = {
     "adb_pack_uint8": (_I, [_P, _P, _P, _I, _I, _I, _P]),
     "adb_moments_accumulate": (_I, [_P, _P, _I, _I, _P, _P, _P]),
     "adb_memset0": (_I, [_P, _P, C.c_size_t, _P]),
+    "adb_attention_lse": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _P]),
+    "adb_attention_backward": (_I, [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _P]),
+    "adb_gn_backward": (_I, [_P, C.POINTER(GnBwdDesc), _P]),
+    "adb_pool_prepare": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _P]),
+    "adb_pool_attention": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _P]),
+    "adb_pool_attention_backward": (_I, [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _P]),
+    "adb_pool_merge": (_I, [_P, _P, _P, _P, _I, _I, _I, _P]),
+    "adb_logsoftmax_grad": (_I, [_P, _P, _P, _P, _I, _I, C.c_float, _P]),
 }
 
 _lib = None

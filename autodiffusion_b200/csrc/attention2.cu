@@ -39,6 +39,7 @@ struct AttnParams {
   CUtensorMap tmQ;   // box {64, 128}
   CUtensorMap tmKV;  // box {64, KT}
   __nv_bfloat16* out;
+  float* lse;  // optional [b*heads, T]: log2-domain log-sum-exp of the scaled scores (for the backward pass)
   int T, heads, C;
   int legacy;
 };
@@ -230,6 +231,8 @@ __global__ void __launch_bounds__(AT_THREADS, 2) attention2_kernel(const __grid_
     tc_fence_after();
     const float inv = 1.0f / l_run;
     const bool ok = (q0 + row) < p.T;
+    // P_ij = exp2(s_ij * sc - lse): what attention_bwd.cu recomputes the probabilities from
+    if (p.lse != nullptr && ok) p.lse[(size_t)bh * p.T + q0 + row] = m_run + __log2f(l_run);
     __nv_bfloat16* orow = p.out + ((size_t)(row_base + q0 + row)) * p.C + h * HD;
 #pragma unroll 1
     for (int c = 0; c < HD; c += 32) {
@@ -275,14 +278,14 @@ int launch_attn2(const AttnParams& ap, int b, cudaStream_t stream) {
 int attention_v1_submit(adb_plan* plan, const void* qkv, void* out, int b, int t, int heads, int legacy_order,
                         cudaStream_t stream);
 
-int attention_submit(adb_plan* plan, const void* qkv, void* out, int b, int t, int heads, int legacy_order,
+int attention_submit(adb_plan* plan, const void* qkv, void* out, float* lse, int b, int t, int heads, int legacy_order,
                      cudaStream_t stream) {
   static int use_v1 = -1;
   if (use_v1 < 0) {
     const char* e = getenv("ADB_ATTENTION_V1");
     use_v1 = (e && e[0] == '1') ? 1 : 0;
   }
-  if (use_v1) return attention_v1_submit(plan, qkv, out, b, t, heads, legacy_order, stream);
+  if (use_v1 && lse == nullptr) return attention_v1_submit(plan, qkv, out, b, t, heads, legacy_order, stream);
   ADB_REQUIRE(qkv && out && b > 0 && heads > 0, "attention: bad arguments");
   ADB_REQUIRE(t == 64 || (t >= 128 && t % 128 == 0), "attention: sequence length %d unsupported (64 or a multiple of 128)", t);
   const int C = heads * HD;
@@ -298,6 +301,7 @@ int attention_submit(adb_plan* plan, const void* qkv, void* out, int b, int t, i
   r = make_tmap_bf16(&ap.tmKV, qkv, 2, dims, strides, boxkv);
   if (r != ADB_OK) return r;
   ap.out = reinterpret_cast<__nv_bfloat16*>(out);
+  ap.lse = lse;
   ap.T = t;
   ap.heads = heads;
   ap.C = C;

@@ -1,0 +1,474 @@
+// attention_bwd.cu — input-gradient of the fused softmax attention (head dim 64) on tcgen05 + TMEM.
+//
+// Needed by classifier guidance: the search's cond_fn differentiates log p(y | x_t) of the noisy
+// classifier w.r.t. x_t (search_dynamic_unet_imagenet64_classifier_guidance_progressive.py:383-390),
+// which back-propagates through every QKVAttentionLegacy / QKVAttention of the EncoderUNetModel
+// (guided_diffusion/unet.py:325-371; forward restated in attention2.cu).
+//
+// With S = (q s)(k s)^T, s = 64^-1/4, P = softmax(S), O = P V and the incoming dO:
+//   D_i  = sum_d dO_id O_id                       (attn_rowdot_kernel)
+//   dP   = dO V^T,  dS = P o (dP - D),            P recomputed from the forward's log-sum-exp
+//   dQ   = s^2 dS K        (attn_bwd_dq_kernel : one CTA per 128-query tile, loop over 64-key tiles)
+//   dK   = s^2 dS^T Q,  dV = P^T dO   (attn_bwd_dkv_kernel: one CTA per 128-key tile, loop over 64-query tiles)
+// Both kernels keep the structure of the forward kernel: operands by TMA straight out of the
+// [b*t, 3C] qkv matrix and the [b*t, C] dO matrix, the two score-shaped products of a step
+// (S and dP, or their transposes) accumulate in TMEM, the softmax warps turn them into bf16
+// P / dS *in place* in TMEM, and the gradient products take that as their A operand (TS form)
+// with the row-major K / Q / dO tiles as MN-major B operands - no transposes, no staging of P.
+// tcgen05.mma ops of one thread execute in order, which makes the in-place aliasing safe.
+#include <string.h>
+
+#include "common.cuh"
+
+namespace adb {
+
+namespace {
+
+constexpr int BW_THREADS = 192;  // warps 0-3: softmax / epilogue, warp 4: TMA, warp 5: MMA + TMEM
+constexpr int BM = 128;
+constexpr int HD = 64;
+constexpr int TN = 64;                  // inner tile (keys for dQ, queries for dK/dV)
+constexpr int BIG_BYTES = BM * HD * 2;  // 16 KiB
+constexpr int SMALL_BYTES = TN * HD * 2;  // 8 KiB
+constexpr int STAGES = 4;
+constexpr int TMEM_COLS = 256;
+constexpr int SMEM_BYTES = 2 * BIG_BYTES + STAGES * 2 * SMALL_BYTES + 1024;
+
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+// 1-D bulk copy global -> shared, completion on an mbarrier (size multiple of 16, 16-byte aligned)
+__device__ __forceinline__ void bulk_load_1d(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(dst), "l"(src), "r"(bytes), "r"(bar)
+               : "memory");
+}
+
+struct BwdParams {
+  CUtensorMap tmQKV128;  // qkv [b*t, 3C], box {64, 128}
+  CUtensorMap tmQKV64;   // qkv, box {64, 64}
+  CUtensorMap tmDO128;   // dO [b*t, C], box {64, 128}
+  CUtensorMap tmDO64;    // dO, box {64, 64}
+  const float* lse;      // [b*heads, T] log2-domain log-sum-exp from the forward
+  const float* dsum;     // [b*heads, T] D_i
+  __nv_bfloat16* dqkv;   // [b*t, 3C], same column layout as qkv
+  int T, heads, C, legacy;
+};
+
+// barrier indices (shared by both kernels)
+constexpr int B_BIG = 0;                        // the CTA's two resident 128-row tiles landed
+constexpr int B_FULL = 1;                       // [STAGES] inner tiles landed
+constexpr int B_EMPTY = B_FULL + STAGES;        // [STAGES]
+constexpr int B_SP = B_EMPTY + STAGES;          // score-shaped accumulators ready (phase = step)
+constexpr int B_PD = B_SP + 1;                  // bf16 P / dS written back to TMEM (4 warp arrivals)
+constexpr int B_DONE = B_PD + 1;                // all gradient MMAs complete
+constexpr int NUM_BARS = B_DONE + 1;
+
+// ---------------------------------------------------------------------------------------------
+// dQ: CTA = (128-query tile, batch*head). TMEM: S [0,64) | dP [64,128) | dQ [128,192).
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(BW_THREADS, 2) attn_bwd_dq_kernel(const __grid_constant__ BwdParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t bars[NUM_BARS];
+  __shared__ uint32_t tmem_slot_s;
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t q_smem = smem_base;
+  const uint32_t do_smem = smem_base + BIG_BYTES;
+  auto k_smem = [&](int st) { return smem_base + 2 * BIG_BYTES + st * 2 * SMALL_BYTES; };
+  auto v_smem = [&](int st) { return k_smem(st) + SMALL_BYTES; };
+  const uint32_t bar0 = smem_u32(bars);
+  auto bar = [&](int i) { return bar0 + 8u * i; };
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int bh = blockIdx.y;
+  const int b = bh / p.heads;
+  const int h = bh - b * p.heads;
+  const int q0 = blockIdx.x * BM;
+  const int row_base = b * p.T;
+  const int qc = p.legacy ? h * 3 * HD : h * HD;
+  const int kc = p.legacy ? qc + HD : p.C + h * HD;
+  const int vc = p.legacy ? qc + 2 * HD : 2 * p.C + h * HD;
+  const int nt = p.T / TN;
+
+  if (warp == 4 && lane == 0) {
+    tma_prefetch_desc(&p.tmQKV128);
+    tma_prefetch_desc(&p.tmQKV64);
+    tma_prefetch_desc(&p.tmDO128);
+    for (int i = 0; i < NUM_BARS; ++i) mbar_init(bar(i), i == B_PD ? 4 : 1);
+    fence_mbar_init();
+  }
+  if (warp == 5) {
+    tmem_alloc(smem_u32(&tmem_slot_s), TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(&tmem_slot_s);
+
+  if (warp == 4) {
+    if (lane == 0) {
+      mbar_arrive_expect_tx(bar(B_BIG), 2 * BIG_BYTES);
+      tma_load_2d(q_smem, &p.tmQKV128, bar(B_BIG), qc, row_base + q0);
+      tma_load_2d(do_smem, &p.tmDO128, bar(B_BIG), h * HD, row_base + q0);
+      for (int j = 0; j < nt; ++j) {
+        const int st = j % STAGES;
+        mbar_wait(bar(B_EMPTY + st), ((uint32_t)(j / STAGES) & 1u) ^ 1u);
+        mbar_arrive_expect_tx(bar(B_FULL + st), 2 * SMALL_BYTES);
+        tma_load_2d(k_smem(st), &p.tmQKV64, bar(B_FULL + st), kc, row_base + j * TN);
+        tma_load_2d(v_smem(st), &p.tmQKV64, bar(B_FULL + st), vc, row_base + j * TN);
+      }
+    }
+  } else if (warp == 5) {
+    if (lane == 0) {
+      constexpr uint32_t idesc_s = umma_idesc_bf16(BM, TN, 0, 0);
+      constexpr uint32_t idesc_g = umma_idesc_bf16(BM, HD, 0, 1);  // B = K_j rows [key][d]: MN-major
+      mbar_wait(bar(B_BIG), 0);
+      for (int j = 0; j < nt; ++j) {
+        const int st = j % STAGES;
+        mbar_wait(bar(B_FULL + st), (uint32_t)(j / STAGES) & 1u);
+        tc_fence_after();
+        const uint64_t q_desc = umma_desc_kmajor_sw128(q_smem);
+        const uint64_t do_desc = umma_desc_kmajor_sw128(do_smem);
+        const uint64_t k_desc = umma_desc_kmajor_sw128(k_smem(st));
+        const uint64_t v_desc = umma_desc_kmajor_sw128(v_smem(st));
+        // S_j = Q K_j^T and dP_j = dO V_j^T. The softmax warps finished reading step j-1's S / dP
+        // before they signalled B_PD, and dQ_{j-1} (issued below, in order) has consumed dS_{j-1}.
+#pragma unroll
+        for (int kk = 0; kk < HD / 16; ++kk)
+          umma_bf16_ss(tmem_base, q_desc + 2u * kk, k_desc + 2u * kk, idesc_s, kk != 0);
+#pragma unroll
+        for (int kk = 0; kk < HD / 16; ++kk)
+          umma_bf16_ss(tmem_base + TN, do_desc + 2u * kk, v_desc + 2u * kk, idesc_s, kk != 0);
+        umma_commit(bar(B_SP));
+        mbar_wait(bar(B_PD), (uint32_t)j & 1u);  // bf16 dS_j sits in TMEM columns [0,32)
+        tc_fence_after();
+#pragma unroll
+        for (int kk = 0; kk < TN / 16; ++kk) {
+          const uint64_t b_desc = umma_desc_mnmajor_sw128(k_smem(st) + kk * 2048, 1024);
+          umma_bf16_ts(tmem_base + 2 * TN, tmem_base + 8 * kk, b_desc, idesc_g, (j | kk) != 0);
+        }
+        umma_commit(bar(B_EMPTY + st));
+      }
+      umma_commit(bar(B_DONE));
+    }
+  } else {
+    const int quarter = warp & 3;
+    const int row = quarter * 32 + lane;
+    const bool ok = (q0 + row) < p.T;
+    const uint32_t lane_addr = tmem_base + ((uint32_t)(quarter * 32) << 16);
+    const float sc = 0.125f * 1.4426950408889634f;
+    // dS carries the s^2 = 1/8 of d(scores)/d(q.k): folded into the exponent (2^-3)
+    const float L = ok ? (p.lse[(size_t)bh * p.T + q0 + row] + 3.0f) : 0.f;
+    const float Dr = ok ? p.dsum[(size_t)bh * p.T + q0 + row] : 0.f;
+    for (int j = 0; j < nt; ++j) {
+      mbar_wait(bar(B_SP), (uint32_t)j & 1u);
+      tc_fence_after();
+      uint32_t ds[TN / 2];
+#pragma unroll
+      for (int hf = 0; hf < 2; ++hf) {
+        uint32_t sv[32], dp[32];
+        tmem_ld_32x32b_x32(lane_addr + hf * 32, sv);
+        tmem_ld_32x32b_x32(lane_addr + TN + hf * 32, dp);
+        tmem_wait_ld();
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          const float p0 = ex2_approx(fmaf(__uint_as_float(sv[2 * i]), sc, -L));
+          const float p1 = ex2_approx(fmaf(__uint_as_float(sv[2 * i + 1]), sc, -L));
+          ds[hf * 16 + i] = pack_bf16x2(p0 * (__uint_as_float(dp[2 * i]) - Dr), p1 * (__uint_as_float(dp[2 * i + 1]) - Dr));
+        }
+      }
+      tmem_st_32x32b_x32(lane_addr, ds);
+      tmem_wait_st();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar(B_PD));
+    }
+    mbar_wait(bar(B_DONE), 0);
+    tc_fence_after();
+    __nv_bfloat16* orow = p.dqkv + ((size_t)(row_base + q0 + row)) * (3 * p.C) + qc;
+#pragma unroll 1
+    for (int c = 0; c < HD; c += 32) {
+      uint32_t v[32];
+      tmem_ld_32x32b_x32(lane_addr + 2 * TN + c, v);
+      tmem_wait_ld();
+      if (ok) {
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          uint4 o;
+          o.x = pack_bf16x2(__uint_as_float(v[g * 8 + 0]), __uint_as_float(v[g * 8 + 1]));
+          o.y = pack_bf16x2(__uint_as_float(v[g * 8 + 2]), __uint_as_float(v[g * 8 + 3]));
+          o.z = pack_bf16x2(__uint_as_float(v[g * 8 + 4]), __uint_as_float(v[g * 8 + 5]));
+          o.w = pack_bf16x2(__uint_as_float(v[g * 8 + 6]), __uint_as_float(v[g * 8 + 7]));
+          *reinterpret_cast<uint4*>(orow + c + g * 8) = o;
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 5) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, TMEM_COLS);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// dK, dV: CTA = (128-key tile, batch*head). TMEM: S^T [0,64) | dP^T [64,128) | dV [128,192) | dK [192,256).
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(BW_THREADS, 2) attn_bwd_dkv_kernel(const __grid_constant__ BwdParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t bars[NUM_BARS];
+  __shared__ uint32_t tmem_slot_s;
+  __shared__ __align__(16) float lse_s[STAGES][TN];
+  __shared__ __align__(16) float dsum_s[STAGES][TN];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t k_smem = smem_base;
+  const uint32_t v_smem = smem_base + BIG_BYTES;
+  auto q_smem = [&](int st) { return smem_base + 2 * BIG_BYTES + st * 2 * SMALL_BYTES; };
+  auto do_smem = [&](int st) { return q_smem(st) + SMALL_BYTES; };
+  const uint32_t bar0 = smem_u32(bars);
+  auto bar = [&](int i) { return bar0 + 8u * i; };
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int bh = blockIdx.y;
+  const int b = bh / p.heads;
+  const int h = bh - b * p.heads;
+  const int k0 = blockIdx.x * BM;
+  const int row_base = b * p.T;
+  const int qc = p.legacy ? h * 3 * HD : h * HD;
+  const int kc = p.legacy ? qc + HD : p.C + h * HD;
+  const int vc = p.legacy ? qc + 2 * HD : 2 * p.C + h * HD;
+  const int nt = p.T / TN;
+
+  if (warp == 4 && lane == 0) {
+    tma_prefetch_desc(&p.tmQKV128);
+    tma_prefetch_desc(&p.tmQKV64);
+    tma_prefetch_desc(&p.tmDO64);
+    for (int i = 0; i < NUM_BARS; ++i) mbar_init(bar(i), i == B_PD ? 4 : 1);
+    fence_mbar_init();
+  }
+  if (warp == 5) {
+    tmem_alloc(smem_u32(&tmem_slot_s), TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(&tmem_slot_s);
+
+  if (warp == 4) {
+    if (lane == 0) {
+      mbar_arrive_expect_tx(bar(B_BIG), 2 * BIG_BYTES);
+      tma_load_2d(k_smem, &p.tmQKV128, bar(B_BIG), kc, row_base + k0);
+      tma_load_2d(v_smem, &p.tmQKV128, bar(B_BIG), vc, row_base + k0);
+      for (int i = 0; i < nt; ++i) {
+        const int st = i % STAGES;
+        mbar_wait(bar(B_EMPTY + st), ((uint32_t)(i / STAGES) & 1u) ^ 1u);
+        mbar_arrive_expect_tx(bar(B_FULL + st), 2 * SMALL_BYTES + 2 * TN * 4);
+        tma_load_2d(q_smem(st), &p.tmQKV64, bar(B_FULL + st), qc, row_base + i * TN);
+        tma_load_2d(do_smem(st), &p.tmDO64, bar(B_FULL + st), h * HD, row_base + i * TN);
+        bulk_load_1d(smem_u32(&lse_s[st][0]), p.lse + (size_t)bh * p.T + i * TN, TN * 4, bar(B_FULL + st));
+        bulk_load_1d(smem_u32(&dsum_s[st][0]), p.dsum + (size_t)bh * p.T + i * TN, TN * 4, bar(B_FULL + st));
+      }
+    }
+  } else if (warp == 5) {
+    if (lane == 0) {
+      constexpr uint32_t idesc_s = umma_idesc_bf16(BM, TN, 0, 0);
+      constexpr uint32_t idesc_g = umma_idesc_bf16(BM, HD, 0, 1);  // B = dO_i / Q_i rows [query][d]: MN-major
+      mbar_wait(bar(B_BIG), 0);
+      for (int i = 0; i < nt; ++i) {
+        const int st = i % STAGES;
+        mbar_wait(bar(B_FULL + st), (uint32_t)(i / STAGES) & 1u);
+        tc_fence_after();
+        const uint64_t k_desc = umma_desc_kmajor_sw128(k_smem);
+        const uint64_t v_desc = umma_desc_kmajor_sw128(v_smem);
+        const uint64_t q_desc = umma_desc_kmajor_sw128(q_smem(st));
+        const uint64_t do_desc = umma_desc_kmajor_sw128(do_smem(st));
+        // S^T = K Q_i^T and dP^T = V dO_i^T (rows = this CTA's keys, columns = the 64 queries of tile i)
+#pragma unroll
+        for (int kk = 0; kk < HD / 16; ++kk)
+          umma_bf16_ss(tmem_base, k_desc + 2u * kk, q_desc + 2u * kk, idesc_s, kk != 0);
+#pragma unroll
+        for (int kk = 0; kk < HD / 16; ++kk)
+          umma_bf16_ss(tmem_base + TN, v_desc + 2u * kk, do_desc + 2u * kk, idesc_s, kk != 0);
+        umma_commit(bar(B_SP));
+        mbar_wait(bar(B_PD), (uint32_t)i & 1u);  // bf16 P^T in columns [0,32), bf16 dS^T in [64,96)
+        tc_fence_after();
+#pragma unroll
+        for (int kk = 0; kk < TN / 16; ++kk) {
+          const uint64_t b_desc = umma_desc_mnmajor_sw128(do_smem(st) + kk * 2048, 1024);
+          umma_bf16_ts(tmem_base + 2 * TN, tmem_base + 8 * kk, b_desc, idesc_g, (i | kk) != 0);  // dV += P^T dO_i
+        }
+#pragma unroll
+        for (int kk = 0; kk < TN / 16; ++kk) {
+          const uint64_t b_desc = umma_desc_mnmajor_sw128(q_smem(st) + kk * 2048, 1024);
+          umma_bf16_ts(tmem_base + 3 * TN, tmem_base + TN + 8 * kk, b_desc, idesc_g, (i | kk) != 0);  // dK += dS^T Q_i
+        }
+        umma_commit(bar(B_EMPTY + st));
+      }
+      umma_commit(bar(B_DONE));
+    }
+  } else {
+    const int quarter = warp & 3;
+    const int row = quarter * 32 + lane;
+    const bool ok = (k0 + row) < p.T;
+    const uint32_t lane_addr = tmem_base + ((uint32_t)(quarter * 32) << 16);
+    const float sc = 0.125f * 1.4426950408889634f;
+    for (int i = 0; i < nt; ++i) {
+      const int st = i % STAGES;
+      mbar_wait(bar(B_FULL + st), (uint32_t)(i / STAGES) & 1u);  // lse / D of tile i visible to this thread
+      mbar_wait(bar(B_SP), (uint32_t)i & 1u);
+      tc_fence_after();
+      uint32_t pt[TN / 2], ds[TN / 2];
+#pragma unroll
+      for (int hf = 0; hf < 2; ++hf) {
+        uint32_t sv[32], dp[32];
+        tmem_ld_32x32b_x32(lane_addr + hf * 32, sv);
+        tmem_ld_32x32b_x32(lane_addr + TN + hf * 32, dp);
+        tmem_wait_ld();
+#pragma unroll
+        for (int c = 0; c < 16; ++c) {
+          const float2 l2 = *reinterpret_cast<const float2*>(&lse_s[st][hf * 32 + 2 * c]);
+          const float2 d2 = *reinterpret_cast<const float2*>(&dsum_s[st][hf * 32 + 2 * c]);
+          const float p0 = ex2_approx(fmaf(__uint_as_float(sv[2 * c]), sc, -l2.x));
+          const float p1 = ex2_approx(fmaf(__uint_as_float(sv[2 * c + 1]), sc, -l2.y));
+          pt[hf * 16 + c] = pack_bf16x2(p0, p1);
+          ds[hf * 16 + c] = pack_bf16x2(0.125f * p0 * (__uint_as_float(dp[2 * c]) - d2.x),
+                                        0.125f * p1 * (__uint_as_float(dp[2 * c + 1]) - d2.y));
+        }
+      }
+      tmem_st_32x32b_x32(lane_addr, pt);
+      tmem_st_32x32b_x32(lane_addr + TN, ds);
+      tmem_wait_st();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar(B_PD));
+    }
+    mbar_wait(bar(B_DONE), 0);
+    tc_fence_after();
+    __nv_bfloat16* rowp = p.dqkv + ((size_t)(row_base + k0 + row)) * (3 * p.C);
+#pragma unroll 1
+    for (int c = 0; c < 2 * HD; c += 32) {
+      uint32_t v[32];
+      tmem_ld_32x32b_x32(lane_addr + 2 * TN + c, v);  // [128,192) = dV, [192,256) = dK
+      tmem_wait_ld();
+      __nv_bfloat16* orow = rowp + (c < HD ? vc + c : kc + (c - HD));
+      if (ok) {
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          uint4 o;
+          o.x = pack_bf16x2(__uint_as_float(v[g * 8 + 0]), __uint_as_float(v[g * 8 + 1]));
+          o.y = pack_bf16x2(__uint_as_float(v[g * 8 + 2]), __uint_as_float(v[g * 8 + 3]));
+          o.z = pack_bf16x2(__uint_as_float(v[g * 8 + 4]), __uint_as_float(v[g * 8 + 5]));
+          o.w = pack_bf16x2(__uint_as_float(v[g * 8 + 6]), __uint_as_float(v[g * 8 + 7]));
+          *reinterpret_cast<uint4*>(orow + g * 8) = o;
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 5) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, TMEM_COLS);
+  }
+}
+
+// D[b, h, t] = sum_d dO[b*t, h*64+d] * O[b*t, h*64+d]; 8 lanes x 8 channels per (row, head)
+__global__ void __launch_bounds__(256) attn_rowdot_kernel(const __nv_bfloat16* __restrict__ o,
+                                                         const __nv_bfloat16* __restrict__ dout,
+                                                         float* __restrict__ dsum, int b, int T, int heads) {
+  const int C = heads * HD;
+  const size_t total = (size_t)b * T * (C / 8);
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const uint4 a = __ldg(reinterpret_cast<const uint4*>(o) + i);
+    const uint4 g = __ldg(reinterpret_cast<const uint4*>(dout) + i);
+    float s = bf16_lo(a.x) * bf16_lo(g.x) + bf16_hi(a.x) * bf16_hi(g.x);
+    s += bf16_lo(a.y) * bf16_lo(g.y) + bf16_hi(a.y) * bf16_hi(g.y);
+    s += bf16_lo(a.z) * bf16_lo(g.z) + bf16_hi(a.z) * bf16_hi(g.z);
+    s += bf16_lo(a.w) * bf16_lo(g.w) + bf16_hi(a.w) * bf16_hi(g.w);
+    // total and the stride are multiples of 8, so the 8 lanes of a (row, head) stay together
+    s += __shfl_xor_sync(0xffffffffu, s, 1);
+    s += __shfl_xor_sync(0xffffffffu, s, 2);
+    s += __shfl_xor_sync(0xffffffffu, s, 4);
+    if ((threadIdx.x & 7) == 0) {
+      const size_t rh = i / 8;            // (row, head) index, head fastest
+      const int hh = (int)(rh % heads);
+      const size_t r = rh / heads;        // b*T + t
+      const size_t bb = r / T;
+      dsum[(bb * heads + hh) * T + (r - bb * T)] = s;
+    }
+  }
+}
+
+}  // namespace
+
+int attention_backward_submit(adb_plan* plan, const void* qkv, const void* out, const void* dout, const float* lse,
+                              float* dsum, void* dqkv, int b, int t, int heads, int legacy_order, cudaStream_t stream) {
+  ADB_REQUIRE(qkv && out && dout && lse && dsum && dqkv && b > 0 && heads > 0, "attention_backward: bad arguments");
+  ADB_REQUIRE(t == 64 || (t >= 128 && t % 128 == 0), "attention_backward: sequence length %d unsupported (64 or a multiple of 128)", t);
+  const int C = heads * HD;
+  BwdParams bp;
+  memset(&bp, 0, sizeof(bp));
+  {
+    const uint64_t dims[2] = {(uint64_t)3 * C, (uint64_t)b * t};
+    const uint64_t strides[1] = {(uint64_t)3 * C * 2};
+    const uint32_t box128[2] = {64, 128};
+    const uint32_t box64[2] = {64, 64};
+    int r = make_tmap_bf16(&bp.tmQKV128, qkv, 2, dims, strides, box128);
+    if (r != ADB_OK) return r;
+    r = make_tmap_bf16(&bp.tmQKV64, qkv, 2, dims, strides, box64);
+    if (r != ADB_OK) return r;
+  }
+  {
+    const uint64_t dims[2] = {(uint64_t)C, (uint64_t)b * t};
+    const uint64_t strides[1] = {(uint64_t)C * 2};
+    const uint32_t box128[2] = {64, 128};
+    const uint32_t box64[2] = {64, 64};
+    int r = make_tmap_bf16(&bp.tmDO128, dout, 2, dims, strides, box128);
+    if (r != ADB_OK) return r;
+    r = make_tmap_bf16(&bp.tmDO64, dout, 2, dims, strides, box64);
+    if (r != ADB_OK) return r;
+  }
+  bp.lse = lse;
+  bp.dsum = dsum;
+  bp.dqkv = reinterpret_cast<__nv_bfloat16*>(dqkv);
+  bp.T = t;
+  bp.heads = heads;
+  bp.C = C;
+  bp.legacy = legacy_order ? 1 : 0;
+  const __nv_bfloat16* o = reinterpret_cast<const __nv_bfloat16*>(out);
+  const __nv_bfloat16* dO = reinterpret_cast<const __nv_bfloat16*>(dout);
+  // S and dP are each computed twice (once per kernel), then dQ, dK, dV: 7 products of 2*T*T*64
+  const double flops = 14.0 * (double)b * heads * (double)t * (double)t * HD;
+  return submit(plan, stream, "attention_bwd", flops, 0.0, [bp, o, dO, dsum, b, t, heads](cudaStream_t s) -> int {
+    static bool attr_set = false;
+    if (!attr_set) {
+      ADB_CUDA(cudaFuncSetAttribute(attn_bwd_dq_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+      ADB_CUDA(cudaFuncSetAttribute(attn_bwd_dkv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+      attr_set = true;
+    }
+    const size_t vecs = (size_t)b * t * (heads * HD / 8);
+    size_t blocks = (vecs + 255) / 256;
+    const size_t cap = (size_t)num_sms() * 16;
+    if (blocks > cap) blocks = cap;
+    attn_rowdot_kernel<<<(unsigned)blocks, 256, 0, s>>>(o, dO, dsum, b, t, heads);
+    ADB_CUDA(cudaGetLastError());
+    dim3 grid((t + BM - 1) / BM, b * heads);
+    attn_bwd_dq_kernel<<<grid, BW_THREADS, SMEM_BYTES, s>>>(bp);
+    ADB_CUDA(cudaGetLastError());
+    attn_bwd_dkv_kernel<<<grid, BW_THREADS, SMEM_BYTES, s>>>(bp);
+    ADB_CUDA(cudaGetLastError());
+    return 3;
+  });
+}
+
+}  // namespace adb

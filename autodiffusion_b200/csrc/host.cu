@@ -97,7 +97,16 @@ int make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t*
 // implemented in the kernel translation units
 int conv_block_n(int cout);
 int conv_igemm_submit(adb_plan*, const adb_conv_desc*, cudaStream_t);
-int attention_submit(adb_plan*, const void*, void*, int, int, int, int, cudaStream_t);
+int attention_submit(adb_plan*, const void*, void*, float*, int, int, int, int, cudaStream_t);
+int attention_backward_submit(adb_plan*, const void*, const void*, const void*, const float*, float*, void*, int, int,
+                              int, int, cudaStream_t);
+int gn_backward_submit(adb_plan*, const adb_gn_bwd_desc*, cudaStream_t);
+int pool_prepare_submit(adb_plan*, const void*, const float*, void*, float*, int, int, int, cudaStream_t);
+int pool_attention_submit(adb_plan*, const float*, const void*, float*, float*, int, int, int, cudaStream_t);
+int pool_attention_backward_submit(adb_plan*, const float*, const float*, const float*, const void*, float*, void*, int,
+                                   int, int, cudaStream_t);
+int pool_merge_submit(adb_plan*, const void*, const float*, void*, int, int, int, cudaStream_t);
+int logsoftmax_grad_submit(adb_plan*, const float*, const int64_t*, float*, int, int, float, cudaStream_t);
 int groupnorm_submit(adb_plan*, const adb_gn_desc*, cudaStream_t);
 int resample2x_submit(adb_plan*, const void*, void*, int, int, int, int, int, cudaStream_t);
 int stem_conv_submit(adb_plan*, const float*, const float*, const float*, void*, int, int, int, int,
@@ -201,7 +210,53 @@ int adb_conv_igemm(adb_plan* plan, const adb_conv_desc* d, adb_stream stream) {
 
 int adb_attention(adb_plan* plan, const void* qkv, void* out, int b, int t, int heads,
                   int legacy_order, adb_stream stream) {
-  return attention_submit(plan, qkv, out, b, t, heads, legacy_order, static_cast<cudaStream_t>(stream));
+  return attention_submit(plan, qkv, out, nullptr, b, t, heads, legacy_order, static_cast<cudaStream_t>(stream));
+}
+
+int adb_attention_lse(adb_plan* plan, const void* qkv, void* out, float* lse, int b, int t, int heads,
+                      int legacy_order, adb_stream stream) {
+  if (!lse) {
+    set_error("adb_attention_lse: null lse");
+    return ADB_ERR_INVALID;
+  }
+  return attention_submit(plan, qkv, out, lse, b, t, heads, legacy_order, static_cast<cudaStream_t>(stream));
+}
+
+int adb_attention_backward(adb_plan* plan, const void* qkv, const void* out, const void* dout, const float* lse,
+                           float* dsum, void* dqkv, int b, int t, int heads, int legacy_order,
+                           adb_stream stream) {
+  return attention_backward_submit(plan, qkv, out, dout, lse, dsum, dqkv, b, t, heads, legacy_order,
+                                   static_cast<cudaStream_t>(stream));
+}
+
+int adb_gn_backward(adb_plan* plan, const adb_gn_bwd_desc* d, adb_stream stream) {
+  return gn_backward_submit(plan, d, static_cast<cudaStream_t>(stream));
+}
+
+int adb_pool_prepare(adb_plan* plan, const void* h, const float* pos, void* xp, float* mean, int n, int p, int c,
+                     adb_stream stream) {
+  return pool_prepare_submit(plan, h, pos, xp, mean, n, p, c, static_cast<cudaStream_t>(stream));
+}
+
+int adb_pool_attention(adb_plan* plan, const float* qkv0, const void* kv, float* out0, float* probs, int n, int p,
+                       int c, adb_stream stream) {
+  return pool_attention_submit(plan, qkv0, kv, out0, probs, n, p, c, static_cast<cudaStream_t>(stream));
+}
+
+int adb_pool_attention_backward(adb_plan* plan, const float* dout0, const float* probs, const float* qkv0,
+                                const void* kv, float* dqkv0, void* dkv, int n, int p, int c, adb_stream stream) {
+  return pool_attention_backward_submit(plan, dout0, probs, qkv0, kv, dqkv0, dkv, n, p, c,
+                                        static_cast<cudaStream_t>(stream));
+}
+
+int adb_pool_merge(adb_plan* plan, const void* dxp, const float* dmean, void* dh, int n, int p, int c,
+                   adb_stream stream) {
+  return pool_merge_submit(plan, dxp, dmean, dh, n, p, c, static_cast<cudaStream_t>(stream));
+}
+
+int adb_logsoftmax_grad(adb_plan* plan, const float* logits, const int64_t* y, float* dlogits, int n, int k,
+                        float scale, adb_stream stream) {
+  return logsoftmax_grad_submit(plan, logits, y, dlogits, n, k, scale, static_cast<cudaStream_t>(stream));
 }
 
 int adb_groupnorm(adb_plan* plan, const adb_gn_desc* d, adb_stream stream) {

@@ -33,6 +33,8 @@ __all__ = [
     "Plan", "conv_block_n", "pack_conv_weight", "conv_igemm", "attention", "groupnorm", "resample2x",
     "stem_conv", "timestep_embedding", "linear", "ddim_step", "pack_uint8", "moments_accumulate",
     "memset0", "nchw_to_nhwc_bf16", "nhwc_to_nchw_f32",
+    "attention_backward", "gn_backward", "pool_prepare", "pool_attention", "pool_attention_backward", "pool_merge",
+    "logsoftmax_grad", "pack_conv_weight_dgrad",
 ]
 
 
@@ -190,19 +192,174 @@ def conv_igemm(
 
 
 def attention(qkv: torch.Tensor, b: int, t: int, heads: int, legacy_order: bool,
-              out: Optional[torch.Tensor] = None, plan: Optional[Plan] = None) -> torch.Tensor:
-    """qkv: bf16 [b*t, 3*heads*64] -> bf16 [b*t, heads*64]."""
+              out: Optional[torch.Tensor] = None, plan: Optional[Plan] = None,
+              lse: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """qkv: bf16 [b*t, 3*heads*64] -> bf16 [b*t, heads*64]. lse: optional fp32 [b*heads, t] output
+    (log2-domain log-sum-exp of the scaled scores) consumed by `attention_backward`."""
     c = heads * 64
     assert qkv.numel() == b * t * 3 * c
     if out is None:
         out = torch.empty((b * t, c), dtype=torch.bfloat16, device=qkv.device)
+    if lse is None:
+        _lib.check(
+            _lib.lib().adb_attention(_ph(plan), _dev(qkv, "qkv", torch.bfloat16), _dev(out, "out", torch.bfloat16),
+                                     b, t, heads, int(bool(legacy_order)), _stream()),
+            "adb_attention",
+        )
+    else:
+        assert lse.numel() == b * heads * t
+        _lib.check(
+            _lib.lib().adb_attention_lse(_ph(plan), _dev(qkv, "qkv", torch.bfloat16), _dev(out, "out", torch.bfloat16),
+                                         _dev(lse, "lse", torch.float32), b, t, heads, int(bool(legacy_order)), _stream()),
+            "adb_attention_lse",
+        )
+    if plan is not None:
+        plan.keep(qkv, out, lse)
+    return out
+
+
+def attention_backward(qkv: torch.Tensor, out: torch.Tensor, dout: torch.Tensor, lse: torch.Tensor, b: int, t: int,
+                       heads: int, legacy_order: bool, dqkv: Optional[torch.Tensor] = None,
+                       dsum: Optional[torch.Tensor] = None, plan: Optional[Plan] = None) -> torch.Tensor:
+    """Gradient of `attention` w.r.t. qkv. out/dout bf16 [b*t, heads*64] -> dqkv bf16 [b*t, 3*heads*64]."""
+    c = heads * 64
+    assert qkv.numel() == b * t * 3 * c and out.numel() == b * t * c and dout.numel() == b * t * c
+    if dqkv is None:
+        dqkv = torch.empty((b * t, 3 * c), dtype=torch.bfloat16, device=qkv.device)
+    if dsum is None:
+        dsum = torch.empty((b * heads, t), dtype=torch.float32, device=qkv.device)
     _lib.check(
-        _lib.lib().adb_attention(_ph(plan), _dev(qkv, "qkv", torch.bfloat16), _dev(out, "out", torch.bfloat16),
-                                 b, t, heads, int(bool(legacy_order)), _stream()),
-        "adb_attention",
+        _lib.lib().adb_attention_backward(_ph(plan), _dev(qkv, "qkv", torch.bfloat16), _dev(out, "out", torch.bfloat16),
+                                          _dev(dout, "dout", torch.bfloat16), _dev(lse, "lse", torch.float32),
+                                          _dev(dsum, "dsum", torch.float32), _dev(dqkv, "dqkv", torch.bfloat16),
+                                          b, t, heads, int(bool(legacy_order)), _stream()),
+        "adb_attention_backward",
     )
     if plan is not None:
-        plan.keep(qkv, out)
+        plan.keep(qkv, out, dout, lse, dsum, dqkv)
+    return dqkv
+
+
+def gn_backward(x: torch.Tensor, stats: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, dout: torch.Tensor,
+                scale_shift=None, ss_stride: int = 0, silu: bool = True, resample: int = RESAMPLE_NONE,
+                add: Optional[torch.Tensor] = None, add_mode: int = RES_NONE, eps: float = 1e-5,
+                dx: Optional[torch.Tensor] = None, bstats: Optional[torch.Tensor] = None,
+                plan: Optional[Plan] = None) -> torch.Tensor:
+    """Gradient of `groupnorm` (single source) w.r.t. its input x [n,h,w,c]; `stats` are the forward sums of x."""
+    n, h, w, c = x.shape
+    if dx is None:
+        dx = torch.empty_like(x)
+    if bstats is None:
+        bstats = torch.empty((n, 32, 2), dtype=torch.float64, device=x.device)
+    d = _lib.GnBwdDesc()
+    d.n, d.h, d.w, d.c = n, h, w, c
+    d.x = _dev(x, "x", torch.bfloat16)
+    d.stats = _dev(stats, "stats", torch.float64)
+    d.gamma = _dev(gamma, "gamma", torch.float32)
+    d.beta = _dev(beta, "beta", torch.float32)
+    d.eps = eps
+    ss_base = None
+    if isinstance(scale_shift, tuple):
+        ss_base, ss_off = scale_shift
+        d.scale_shift = _dev(ss_base, "scale_shift", torch.float32) + 4 * int(ss_off)
+    else:
+        d.scale_shift = _opt(scale_shift, "scale_shift", torch.float32)
+        ss_base = scale_shift
+    d.ss_stride = ss_stride
+    d.silu = int(bool(silu))
+    d.resample = resample
+    exp = (n, h // 2, w // 2, c) if resample == RESAMPLE_AVGPOOL2 else (n, h, w, c)
+    assert tuple(dout.shape) == exp, f"dout shape {tuple(dout.shape)} != {exp}"
+    d.dout = _dev(dout, "dout", torch.bfloat16)
+    d.add = _opt(add, "add", torch.bfloat16)
+    d.add_mode = add_mode
+    if add is not None:
+        exp = (n, h // 2, w // 2, c) if add_mode == RES_AVGPOOL2 else (n, h, w, c)
+        assert tuple(add.shape) == exp, f"add shape {tuple(add.shape)} != {exp}"
+    d.dx = _dev(dx, "dx", torch.bfloat16)
+    d.bstats = _dev(bstats, "bstats", torch.float64)
+    _lib.check(_lib.lib().adb_gn_backward(_ph(plan), C.byref(d), _stream()), "adb_gn_backward")
+    if plan is not None:
+        plan.keep(x, stats, gamma, beta, ss_base, dout, add, dx, bstats)
+    return dx
+
+
+def pack_conv_weight_dgrad(weight: torch.Tensor, device=None) -> torch.Tensor:
+    """Operand of the data-gradient of a conv: dx = conv(dy, W^T flipped). weight [cout, cin, kh, kw] (or
+    [cout, cin, 1]) -> packed matrix of the transposed conv, rows = cin, K = (tap, cout)."""
+    w = weight.detach()
+    if w.dim() == 3:
+        w = w.unsqueeze(-1)
+    return pack_conv_weight([w.transpose(0, 1).flip(2, 3).contiguous()], device)
+
+
+def pool_prepare(h: torch.Tensor, pos: torch.Tensor, plan: Optional[Plan] = None):
+    """h bf16 [n, hh, ww, c], pos fp32 [c, hh*ww+1] -> (xp bf16 like h, mean fp32 [n, c])."""
+    n, hh, ww, c = h.shape
+    P = hh * ww
+    assert tuple(pos.shape) == (c, P + 1)
+    xp = torch.empty_like(h)
+    mean = torch.empty((n, c), dtype=torch.float32, device=h.device)
+    _lib.check(_lib.lib().adb_pool_prepare(_ph(plan), _dev(h, "h", torch.bfloat16), _dev(pos, "pos", torch.float32),
+                                           _dev(xp, "xp", torch.bfloat16), _dev(mean, "mean", torch.float32), n, P, c,
+                                           _stream()), "adb_pool_prepare")
+    if plan is not None:
+        plan.keep(h, pos, xp, mean)
+    return xp, mean
+
+
+def pool_attention(qkv0: torch.Tensor, kv: torch.Tensor, plan: Optional[Plan] = None):
+    """qkv0 fp32 [n, 3c], kv bf16 [n, hh, ww, 2c] -> (out0 fp32 [n, c], probs fp32 [n, c/64, P+1])."""
+    n, hh, ww, c2 = kv.shape
+    c, P = c2 // 2, hh * ww
+    out0 = torch.empty((n, c), dtype=torch.float32, device=kv.device)
+    probs = torch.empty((n, c // 64, P + 1), dtype=torch.float32, device=kv.device)
+    _lib.check(_lib.lib().adb_pool_attention(_ph(plan), _dev(qkv0, "qkv0", torch.float32), _dev(kv, "kv", torch.bfloat16),
+                                             _dev(out0, "out0", torch.float32), _dev(probs, "probs", torch.float32),
+                                             n, P, c, _stream()), "adb_pool_attention")
+    if plan is not None:
+        plan.keep(qkv0, kv, out0, probs)
+    return out0, probs
+
+
+def pool_attention_backward(dout0: torch.Tensor, probs: torch.Tensor, qkv0: torch.Tensor, kv: torch.Tensor,
+                            plan: Optional[Plan] = None):
+    """-> (dqkv0 fp32 [n, 3c], dkv bf16 like kv)."""
+    n, hh, ww, c2 = kv.shape
+    c, P = c2 // 2, hh * ww
+    dqkv0 = torch.empty((n, 3 * c), dtype=torch.float32, device=kv.device)
+    dkv = torch.empty_like(kv)
+    _lib.check(_lib.lib().adb_pool_attention_backward(
+        _ph(plan), _dev(dout0, "dout0", torch.float32), _dev(probs, "probs", torch.float32),
+        _dev(qkv0, "qkv0", torch.float32), _dev(kv, "kv", torch.bfloat16), _dev(dqkv0, "dqkv0", torch.float32),
+        _dev(dkv, "dkv", torch.bfloat16), n, P, c, _stream()), "adb_pool_attention_backward")
+    if plan is not None:
+        plan.keep(dout0, probs, qkv0, kv, dqkv0, dkv)
+    return dqkv0, dkv
+
+
+def pool_merge(dxp: torch.Tensor, dmean: torch.Tensor, plan: Optional[Plan] = None) -> torch.Tensor:
+    """dh[n,p,:] = dxp[n,p,:] + dmean[n,:] / P."""
+    n, hh, ww, c = dxp.shape
+    dh = torch.empty_like(dxp)
+    _lib.check(_lib.lib().adb_pool_merge(_ph(plan), _dev(dxp, "dxp", torch.bfloat16), _dev(dmean, "dmean", torch.float32),
+                                         _dev(dh, "dh", torch.bfloat16), n, hh * ww, c, _stream()), "adb_pool_merge")
+    if plan is not None:
+        plan.keep(dxp, dmean, dh)
+    return dh
+
+
+def logsoftmax_grad(logits: torch.Tensor, y: torch.Tensor, scale: float, out: Optional[torch.Tensor] = None,
+                    plan: Optional[Plan] = None) -> torch.Tensor:
+    """d/dlogits of log_softmax(logits)[range(n), y].sum() * scale."""
+    n, k = logits.shape
+    if out is None:
+        out = torch.empty_like(logits)
+    _lib.check(_lib.lib().adb_logsoftmax_grad(_ph(plan), _dev(logits, "logits", torch.float32), _dev(y, "y", torch.int64),
+                                              _dev(out, "out", torch.float32), n, k, float(scale), _stream()),
+               "adb_logsoftmax_grad")
+    if plan is not None:
+        plan.keep(logits, y, out)
     return out
 
 

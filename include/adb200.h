@@ -181,6 +181,70 @@ int adb_moments_accumulate(adb_plan* plan, const float* feats, int n, int d, dou
 /* zero `bytes` bytes at `ptr` (recorded memset node) */
 int adb_memset0(adb_plan* plan, void* ptr, size_t bytes, adb_stream stream);
 
+/* ==== classifier guidance: forward extras and the input-gradient (backward-data) path ====
+ * The search's cond_fn (search_dynamic_unet_imagenet64_classifier_guidance_progressive.py:383-390)
+ * is th.autograd.grad(log_softmax(classifier(x_t, t))[range(B), y].sum(), x_t) * classifier_scale
+ * with classifier = EncoderUNetModel (guided_diffusion/unet.py:685-896, pool="attention").
+ * Its convolutions' data gradients are adb_conv_igemm calls with transposed / flipped weights;
+ * the entries below are the remaining pieces. */
+
+/* adb_attention that also writes lse[b*heads, t] (fp32, log2 domain: P_ij = 2^(s_ij*log2(e)/8 - lse_i)),
+ * which adb_attention_backward recomputes the probabilities from. */
+int adb_attention_lse(adb_plan* plan, const void* qkv, void* out, float* lse, int b, int t, int heads,
+                      int legacy_order, adb_stream stream);
+
+/* Gradient of adb_attention w.r.t. qkv (autograd of QKVAttention(Legacy).forward, unet.py:325-371).
+ * out / dout: bf16 [b*t, heads*64] (forward output and its gradient); dqkv: bf16 [b*t, 3*heads*64], same
+ * column layout as qkv; dsum: fp32 [b*heads, t] scratch (row sums of dout*out). */
+int adb_attention_backward(adb_plan* plan, const void* qkv, const void* out, const void* dout, const float* lse,
+                           float* dsum, void* dqkv, int b, int t, int heads, int legacy_order,
+                           adb_stream stream);
+
+/* Gradient of adb_groupnorm (single source) w.r.t. its input: GroupNorm32 (+FiLM) (+SiLU) (+2x average
+ * pool) backward (nn.py:17-19, unet.py:236-258 under autograd). */
+typedef struct {
+  int n, h, w, c;           /* geometry of x, the forward op's INPUT */
+  const void* x;            /* bf16 NHWC [n,h,w,c] */
+  const double* stats;      /* the forward's [n,32,2] (sum, sum of squares) of x */
+  const float* gamma;
+  const float* beta;
+  float eps;
+  const float* scale_shift; /* as in adb_gn_desc, or NULL */
+  int ss_stride;
+  int silu;
+  int resample;             /* ADB_RESAMPLE_NONE, or ADB_RESAMPLE_AVGPOOL2: dout is [n,h/2,w/2,c] */
+  const void* dout;         /* bf16 NHWC gradient w.r.t. the forward op's output */
+  const void* add;          /* optional bf16 gradient added to dx (the block's skip path) */
+  int add_mode;             /* ADB_RES_NONE; ADB_RES_SAME: add is [n,h,w,c]; ADB_RES_AVGPOOL2: the skip path
+                               average-pooled x, add is [n,h/2,w/2,c] and contributes add/4 */
+  void* dx;                 /* bf16 NHWC [n,h,w,c] */
+  double* bstats;           /* scratch [n,32,2] */
+} adb_gn_bwd_desc;
+int adb_gn_backward(adb_plan* plan, const adb_gn_bwd_desc* d, adb_stream stream);
+
+/* AttentionPool2d (unet.py:22-51) restricted to the token it returns (index 0 = the spatial mean):
+ *   prepare : xp[n,p,:] = h[n,p,:] + pos[:,1+p] (bf16), mean[n,:] = mean_p h[n,p,:] + pos[:,0] (fp32);
+ *             h bf16 [n,P,C] (NHWC pixels), pos fp32 [C, P+1]
+ *   the k/v rows of qkv_proj over xp run on adb_conv_igemm, the mean token's q/k/v on adb_linear
+ *   attention: out0[n,:] = softmax(q0 . k_j / 8) v_j over the P+1 tokens, per 64-channel head;
+ *             qkv0 fp32 [n,3C] = (q|k|v) of the mean token, kv bf16 [n,P,2C] = (k|v) of the pixels;
+ *             probs fp32 [n, C/64, P+1] is kept for the backward
+ *   backward: dout0 fp32 [n,C] -> dqkv0 fp32 [n,3C], dkv bf16 [n,P,2C]
+ *   merge   : dh[n,p,:] = dxp[n,p,:] + dmean[n,:] / P */
+int adb_pool_prepare(adb_plan* plan, const void* h, const float* pos, void* xp, float* mean, int n, int p, int c,
+                     adb_stream stream);
+int adb_pool_attention(adb_plan* plan, const float* qkv0, const void* kv, float* out0, float* probs, int n, int p,
+                       int c, adb_stream stream);
+int adb_pool_attention_backward(adb_plan* plan, const float* dout0, const float* probs, const float* qkv0,
+                                const void* kv, float* dqkv0, void* dkv, int n, int p, int c, adb_stream stream);
+int adb_pool_merge(adb_plan* plan, const void* dxp, const float* dmean, void* dh, int n, int p, int c,
+                   adb_stream stream);
+
+/* dlogits[n,c] = scale * ((c == y[n]) - softmax(logits[n])[c]): the gradient of
+ * log_softmax(logits)[range(n), y].sum() * scale (…progressive.py:387-390). */
+int adb_logsoftmax_grad(adb_plan* plan, const float* logits, const int64_t* y, float* dlogits, int n, int k,
+                        float scale, adb_stream stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -10,6 +10,10 @@ from .script_util import (  # noqa: F401
     NUM_CLASSES,
     add_dict_to_argparser,
     args_to_dict,
+    classifier_and_diffusion_defaults,
+    classifier_defaults,
+    create_classifier,
+    create_classifier_and_diffusion,
     create_gaussian_diffusion,
     create_model,
     create_model_and_diffusion,

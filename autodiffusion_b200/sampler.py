@@ -12,7 +12,9 @@ launches around an ~800-launch eager UNet forward.
     sorted-rank indexing, :394-396), entries beyond K' unused,
   * every step's UNet forward (skipped blocks elided; one cached CUDA graph per (batch, skip set)) +
     fused guidance/DDIM update is chained in sampling order K'-1 .. 0 and captured in ONE CUDA graph
-    when there is no caller-supplied `cond_fn`. With a `cond_fn` (an arbitrary torch callable
+    when there is no caller-supplied `cond_fn`, or when the `cond_fn` is this package's
+    `classifier.ClassifierGuidance` (the noisy classifier's forward + input-gradient is then recorded
+    into the same graph, one instance per step). With any other `cond_fn` (an arbitrary torch callable
     returning grad log p(y|x) * scale) the chain is run step by step around that call.
   * the final `((x+1)*127.5).clamp(0,255).to(uint8)` NHWC pack (:421-423) is the last node.
 """
@@ -25,6 +27,7 @@ from typing import Callable, List, Optional, Sequence
 import torch as th
 
 from . import ops
+from .classifier import ClassifierGuidance
 from .gaussian_diffusion import ModelMeanType, ddim_coefficients
 from .respace import reset_diffusion
 
@@ -98,8 +101,17 @@ class SchedulePlan:
         self.grad = th.zeros(self.shape, dtype=th.float32, device=dev) if cond_fn is not None else None
         self.u8 = th.empty((batch, hw, hw, model.in_channels), dtype=th.uint8, device=dev) if pack_uint8 else None
         self.launches = sum(up.launches for up in self.steps) + self.K + (1 if pack_uint8 else 0)
+        # native classifier guidance: forward + input-gradient recorded once over the shared x / t / y buffers
+        self.guidance: Optional[ops.Plan] = None
+        if isinstance(cond_fn, ClassifierGuidance):
+            if self.y is None:  # unconditional UNet guided by a classifier: labels still drive the guidance
+                self.y = th.zeros((batch,), dtype=th.int64, device=dev)
+            with th.no_grad():
+                self.guidance = ops.Plan()
+                cond_fn.record(self.guidance, self.x, self.t_in, self.y, self.grad)
+                self.launches += self.K * self.guidance.run()
         self.graph: Optional[th.cuda.CUDAGraph] = None
-        if cond_fn is None and use_graph:
+        if (cond_fn is None or self.guidance is not None) and use_graph:
             th.cuda.current_stream().synchronize()
             g = th.cuda.CUDAGraph()
             with th.cuda.graph(g):
@@ -120,6 +132,8 @@ class SchedulePlan:
     def _run_chain(self):
         for n in range(self.K):
             self._step(n)
+            if self.guidance is not None:
+                self.guidance.run()  # grad log p(y | x_t) * scale at the ORIGINAL timestep (t_in), into self.grad
             self._update(n)
         if self.u8 is not None:
             ops.pack_uint8(self.final, out=self.u8)
@@ -128,11 +142,11 @@ class SchedulePlan:
         """x_T = noise (fp32 [B,C,H,W]), labels y -> x_0 (a view of the shared buffer; clone to keep)."""
         assert tuple(noise.shape) == self.shape
         self.x.copy_(noise, non_blocking=True)
-        if self.class_cond:
+        if self.class_cond or self.guidance is not None:
             assert y is not None and y.shape == (self.B,)
             self.y.copy_(y, non_blocking=True)
         self.model.gpu_launches += self.launches
-        if self.cond_fn is None:
+        if self.cond_fn is None or self.guidance is not None:
             if self.graph is not None:
                 self.graph.replay()
             else:

@@ -447,8 +447,9 @@ int attention_backward_submit(adb_plan* plan, const void* qkv, const void* out, 
   bp.legacy = legacy_order ? 1 : 0;
   const __nv_bfloat16* o = reinterpret_cast<const __nv_bfloat16*>(out);
   const __nv_bfloat16* dO = reinterpret_cast<const __nv_bfloat16*>(dout);
-  // S and dP are each computed twice (once per kernel), then dQ, dK, dV: 7 products of 2*T*T*64
-  const double flops = 14.0 * (double)b * heads * (double)t * (double)t * HD;
+  // algorithmic work = the four gradient products autograd executes (dP, dV, dQ, dK: 2*T*T*64 each); the S
+  // recomputation (twice) and the second dP these kernels do instead of storing P are not counted
+  const double flops = 8.0 * (double)b * heads * (double)t * (double)t * HD;
   return submit(plan, stream, "attention_bwd", flops, 0.0, [bp, o, dO, dsum, b, t, heads](cudaStream_t s) -> int {
     static bool attr_set = false;
     if (!attr_set) {

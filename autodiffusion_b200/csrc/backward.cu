@@ -123,47 +123,64 @@ __global__ void __launch_bounds__(GB_THREADS) gn_bwd_kernel(const GnBwdParams p)
       float s1[8], s2[8];
 #pragma unroll
       for (int i = 0; i < 8; ++i) s1[i] = s2[i] = 0.f;
-      for (int pix = p_begin + pl; pix < p_end; pix += lanes) {
-        const size_t ipix = (size_t)n * P + pix;
-        size_t hpix = 0;  // the matching pixel of a half-resolution gradient
-        if (p.resample == ADB_RESAMPLE_AVGPOOL2 || p.add_mode == ADB_RES_AVGPOOL2) {
-          const int y = pix / p.W, xx = pix - y * p.W;
-          hpix = (size_t)n * Ph + (size_t)(y >> 1) * Wh + (xx >> 1);
-        }
-        float xf[8], df[8];
-        unpack8(__ldg(reinterpret_cast<const uint4*>(p.x + ipix * p.C) + v), xf);
-        const size_t dpix = (p.resample == ADB_RESAMPLE_AVGPOOL2) ? hpix : ipix;
-        unpack8(__ldg(reinterpret_cast<const uint4*>(p.dout + dpix * p.C) + v), df);
-        float o[8];
+      const bool half_d = p.resample == ADB_RESAMPLE_AVGPOOL2;
+      const bool half_a = p.add_mode == ADB_RES_AVGPOOL2;
+      const bool has_add = APPLY && p.add_mode != ADB_RES_NONE;
+      const float ascale = half_a ? 0.25f : 1.0f;
+      // U pixels per trip: all of a trip's 16-byte loads (x, dout, add) are issued before any math
+      constexpr int U = 4;
+      for (int pix0 = p_begin + pl; pix0 < p_end; pix0 += U * lanes) {
+        uint4 xr[U], dr[U], ar[U];
+        size_t ipix[U];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const float xh = fmaf(xf[i], r[i], m0[i]);
-          const float z = fmaf(xh, A[i], B[i]);
-          float dz = df[i] * dscale;
-          if (p.silu) {
-            float th;
-            asm("tanh.approx.f32 %0, %1;" : "=f"(th) : "f"(0.5f * z));
-            const float sg = fmaf(0.5f, th, 0.5f);  // sigmoid(z)
-            dz *= sg * fmaf(z, 1.0f - sg, 1.0f);     // silu'(z) = s (1 + z (1 - s))
+        for (int u = 0; u < U; ++u) {
+          const int pix = pix0 + u * lanes;
+          const bool ok = pix < p_end;
+          const int pc = ok ? pix : p_begin;  // clamp: the tail re-reads a valid pixel and is discarded
+          ipix[u] = (size_t)n * P + pc;
+          size_t hpix = 0;  // the matching pixel of a half-resolution gradient
+          if (half_d || half_a) {
+            const int y = pc / p.W, xx = pc - y * p.W;
+            hpix = (size_t)n * Ph + (size_t)(y >> 1) * Wh + (xx >> 1);
           }
-          const float dxh = dz * A[i];
+          xr[u] = __ldg(reinterpret_cast<const uint4*>(p.x + ipix[u] * p.C) + v);
+          dr[u] = __ldg(reinterpret_cast<const uint4*>(p.dout + (half_d ? hpix : ipix[u]) * p.C) + v);
+          if (has_add) ar[u] = __ldg(reinterpret_cast<const uint4*>(p.add + (half_a ? hpix : ipix[u]) * p.C) + v);
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          if (pix0 + u * lanes >= p_end) break;
+          float xf[8], df[8], o[8];
+          unpack8(xr[u], xf);
+          unpack8(dr[u], df);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const float xh = fmaf(xf[i], r[i], m0[i]);
+            const float z = fmaf(xh, A[i], B[i]);
+            float dz = df[i] * dscale;
+            if (p.silu) {
+              float th;
+              asm("tanh.approx.f32 %0, %1;" : "=f"(th) : "f"(0.5f * z));
+              const float sg = fmaf(0.5f, th, 0.5f);  // sigmoid(z)
+              dz *= sg * fmaf(z, 1.0f - sg, 1.0f);     // silu'(z) = s (1 + z (1 - s))
+            }
+            const float dxh = dz * A[i];
+            if (APPLY) {
+              o[i] = r[i] * (dxh - k1[i] - xh * k2[i]);
+            } else {
+              s1[i] += dxh;
+              s2[i] = fmaf(dxh, xh, s2[i]);
+            }
+          }
           if (APPLY) {
-            o[i] = r[i] * (dxh - k1[i] - xh * k2[i]);
-          } else {
-            s1[i] += dxh;
-            s2[i] = fmaf(dxh, xh, s2[i]);
-          }
-        }
-        if (APPLY) {
-          if (p.add_mode != ADB_RES_NONE) {
-            float af[8];
-            const size_t apix = (p.add_mode == ADB_RES_AVGPOOL2) ? hpix : ipix;
-            unpack8(__ldg(reinterpret_cast<const uint4*>(p.add + apix * p.C) + v), af);
-            const float ascale = (p.add_mode == ADB_RES_AVGPOOL2) ? 0.25f : 1.0f;
+            if (has_add) {
+              float af[8];
+              unpack8(ar[u], af);
 #pragma unroll
-            for (int i = 0; i < 8; ++i) o[i] = fmaf(af[i], ascale, o[i]);
+              for (int i = 0; i < 8; ++i) o[i] = fmaf(af[i], ascale, o[i]);
+            }
+            *(reinterpret_cast<uint4*>(p.dx + ipix[u] * p.C) + v) = pack8(o);
           }
-          *(reinterpret_cast<uint4*>(p.dx + ipix * p.C) + v) = pack8(o);
         }
       }
       if (!APPLY) {

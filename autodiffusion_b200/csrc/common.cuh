@@ -131,8 +131,11 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   long long t0 = clock64();
   while (!mbar_try_wait(bar, parity)) {
     if (clock64() - t0 > 4000000000LL) {
-      printf("adb200: mbarrier timeout block %d thread %d bar %u parity %u\n", blockIdx.x,
-             threadIdx.x, bar, parity);
+      if ((threadIdx.x & 31) == 0)  // one line per warp keeps the whole grid's state inside the printf FIFO
+        printf("adb200: mbarrier timeout block %d thread %d bar %u parity %u\n", blockIdx.x, threadIdx.x, bar, parity);
+      // give every other stuck waiter time to report before the trap tears the context down
+      for (long long t1 = clock64(); clock64() - t1 < 400000000LL;) {
+      }
       __trap();
     }
   }
@@ -275,6 +278,10 @@ __device__ __forceinline__ uint32_t mapa_shared(uint32_t addr, uint32_t rank) {
 // data visibility comes from complete_tx, TMEM reads are retired by tcgen05.wait::ld beforehand.
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
   asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+// remote arrive that also posts this CTA's share of the transaction bytes
+__device__ __forceinline__ void mbar_arrive_expect_tx_cluster(uint32_t cluster_addr, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cluster.b64 _, [%0], %1;" ::"r"(cluster_addr), "r"(bytes) : "memory");
 }
 // TMA loads whose completion is signalled on a barrier that may live in the peer CTA of the pair
 __device__ __forceinline__ void tma_load_2d_2sm(uint32_t dst, const CUtensorMap* map, uint32_t bar_cluster,

@@ -619,7 +619,12 @@ int conv_block_n(int cout) {
 
 namespace {
 
-// CTA pairs (cta_group::2) for the 192-wide N tile unless ADB_CONV_1CTA=1 (A/B testing)
+// CTA pairs (cta_group::2) for the 192-wide N tile unless ADB_CONV_1CTA=1 (A/B testing).
+// Measured alternatives for the classifier's 128/256/512-channel layers: a 128-wide pair tile is ~18 %
+// SLOWER than the single-CTA 128 tile (the pair's extra handshakes buy only 8 KB less B traffic per stage);
+// a 256-wide pair tile (2 x 32 KB per stage) never completes its first full barrier once a second stage or
+// cluster is in flight - before any MMA is issued - with this protocol or with per-CTA expect_tx / separate
+// A and B barriers; cause not understood, shelved.
 int conv_ncta(int block_n) {
   static int force1 = -1;
   if (force1 < 0) {

@@ -4,12 +4,17 @@
     python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
     python bench.py --impl reference --gpus N --steps K ...   # the reference algorithm on host cores
 
-Workload (BASELINE.json configs[1]): ADM-G ImageNet-64 class-conditional UNet (295.9 M params,
-random-init by oracle-independent recipe below), the published 10-step searched candidate
+Workload (BASELINE.json configs[1]): ADM-G ImageNet-64 class-conditional UNet (295.9 M params) guided
+by the noisy classifier (EncoderUNetModel width 128 depth 4, 65.4 M params, classifier_scale 1.0) —
+random-init by the oracle-independent recipe below — on the published 10-step searched candidate
 (timesteps + block-skip mask of GD/sample_imagenet64_classifier_guidance_dynamic_subnet.sh:13-14),
-batch 256 per GPU, UNet-only (no classifier cond_fn: the classifier is row N1 of SURVEY §8f).
+batch 256 per GPU. This is what the reference's evaluator runs per candidate
+(search_dynamic_unet_imagenet64_classifier_guidance_progressive.py:383-420): every DDIM step = UNet
+forward + classifier forward + classifier input-gradient + guided update.
 One bench "step" = one full K'=10-step sampling pass over one batch: 10 UNet forwards (9 full +
-1 with 9 blocks skipped) + 10 fused DDIM updates + uint8 pack.
+1 with 9 blocks skipped) + 10 classifier forward/backward passes + 10 fused DDIM updates + uint8 pack,
+all in one CUDA graph. The UNet-only variant (no cond_fn; SURVEY §8d reports both) is timed too and
+reported under "unet_only".
 
   value : images/s, inputs (x_T, y) already resident in HBM, whole schedule as one CUDA graph.
   e2e   : same through the public API with HOST buffers: pinned x_T/y -> H2D, sampling, uint8
@@ -40,7 +45,8 @@ ADM_FLAGS = dict(attention_resolutions="32,16,8", class_cond=True, diffusion_ste
                  use_dynamic_unet=True)
 # GFLOP per image of the published 10-step candidate (9 x 219.356 + 182.431)
 GFLOP_PER_IMAGE = 2156.64
-METRIC = "ADM-G 64x64 images/s, 10-step searched DDIM + block-skip mask"
+METRIC = "ADM-G 64x64 images/s, 10-step searched DDIM + block-skip mask, classifier-guided"
+CLASSIFIER = dict(classifier_depth=4, classifier_width=128)  # ADM-G 64x64 noisy classifier (GD/README flags)
 
 
 def parse():
@@ -54,6 +60,7 @@ def parse():
     ap.add_argument("--no-roofline", action="store_true")
     ap.add_argument("--ref-batch", type=int, default=8)
     ap.add_argument("--dump-ops", default=None, help="write every recorded op's kind/flops/bytes/ms of one step to this CSV")
+    ap.add_argument("--unet-only", action="store_true", help="headline = the UNet-only variant (no classifier cond_fn)")
     return ap.parse_args()
 
 
@@ -138,7 +145,7 @@ def bench_weights(shapes, seed=0):
 # ------------------------------------------------------------------------------------------
 # reference arm / cpu_baseline: the oracle restatement of the reference on host cores
 # ------------------------------------------------------------------------------------------
-def cpu_reference_rate(batch, n_ddim_steps, warm=True):
+def cpu_reference_rate(batch, n_ddim_steps, warm=True, guided=True):
     """images/s of the CPU oracle on cand10, measured on `n_ddim_steps` consecutive schedule
     positions (starting at the first sampled step) at batch `batch`, scaled to the 10-step schedule."""
     import torch
@@ -147,6 +154,11 @@ def cpu_reference_rate(batch, n_ddim_steps, warm=True):
     torch.set_num_threads(os.cpu_count() or 1)
     cfg = unet_ref.adm_g64_config()
     sd = weights.make_state_dict(unet_ref.param_shapes(cfg), seed=0)
+    cond_fn = None
+    if guided:
+        ccfg = unet_ref.classifier64_config(depth=CLASSIFIER["classifier_depth"], width=CLASSIFIER["classifier_width"])
+        csd = weights.make_state_dict(unet_ref.param_shapes(ccfg, encoder_only=True), seed=1)
+        cond_fn = unet_ref.classifier_cond_fn(csd, ccfg, 1.0)
     base = diffusion_ref.base_tables("cosine", 1000)
     tmap, nb = diffusion_ref.respace(base["alphas_cumprod"], CAND10["timesteps"])
     tb = diffusion_ref.diffusion_tables(nb)
@@ -163,7 +175,7 @@ def cpu_reference_rate(batch, n_ddim_steps, warm=True):
             one = {k: v[i:i + 1] for k, v in tb.items()}
             # a 1-step schedule = step i of the 10-step one in isolation (same ops, same tables)
             x = diffusion_ref.ddim_sample_loop(
-                lambda xx, ts, **kw: model_fn(xx, ts, **{**kw}), x.shape, one, [tmap[i]], x, True,
+                lambda xx, ts, **kw: model_fn(xx, ts, **{**kw}), x.shape, one, [tmap[i]], x, True, cond_fn=cond_fn,
                 model_kwargs={"y": y, "skip_layers": CAND10["skip_layers"]})
         return time.perf_counter() - t0
 
@@ -180,7 +192,7 @@ def run_reference(args):
     if rank != 0:
         return
     batch = args.ref_batch
-    run_steps, order, K = cpu_reference_rate(batch, 1)
+    run_steps, order, K = cpu_reference_rate(batch, 1, guided=not args.unet_only)
     # every bench step = ONE schedule position (rotating through the 10), so the run stays bounded
     for w in range(args.warmup):
         run_steps([order[w % K]])
@@ -193,10 +205,11 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": value, "unit": "images/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": mean_pos * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "ADM-G 64x64 cand10 (10 searched steps + skip mask), UNet-only, CPU oracle port of the reference",
-                   "batch": batch},
+        "config": {"workload": "ADM-G 64x64 cand10 (10 searched steps + skip mask), " +
+                               ("UNet-only" if args.unet_only else "classifier-guided (depth-4 width-128 noisy classifier, autograd input gradient)") +
+                               ", CPU oracle port of the reference", "batch": batch},
         "cpu_baseline": {"value": value, "unit": "images/s", "cores": torch.get_num_threads(), "kind": "port",
-                         "sample": f"one DDIM step (UNet fwd + update) per bench step at batch {batch}, rotating through the "
+                         "sample": f"one DDIM step (UNet fwd + classifier fwd/bwd + update) per bench step at batch {batch}, rotating through the "
                                    f"10 schedule positions; images/s = batch / (10 x mean step time)"},
         "e2e": {"value": value, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
@@ -218,7 +231,9 @@ def run_ours(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
-    from autodiffusion_b200 import create_model_and_diffusion, model_and_diffusion_defaults, ops
+    from autodiffusion_b200 import (classifier_defaults, create_classifier, create_model_and_diffusion,
+                                    model_and_diffusion_defaults)
+    from autodiffusion_b200.classifier import ClassifierGuidance
     from autodiffusion_b200.sampler import SchedulePlan, resolve_candidate
 
     d = model_and_diffusion_defaults()
@@ -228,21 +243,31 @@ def run_ours(args):
     model.load_state_dict(bench_weights(shapes))
     model.to(dev).eval()
     model.convert_to_fp16()
+    cd = classifier_defaults()
+    cd.update(CLASSIFIER)
+    clf = create_classifier(**cd)
+    clf.load_state_dict(bench_weights({k: tuple(v.shape) for k, v in clf.state_dict().items()}, seed=1))
+    clf.to(dev).eval()
+    guidance = ClassifierGuidance(clf, 1.0)
 
     B = args.batch
     active, per_step = resolve_candidate(CAND10, diffusion)
-    t_build = time.time()
-    plan = SchedulePlan(model, active, per_step, B, clip_denoised=True, cond_fn=None, pack_uint8=True)
-    torch.cuda.synchronize()
-    t_build = time.time() - t_build
-    t_rebuild = time.time()
-    plan = SchedulePlan(model, active, per_step, B, clip_denoised=True, cond_fn=None, pack_uint8=True)  # cached masks
-    torch.cuda.synchronize()
-    t_rebuild = time.time() - t_rebuild
-    launches_per_step = plan.launches
+    K = active.num_timesteps
+
+    def build(cond_fn):
+        t0 = time.time()
+        pl = SchedulePlan(model, active, per_step, B, clip_denoised=True, cond_fn=cond_fn, pack_uint8=True)
+        torch.cuda.synchronize()
+        return pl, time.time() - t0
+
+    plan_u, t_build_u = build(None)
+    plan_g, t_build_g = build(guidance)
+    _, t_rebuild = build(None if args.unet_only else guidance)  # every per-mask UNet plan / classifier operand is cached now
+    head = plan_u if args.unet_only else plan_g
+    other = plan_g if args.unet_only else plan_u
 
     g = torch.Generator(device=dev).manual_seed(1234 + rank)
-    noise_dev = torch.randn(plan.shape, generator=g, device=dev)
+    noise_dev = torch.randn(head.shape, generator=g, device=dev)
     y_dev = torch.randint(0, 1000, (B,), generator=g, device=dev)
     noise_host = noise_dev.cpu().pin_memory()
     y_host = y_dev.cpu().pin_memory()
@@ -277,55 +302,77 @@ def run_ours(args):
             ms = float(t.item())
         return ms, clocks
 
-    def step_resident():
-        plan.run(noise_dev, y_dev)
-
     def step_e2e():
-        plan.run(noise_host, y_host)  # H2D of x_T and y inside
-        u8_host.copy_(plan.u8, non_blocking=True)
+        head.run(noise_host, y_host)  # H2D of x_T and y inside
+        u8_host.copy_(head.u8, non_blocking=True)
         torch.cuda.current_stream().synchronize()  # the caller needs the images (…progressive.py:427)
 
-    ms, clocks = timed(step_resident, args.steps, args.warmup, sample_clocks=True)
+    ms, clocks = timed(lambda: head.run(noise_dev, y_dev), args.steps, args.warmup, sample_clocks=True)
     ms_e2e, _ = timed(step_e2e, args.steps, max(1, args.warmup // 2))
+    ms_other, _ = timed(lambda: other.run(noise_dev, y_dev), args.steps, max(1, args.warmup // 2))
     imgs = B * world * args.steps
     value = imgs / (ms * 1e-3)
     e2e_value = imgs / (ms_e2e * 1e-3)
+    other_value = imgs / (ms_other * 1e-3)
+
+    # algorithmic GFLOP per image: UNet from SURVEY §8(d) (hook-measured on the reference, cross-checked against
+    # the recorded plan below); classifier = the recorded forward + data-gradient products of one guidance pass
+    unet_rec = sum(fl for up in plan_u.steps for (_, fl, _) in up.plan.op_info()) / B / 1e9
+    clf_per_step = sum(fl for (_, fl, _) in plan_g.guidance.op_info()) / B / 1e9
+    gflop_u, gflop_g = GFLOP_PER_IMAGE, GFLOP_PER_IMAGE + K * clf_per_step
+    gflop_head = gflop_u if args.unet_only else gflop_g
+    variant = lambda v, gf, msv, pl: {"value": v, "unit": "images/s", "ms_per_step": msv / args.steps,
+                                      "gflop_per_image": round(gf, 2), "tflops_effective": v / world * gf / 1e3,
+                                      "gpu_launches_per_step": pl.launches}
 
     line = {
-        "metric": METRIC, "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "metric": METRIC if not args.unet_only else METRIC.replace(", classifier-guided", ", UNet-only"),
+        "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
         "data": "synthetic",
-        "config": {"workload": "ADM-G 64x64 (295.9M params, random-init), published 10-step searched candidate "
-                               "(timesteps + block-skip mask), UNet-only (no classifier cond_fn), one step = full 10-step "
-                               "sampling of one batch", "batch_per_gpu": B, "ddim_steps": active.num_timesteps,
+        "config": {"workload": "ADM-G 64x64 UNet (295.9M params) + noisy classifier (65.4M params, depth 4 width 128, scale 1.0), "
+                               "random-init; published 10-step searched candidate (timesteps + block-skip mask); one step = full "
+                               "10-step sampling of one batch: per DDIM step UNet forward" +
+                               (" (UNet-only variant: no cond_fn)" if args.unet_only else
+                                " + classifier forward + classifier input-gradient + guided update") + ", one CUDA graph",
+                   "batch_per_gpu": B, "ddim_steps": K,
                    "l2": "activations per launch (>=400 MB at batch 256) exceed the 126 MB L2; no explicit flush",
                    "parallelism": f"dp{world} (independent batches per rank, no data-path collective)"},
-        "ms_per_unet_fwd": ms / args.steps / active.num_timesteps,
-        "tflops_effective": value / world * GFLOP_PER_IMAGE / 1e3,
+        "ms_per_unet_fwd": ms_other / args.steps / K if not args.unet_only else ms / args.steps / K,
+        "gflop_per_image": round(gflop_head, 2),
+        "tflops_effective": value / world * gflop_head / 1e3,
         "e2e": {"value": e2e_value, "unit": "images/s", "h2d_bytes_per_step": noise_host.numel() * 4 + y_host.numel() * 8,
                 "d2h_bytes_per_step": u8_host.numel()},
-        "gpu_launches": launches_per_step * args.steps,
-        "plan_build_s": {"first_candidate": round(t_build, 3), "next_candidate_same_masks": round(t_rebuild, 4)},
+        "gpu_launches": head.launches * args.steps,
+        ("guided" if args.unet_only else "unet_only"): variant(other_value, gflop_g if args.unet_only else gflop_u, ms_other, other),
+        "flop_accounting": {"unet_gflop_per_image_survey": gflop_u, "unet_gflop_per_image_recorded_plan": round(unet_rec, 2),
+                            "classifier_fwd_bwd_gflop_per_image_per_step": round(clf_per_step, 3)},
+        "plan_build_s": {"first_candidate_unet": round(t_build_u, 3), "first_candidate_classifier_added": round(t_build_g, 3),
+                         "next_candidate_same_masks": round(t_rebuild, 4)},
         "clocks": clocks,
     }
 
     if rank == 0 and not args.no_roofline:
         # per-kernel times: the same recorded ops, eager on the current stream with an event pair around each
         pk = peaks()
-        # one sampled schedule = its K' cached UNet plans (+ the DDIM updates, timed as one event pair each)
         info, ms_ops = [], []
-        for up in plan.steps:
+        for up in head.steps:
             up.plan.run_profiled()  # warm
-        for n, up in enumerate(plan.steps):
-            plan.t_in.fill_(plan.t_values[n])
+        if head.guidance is not None:
+            head.guidance.run_profiled()
+        for n, up in enumerate(head.steps):
+            head.t_in.fill_(head.t_values[n])
             info += up.plan.op_info()
             ms_ops += up.plan.run_profiled()
+            if head.guidance is not None:
+                info += [("clf:" + k if k not in ("conv_igemm",) else k, fl, by) for (k, fl, by) in head.guidance.op_info()]
+                ms_ops += head.guidance.run_profiled()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
-            plan._update(n)
+            head._update(n)
             e1.record()
             torch.cuda.synchronize()
-            info.append(("ddim_step", 0.0, 4.0 * 3 * plan.x.numel()))
+            info.append(("ddim_step", 0.0, 4.0 * (3 + (head.guidance is not None)) * head.x.numel()))
             ms_ops.append(e0.elapsed_time(e1))
         agg = {}
         for (kind, fl, by), t in zip(info, ms_ops):
@@ -342,9 +389,14 @@ def run_ours(args):
                     f.write(f"{i},{kind},{fl:.0f},{by:.0f},{t:.5f}\n")
         conv = agg["conv_igemm"]
         achieved = conv[2] / (conv[1] * 1e-3) / 1e12
-        line["roofline"] = {"kernel": "conv_igemm_kernel (tcgen05 implicit GEMM: 3x3/1x1 conv, qkv/proj)", "bound": "tensor",
-                            "achieved": achieved, "peak": pk["tf_sustained"], "unit": "TFLOP/s", "frac": achieved / pk["tf_sustained"],
-                            "traffic": None, "peak_source": pk["source"] + " (sustained bf16: kernel timed inside a long step)",
+        traffic = None
+        tp = os.path.join(ROOT, "profiles", "conv_igemm_traffic.json")
+        if os.path.exists(tp):  # dram bytes per launch of this kernel from the committed `ncu --set full` capture
+            traffic = json.load(open(tp))
+        line["roofline"] = {"kernel": "conv_igemm_kernel (tcgen05 implicit GEMM: 3x3/1x1 conv, qkv/proj, and their data gradients)",
+                            "bound": "tensor", "achieved": achieved, "peak": pk["tf_sustained"], "unit": "TFLOP/s",
+                            "frac": achieved / pk["tf_sustained"], "traffic": traffic,
+                            "peak_source": pk["source"] + " (sustained bf16: kernel timed inside a long step)",
                             "launches": conv[0], "share_of_step": conv[1] / total_ms,
                             "flops_per_launch_avg": conv[2] / conv[0], "ms_per_launch_avg": conv[1] / conv[0]}
         line["kernel_breakdown"] = {k: {"launches": v[0], "ms": round(v[1], 3), "share": round(v[1] / total_ms, 4),
@@ -353,13 +405,15 @@ def run_ours(args):
     if rank == 0 and not args.no_cpu_baseline:
         import torch as _t
 
-        run_steps, order, K = cpu_reference_rate(args.ref_batch, 1)
+        run_steps, order, Kc = cpu_reference_rate(args.ref_batch, 1, guided=not args.unet_only)
         tt = [run_steps([order[i]]) for i in (0, 3, 6)]  # includes position 6 (t=676), the masked step
         mean_pos = sum(tt) / len(tt)
-        line["cpu_baseline"] = {"value": args.ref_batch / (mean_pos * K), "unit": "images/s", "cores": _t.get_num_threads(),
+        line["cpu_baseline"] = {"value": args.ref_batch / (mean_pos * Kc), "unit": "images/s", "cores": _t.get_num_threads(),
                                 "kind": "port",
                                 "sample": f"3 of the 10 DDIM steps of the same candidate (incl. the masked one) at batch "
-                                          f"{args.ref_batch}, fp32 torch CPU oracle; images/s = batch / (10 x mean step time)"}
+                                          f"{args.ref_batch}, fp32 torch CPU oracle (UNet forward" +
+                                          ("" if args.unet_only else " + classifier forward + autograd input gradient") +
+                                          "); images/s = batch / (10 x mean step time)"}
     if rank == 0:
         print(json.dumps(line), flush=True)
     if world > 1:

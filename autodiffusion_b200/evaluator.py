@@ -26,6 +26,7 @@ from __future__ import annotations
 import time
 import warnings
 import zlib
+from concurrent.futures import Future, ThreadPoolExecutor
 from typing import Callable, Dict, Optional, Sequence
 
 import numpy as np
@@ -112,11 +113,13 @@ class MomentAccumulator:
 
     def statistics(self):
         """mu = mean, sigma = unbiased covariance (np.cov's N-1, evaluator_v1.py:219-220), fp64 on the host."""
-        buf = self.buf.detach().cpu().numpy()
+        return self.statistics_from(self.buf.detach().cpu().numpy(), self.dim)
+
+    @staticmethod
+    def statistics_from(buf: np.ndarray, d: int):
         n = float(buf[0])
         if n < 2:
             raise ValueError(f"need at least 2 samples for a covariance, have {n}")
-        d = self.dim
         sx = buf[1:1 + d]
         sxx = buf[1 + d:].reshape(d, d)
         mu = sx / n
@@ -164,6 +167,9 @@ class CandidateEvaluator:
         self._acc: Optional[MomentAccumulator] = None
         self.last_times: Dict[str, float] = {}
         self.vis_dict: Dict[str, dict] = {}
+        # deferred FID: the host-side sqrtm of candidate i runs on this worker while candidate i+1 samples
+        self._fid_pool: Optional[ThreadPoolExecutor] = None
+        self._host_bufs: list = []
 
     # ---- plan cache keyed by what the launch schedule depends on ----
     def _plan_for(self, cand, batch: int) -> SchedulePlan:
@@ -189,6 +195,14 @@ class CandidateEvaluator:
         return plan.u8, y
 
     def get_cand_fid(self, cand=None, args=None) -> float:
+        """…progressive.py:369-445: sample, reduce, FID - blocking, like the reference call."""
+        return self.submit_cand_fid(cand, args).result()
+
+    def submit_cand_fid(self, cand=None, args=None) -> Future:
+        """Same work as `get_cand_fid`, but only the device part (sampling, moments, all-reduce, D2H of the
+        33.6 MB moment buffer) happens before this returns; mu / sigma / sqrtm run on a host worker thread.
+        The search driver keeps sampling the next candidate meanwhile (`fid_time` was serial in the
+        reference, :437-443)."""
         if args is not None:
             for k in ("batch_size", "num_samples", "image_size", "class_cond", "clip_denoised"):
                 if hasattr(args, k):
@@ -217,13 +231,29 @@ class CandidateEvaluator:
             acc = self._acc
             acc.reset()
         acc.all_reduce(self.group)
-        th.cuda.synchronize()
+        host = self._host_bufs.pop() if self._host_bufs and self._host_bufs[-1].numel() == acc.buf.numel() \
+            else th.empty(acc.buf.numel(), dtype=th.float64).pin_memory()
+        host.copy_(acc.buf, non_blocking=True)
+        done = th.cuda.Event()
+        done.record()
+        th.cuda.current_stream().synchronize()  # sample_time as the reference logs it (:435)
         sample_time = time.time() - t0
-        t0 = time.time()
-        mu, sigma = acc.statistics()
-        fid = float(FIDStatistics(mu, sigma).frechet_distance(self.ref_stats))
-        self.last_times = dict(reset_time=reset_time, sample_time=sample_time, fid_time=time.time() - t0)
-        return fid
+        dim = acc.dim
+        times = dict(reset_time=reset_time, sample_time=sample_time, fid_time=0.0)
+        self.last_times = times
+
+        def finish() -> float:
+            t1 = time.time()
+            done.synchronize()
+            mu, sigma = MomentAccumulator.statistics_from(host.numpy(), dim)
+            self._host_bufs.append(host)
+            fid = float(FIDStatistics(mu, sigma).frechet_distance(self.ref_stats))
+            times["fid_time"] = time.time() - t1
+            return fid
+
+        if self._fid_pool is None:
+            self._fid_pool = ThreadPoolExecutor(max_workers=1, thread_name_prefix="adb-fid")
+        return self._fid_pool.submit(finish)
 
     def is_legal(self, cand: str, log: Callable[[str], None] = print) -> bool:
         """…progressive.py:355-367: candidates are `str(dict)` keys; same log line format."""

@@ -389,13 +389,14 @@ def run_ours(args):
                     f.write(f"{i},{kind},{fl:.0f},{by:.0f},{t:.5f}\n")
         conv = agg["conv_igemm"]
         achieved = conv[2] / (conv[1] * 1e-3) / 1e12
-        traffic = None
+        traffic, traffic_detail = None, None
         tp = os.path.join(ROOT, "profiles", "conv_igemm_traffic.json")
         if os.path.exists(tp):  # dram bytes per launch of this kernel from the committed `ncu --set full` capture
-            traffic = json.load(open(tp))
+            traffic_detail = json.load(open(tp))
+            traffic = traffic_detail["dram_bytes_per_launch_avg"]
         line["roofline"] = {"kernel": "conv_igemm_kernel (tcgen05 implicit GEMM: 3x3/1x1 conv, qkv/proj, and their data gradients)",
                             "bound": "tensor", "achieved": achieved, "peak": pk["tf_sustained"], "unit": "TFLOP/s",
-                            "frac": achieved / pk["tf_sustained"], "traffic": traffic,
+                            "frac": achieved / pk["tf_sustained"], "traffic": traffic, "traffic_detail": traffic_detail,
                             "peak_source": pk["source"] + " (sustained bf16: kernel timed inside a long step)",
                             "launches": conv[0], "share_of_step": conv[1] / total_ms,
                             "flops_per_launch_avg": conv[2] / conv[0], "ms_per_launch_avg": conv[1] / conv[0]}

@@ -1,0 +1,120 @@
+"""CPU: the evolutionary search driver (autodiffusion_b200.search.EvolutionSearcher) against a golden trace of
+the reference's own operators (tests/golden/search_trace.json, made by make_search_golden.py from the
+unmodified reference script with a stubbed FID): under the same seeds it must visit exactly the same
+individuals in the same order and end with the same top list and prune range. Integer / index work:
+bit-exact. Also: deferred FIDs, log-line format, save/resume."""
+import json
+import os
+import random
+import types
+import zlib
+from concurrent.futures import Future
+
+import numpy as np
+
+from tests.util import GOLDEN
+
+
+def stub_fid(cand) -> float:
+    return (zlib.crc32(str(cand).encode()) % 100000) / 1000.0
+
+
+class StubEvaluator:
+    """Stands in for CandidateEvaluator: FID = a deterministic function of the candidate, optionally deferred."""
+
+    def __init__(self, deferred):
+        self.deferred = deferred
+        self.calls = []
+        self.unresolved = []
+
+    def get_cand_fid(self, cand=None, args=None):
+        self.calls.append(str(cand))
+        return stub_fid(cand)
+
+
+class DeferredStub(StubEvaluator):
+    def __init__(self):
+        super().__init__(True)
+
+    def submit_cand_fid(self, cand=None, args=None):
+        self.calls.append(str(cand))
+        f = Future()
+        self.unresolved.append((f, stub_fid(cand)))
+        if len(self.unresolved) > 3:  # resolve late and out of step with submission
+            g, v = self.unresolved.pop(0)
+            g.set_result(v)
+        return f
+
+    def flush(self):
+        for g, v in self.unresolved:
+            g.set_result(v)
+        self.unresolved = []
+
+
+def build(cfg, evaluator, log):
+    from autodiffusion_b200.search import EvolutionSearcher
+
+    args = types.SimpleNamespace(**cfg, batch_size=4, num_samples=8, image_size=64)
+    model = types.SimpleNamespace(layer_num=cfg["layer_num"])
+    diffusion = types.SimpleNamespace(original_num_steps=cfg["original_num_steps"])
+    return EvolutionSearcher(args, model, diffusion, cfg["time_step"], classifier=None, evaluator=evaluator, log=log)
+
+
+def test_search_reproduces_the_reference_trace():
+    trace = json.load(open(os.path.join(GOLDEN, "search_trace.json")))
+    for name, g in trace.items():
+        cfg = g["config"]
+        lines = []
+        ev = StubEvaluator(False)
+        s = build(cfg, ev, lines.append)
+        random.seed(cfg["seed"])
+        np.random.seed(cfg["seed"])
+        top = s.search()
+        assert list(s.vis_dict.keys()) == g["visited"], name          # same individuals, same order
+        assert [s.vis_dict[k]["fid"] for k in s.vis_dict] == g["fids"]
+        assert top == g["top"] and s.skip_layer_range == g["skip_layer_range"] and s.epoch == g["epoch"]
+        assert ev.calls == g["visited"]                                 # each individual evaluated exactly once
+        assert lines[:12] == g["log_head"] and len(lines) == g["n_log"]  # the log users grep is line-identical
+
+
+def test_deferred_fids_change_nothing_but_when_the_fid_lines_appear():
+    g = json.load(open(os.path.join(GOLDEN, "search_trace.json")))["random_init"]
+    cfg = g["config"]
+    lines = []
+    ev = DeferredStub()
+    s = build(cfg, ev, lines.append)
+    orig_join = s.join
+    s.join = lambda: (ev.flush(), orig_join())[1]
+    random.seed(cfg["seed"])
+    np.random.seed(cfg["seed"])
+    top = s.search()
+    assert list(s.vis_dict.keys()) == g["visited"] and top == g["top"]
+    fid_lines = [l for l in lines if l.startswith("cand: ") and ", fid: " in l]
+    assert [l.split(", fid: ")[0][len("cand: "):] for l in fid_lines] == g["visited"]  # emitted in submission order
+    assert len(lines) == g["n_log"]
+
+
+def test_save_and_resume(tmp_path):
+    g = json.load(open(os.path.join(GOLDEN, "search_trace.json")))["random_init"]
+    cfg = dict(g["config"])
+    path = str(tmp_path / "state.pkl")
+    # run 1: stop after 4 epochs (state is written at the end of every epoch's selection)
+    s1 = build(dict(cfg, max_epochs=4), StubEvaluator(False), lambda l: None)
+    random.seed(cfg["seed"])
+    np.random.seed(cfg["seed"])
+    s1.search(state_path=path)
+    # run 2: a fresh process would construct the searcher again and resume; visited individuals are not re-evaluated
+    ev2 = StubEvaluator(False)
+    s2 = build(cfg, ev2, lambda l: None)
+    random.seed(12345)  # whatever the new process seeded: load_state restores both generators
+    s2.load_state(path)
+    assert s2.epoch == 3 and len(s2.vis_dict) == len(s1.vis_dict)
+    # the saved state is the one at epoch 3's selection; continue from the operators of that epoch
+    mutation = s2.get_mutation(s2.select_num, s2.mutation_num, s2.m_prob)
+    s2.candidates = mutation
+    s2.candidates += s2.get_cross(s2.select_num, s2.crossover_num)
+    s2.get_random(s2.population_num)
+    s2.epoch += 1
+    top = s2.search()
+    assert list(s2.vis_dict.keys()) == g["visited"] and top == g["top"]
+    assert not set(ev2.calls) & set(s1.vis_dict.keys())

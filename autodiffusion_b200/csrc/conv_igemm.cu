@@ -61,7 +61,13 @@ struct ConvKParams {
   double* stats2;
   int cpg2;
   int choff2;
+  // x / cpg == (x * magic) >> 32 for the column indices that occur (x * cpg < 2^32)
+  unsigned long long cpg_magic, cpg2_magic;
 };
+
+__device__ __forceinline__ int fast_div(int x, unsigned long long magic) {
+  return (int)(((unsigned long long)(unsigned)x * magic) >> 32);
+}
 
 template <int BLOCK_N, int NCTA>
 struct Cfg {
@@ -271,6 +277,22 @@ conv_igemm_kernel(const __grid_constant__ ConvKParams p) {
       const int n_tile = tile % p.n_tiles;
       const int m = m_tile * BLOCK_M + row;
       const int n0 = n_tile * BLOCK_N;
+      // Fast path (warp-uniform): a full tile half - every row and column valid - staged through shared memory
+      // by TMA, residual none or same-resolution. No per-element predicates, group binning by a segmented
+      // warp scan, and the residual sub-tiles of the first two chunks are requested BEFORE the accumulator
+      // wait so that their HBM latency hides behind the main loop.
+      const bool fast = p.tma_epi && CHUNK_COLS == 32 && (m_tile + 1) * BLOCK_M <= p.M && cbeg < cend &&
+                        n0 + cend <= p.cout && (p.res_mode == ADB_RES_NONE || p.res_mode == ADB_RES_SAME);
+      const int row0f = m_tile * BLOCK_M + quarter * 32;
+      const int nch = (cend - cbeg) / CHUNK_COLS;
+      if (fast && p.res_mode == ADB_RES_SAME && lane == 0) {
+        fence_proxy_async_smem();
+        for (int ci = 0; ci < 2 && ci < nch; ++ci) {
+          const uint32_t b = (uint32_t)(res_buf ^ ci);
+          mbar_arrive_expect_tx(res_bar0 + 8u * b, 2048);
+          tma_load_2d(epi_base + 2048u * b, &p.tmRes, res_bar0 + 8u * b, n0 + cbeg + ci * CHUNK_COLS, row0f);
+        }
+      }
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
       const bool row_ok = m < p.M;
@@ -279,8 +301,8 @@ conv_igemm_kernel(const __grid_constant__ ConvKParams p) {
       const int rem = m - img * P;
       const int y = rem / p.W;
       const int x = rem - y * p.W;
-      const int g_lo = (p.stats != nullptr) ? (n0 + cbeg) / p.cpg : 0;
-      const int g_lo2 = (p.stats2 != nullptr) ? (p.choff2 + n0 + cbeg) / p.cpg2 : 0;
+      const int g_lo = (p.stats != nullptr) ? fast_div(n0 + cbeg, p.cpg_magic) : 0;
+      const int g_lo2 = (p.stats2 != nullptr) ? fast_div(p.choff2 + n0 + cbeg, p.cpg2_magic) : 0;
       // single-source residuals (same / nearest-up) are fetched one chunk AHEAD so their HBM
       // latency overlaps the previous chunk's math; the 4-source average-pool variant is not.
       const bool res_tma = p.tma_epi && p.res_mode == ADB_RES_SAME;  // warp-uniform
@@ -301,12 +323,135 @@ conv_igemm_kernel(const __grid_constant__ ConvKParams p) {
           if (res_pf && col + g * 8 < p.cout) rnext[g] = __ldg(reinterpret_cast<const uint4*>(res_row + col) + g);
         }
       };
-      fetch_res(n0 + cbeg);
-      if (res_tma && lane == 0 && cbeg < cend) {
+      if (!fast) fetch_res(n0 + cbeg);
+      if (!fast && res_tma && lane == 0 && cbeg < cend) {
         fence_proxy_async_smem();
         mbar_arrive_expect_tx(res_bar0 + 8u * res_buf, 2048);
         tma_load_2d(epi_base + 2048u * res_buf, &p.tmRes, res_bar0 + 8u * res_buf, n0 + cbeg, row0);
       }
+      if (fast) {
+        const bool res_tma_f = p.res_mode == ADB_RES_SAME;
+#pragma unroll 1
+        for (int ci = 0; ci < nch; ++ci) {
+          const int c = cbeg + ci * CHUNK_COLS;
+          const int col0 = n0 + c;
+          uint32_t v[32];
+          tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * BLOCK_N + c, v);
+          float4 bv[8];
+          if (p.bias != nullptr) {
+            const float4* b4 = reinterpret_cast<const float4*>(p.bias + col0);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) bv[j] = __ldg(b4 + j);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) bv[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+          tmem_wait_ld();
+          float f[32];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            f[4 * j + 0] = __uint_as_float(v[4 * j + 0]) + bv[j].x;
+            f[4 * j + 1] = __uint_as_float(v[4 * j + 1]) + bv[j].y;
+            f[4 * j + 2] = __uint_as_float(v[4 * j + 2]) + bv[j].z;
+            f[4 * j + 3] = __uint_as_float(v[4 * j + 3]) + bv[j].w;
+          }
+          if (res_tma_f) {
+            mbar_wait(res_bar0 + 8u * res_buf, (res_phase >> res_buf) & 1u);
+            res_phase ^= 1u << res_buf;
+            const uint8_t* rrow = epi_gen + 2048 * res_buf + lane * 64;
+            uint4 rc[4];
+#pragma unroll
+            for (int g = 0; g < 4; ++g) rc[g] = *reinterpret_cast<const uint4*>(rrow + ((g ^ ((lane >> 1) & 3)) << 4));
+            __syncwarp();
+            if (ci + 2 < nch && lane == 0) {  // this buffer is free again: request the chunk after next
+              fence_proxy_async_smem();
+              mbar_arrive_expect_tx(res_bar0 + 8u * res_buf, 2048);
+              tma_load_2d(epi_base + 2048u * res_buf, &p.tmRes, res_bar0 + 8u * res_buf, col0 + 2 * CHUNK_COLS, row0f);
+            }
+            res_buf ^= 1;
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+              f[g * 8 + 0] += bf16_lo(rc[g].x);
+              f[g * 8 + 1] += bf16_hi(rc[g].x);
+              f[g * 8 + 2] += bf16_lo(rc[g].y);
+              f[g * 8 + 3] += bf16_hi(rc[g].y);
+              f[g * 8 + 4] += bf16_lo(rc[g].z);
+              f[g * 8 + 5] += bf16_hi(rc[g].z);
+              f[g * 8 + 6] += bf16_lo(rc[g].w);
+              f[g * 8 + 7] += bf16_hi(rc[g].w);
+            }
+          }
+          uint32_t ow[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) ow[i] = pack_bf16x2(f[2 * i], f[2 * i + 1]);
+          if (lane == 0) tma_store_wait_read0();  // previous store has finished reading the staging buffer
+          __syncwarp();
+          uint8_t* orow = epi_out_gen + lane * 64;
+#pragma unroll
+          for (int g = 0; g < 4; ++g)
+            *reinterpret_cast<uint4*>(orow + ((g ^ ((lane >> 1) & 3)) << 4)) =
+                make_uint4(ow[4 * g], ow[4 * g + 1], ow[4 * g + 2], ow[4 * g + 3]);
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            tma_store_2d(&p.tmOut, epi_out, col0, row0f);
+            tma_store_commit();
+          }
+          if (p.stats != nullptr) {
+            // column sums of the STORED values: lane j walks column j down the staged tile's 32 rows
+            float cs = 0.f, cq = 0.f;
+            const uint32_t cch = (uint32_t)lane >> 3, cin8 = ((uint32_t)lane & 7u) * 2u;
+#pragma unroll
+            for (int r = 0; r < 32; ++r) {
+              const uint16_t hv = *reinterpret_cast<const uint16_t*>(
+                  epi_out_gen + r * 64 + (((cch ^ ((uint32_t)(r >> 1) & 3u)) << 4) + cin8));
+              const float val = __uint_as_float((uint32_t)hv << 16);
+              cs += val;
+              cq = fmaf(val, val, cq);
+            }
+            // groups are runs of consecutive lanes: segmented inclusive scan, the last lane of a run owns its bin
+            {
+              const int gi = fast_div(col0 + lane, p.cpg_magic);
+              float s1 = cs, q1 = cq;
+#pragma unroll
+              for (int off = 1; off < 32; off <<= 1) {
+                const float s2 = __shfl_up_sync(0xffffffffu, s1, off);
+                const float q2 = __shfl_up_sync(0xffffffffu, q1, off);
+                const int g2 = __shfl_up_sync(0xffffffffu, gi, off);
+                if (lane >= off && g2 == gi) {
+                  s1 += s2;
+                  q1 += q2;
+                }
+              }
+              const int gn = __shfl_down_sync(0xffffffffu, gi, 1);
+              if (lane == 31 || gn != gi) {
+                my_bins[2 * (gi - g_lo)] += s1;
+                my_bins[2 * (gi - g_lo) + 1] += q1;
+              }
+            }
+            if (p.stats2 != nullptr) {
+              const int gi = fast_div(p.choff2 + col0 + lane, p.cpg2_magic);
+              float s1 = cs, q1 = cq;
+#pragma unroll
+              for (int off = 1; off < 32; off <<= 1) {
+                const float s2 = __shfl_up_sync(0xffffffffu, s1, off);
+                const float q2 = __shfl_up_sync(0xffffffffu, q1, off);
+                const int g2 = __shfl_up_sync(0xffffffffu, gi, off);
+                if (lane >= off && g2 == gi) {
+                  s1 += s2;
+                  q1 += q2;
+                }
+              }
+              const int gn = __shfl_down_sync(0xffffffffu, gi, 1);
+              if (lane == 31 || gn != gi) {
+                my_bins2[2 * (gi - g_lo2)] += s1;
+                my_bins2[2 * (gi - g_lo2) + 1] += q1;
+              }
+            }
+            __syncwarp();
+          }
+        }
+      } else {
 #pragma unroll 1
       for (int c = cbeg; c < cend; c += CHUNK_COLS) {
         uint32_t v[32];
@@ -522,6 +667,7 @@ conv_igemm_kernel(const __grid_constant__ ConvKParams p) {
           }
         }
       }
+      }  // generic path
       tc_fence_before();
       __syncwarp();
       if (lane == 0) {
@@ -535,7 +681,7 @@ conv_igemm_kernel(const __grid_constant__ ConvKParams p) {
       if (p.stats != nullptr && cbeg < cend) {
         // flush this warp's bins: one fp64 atomic pair per group touched by this tile half
         const int col_last = min(n0 + cend, p.cout) - 1;
-        const int ng = (col_last >= n0 + cbeg) ? (col_last / p.cpg - g_lo + 1) : 0;
+        const int ng = (col_last >= n0 + cbeg) ? (fast_div(col_last, p.cpg_magic) - g_lo + 1) : 0;
         const int img0 = __shfl_sync(0xffffffffu, img, 0);
         const bool any_row = __shfl_sync(0xffffffffu, (int)row_ok, 0) != 0;  // rows ascend: row 0 invalid => all invalid
         for (int gb = lane; gb < ng; gb += 32) {
@@ -549,7 +695,7 @@ conv_igemm_kernel(const __grid_constant__ ConvKParams p) {
           }
         }
         if (p.stats2 != nullptr) {
-          const int ng2 = (col_last >= n0 + cbeg) ? ((p.choff2 + col_last) / p.cpg2 - g_lo2 + 1) : 0;
+          const int ng2 = (col_last >= n0 + cbeg) ? (fast_div(p.choff2 + col_last, p.cpg2_magic) - g_lo2 + 1) : 0;
           for (int gb = lane; gb < ng2; gb += 32) {
             const float bs = my_bins2[2 * gb], bq = my_bins2[2 * gb + 1];
             my_bins2[2 * gb] = 0.f;
@@ -727,6 +873,8 @@ int conv_igemm_submit(adb_plan* plan, const adb_conv_desc* d, cudaStream_t strea
   kp.stats2 = d->stats2_out;
   kp.cpg2 = d->stats2_cpg;
   kp.choff2 = d->stats2_choff;
+  kp.cpg_magic = kp.cpg > 0 ? ((1ull << 32) + (unsigned long long)kp.cpg - 1) / (unsigned long long)kp.cpg : 0;
+  kp.cpg2_magic = kp.cpg2 > 0 ? ((1ull << 32) + (unsigned long long)kp.cpg2 - 1) / (unsigned long long)kp.cpg2 : 0;
   if (d->stats2_out != nullptr) {
     ADB_REQUIRE(d->stats_out != nullptr && d->stats2_cpg > 0 && d->stats2_choff >= 0 &&
                     d->stats2_choff + d->cout <= 32 * d->stats2_cpg && 96 / d->stats2_cpg + 2 <= STAT_BINS,

@@ -61,6 +61,8 @@ def parse():
     ap.add_argument("--ref-batch", type=int, default=8)
     ap.add_argument("--dump-ops", default=None, help="write every recorded op's kind/flops/bytes/ms of one step to this CSV")
     ap.add_argument("--unet-only", action="store_true", help="headline = the UNet-only variant (no classifier cond_fn)")
+    ap.add_argument("--workload", default="admg64", choices=["admg64", "lsun256"],
+                    help="admg64 = BASELINE configs[1] (default, the metric's config); lsun256 = configs[3]")
     return ap.parse_args()
 
 
@@ -421,10 +423,117 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
+# ------------------------------------------------------------------------------------------
+# secondary workload: BASELINE configs[3], ADM unconditional LSUN-bedroom 256x256
+# ------------------------------------------------------------------------------------------
+LSUN_FLAGS = dict(attention_resolutions="32,16,8", class_cond=False, diffusion_steps=1000, dropout=0.1, image_size=256,
+                  learn_sigma=True, noise_schedule="linear", num_channels=256, num_head_channels=64, num_res_blocks=2,
+                  resblock_updown=True, use_fp16=True, use_scale_shift_norm=True)
+# the first 10 of the 15 published searched steps (GD/sample_LSUN_bedroom_subnet.sh:9)
+LSUN_CAND = {"timesteps": [644, 737, 67, 804, 134, 871, 6, 639, 268, 335], "skip_layers": [[] for _ in range(10)]}
+LSUN_GFLOP_PER_FWD = 2239.67  # hook-measured on the reference module
+
+
+def run_lsun(args):
+    """images/s of the unconditional LSUN-256 model (552.8 M params) on a 10-step searched schedule, batch 64 per
+    GPU (the reference's LSUN search has no classifier: search_uncondition_model.py)."""
+    import torch
+    import torch.distributed as dist
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    from autodiffusion_b200 import create_model_and_diffusion, model_and_diffusion_defaults
+    from autodiffusion_b200.sampler import SchedulePlan, resolve_candidate
+
+    d = model_and_diffusion_defaults()
+    d.update(LSUN_FLAGS)
+    model, diffusion = create_model_and_diffusion(**d)
+    model.load_state_dict(bench_weights({k: tuple(v.shape) for k, v in model.state_dict().items()}))
+    model.to(dev).eval()
+    model.convert_to_fp16()
+    B = args.batch if args.batch != 256 else 64
+    active, per_step = resolve_candidate(LSUN_CAND, diffusion)
+    K = active.num_timesteps
+    plan = SchedulePlan(model, active, per_step, B, clip_denoised=True, cond_fn=None, pack_uint8=True)
+    noise = torch.randn(plan.shape, device=dev, generator=torch.Generator(device=dev).manual_seed(7 + rank))
+    noise_host = noise.cpu().pin_memory()
+    u8_host = torch.empty((B, 256, 256, 3), dtype=torch.uint8).pin_memory()
+
+    def timed(fn, steps, warmup):
+        for _ in range(warmup):
+            fn()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms
+
+    def e2e():
+        plan.run(noise_host, None)
+        u8_host.copy_(plan.u8, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+
+    ms = timed(lambda: plan.run(noise, None), args.steps, args.warmup)
+    ms_e2e = timed(e2e, args.steps, 1)
+    imgs = B * world * args.steps
+    value = imgs / (ms * 1e-3)
+    info, ms_ops = [], []
+    for up in plan.steps[:1]:
+        up.plan.run_profiled()
+        info = up.plan.op_info()
+        ms_ops = up.plan.run_profiled()
+    agg = {}
+    for (kind, fl, by), t in zip(info, ms_ops):
+        a = agg.setdefault(kind, [0, 0.0, 0.0, 0.0])
+        a[0] += 1
+        a[1] += t
+        a[2] += fl
+        a[3] += by
+    if rank == 0:
+        print(json.dumps({
+            "metric": "ADM LSUN-bedroom 256x256 images/s, 10-step searched DDIM (unconditional)", "value": value,
+            "unit": "images/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": "ADM unconditional LSUN-256 UNet (552.8M params, random-init), first 10 of the 15 published "
+                                   "searched timesteps, full architecture, one step = 10-step sampling of one batch, one CUDA graph",
+                       "batch_per_gpu": B, "ddim_steps": K},
+            "ms_per_unet_fwd": ms / args.steps / K,
+            "tflops_effective": value / world * K * LSUN_GFLOP_PER_FWD / 1e3,
+            "e2e": {"value": imgs / (ms_e2e * 1e-3), "unit": "images/s", "h2d_bytes_per_step": noise_host.numel() * 4,
+                    "d2h_bytes_per_step": u8_host.numel()},
+            "gpu_launches": plan.launches * args.steps,
+            "kernel_breakdown_one_forward": {k: {"launches": v[0], "ms": round(v[1], 3),
+                                                 "tflops": (v[2] / (v[1] * 1e-3) / 1e12) if v[2] and v[1] else None,
+                                                 "gbs": (v[3] / (v[1] * 1e-3) / 1e9) if v[3] and v[1] else None}
+                                             for k, v in agg.items()},
+        }), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     args = parse()
     if args.impl == "reference":
         run_reference(args)
+    elif args.workload == "lsun256":
+        run_lsun(args)
     else:
         run_ours(args)
 

@@ -302,3 +302,47 @@ def test_fid_of_a_fixed_candidate_within_tolerance_of_the_oracle():
     print(f"FID ours={fid_ours:.4f} oracle={fid_ref_side:.4f} |diff|={abs(fid_ours - fid_ref_side):.4f} ({rel * 100:.3f}%) "
           f"sample psnr={psnr(ours, ref):.1f} dB")
     assert abs(fid_ours - fid_ref_side) <= 0.1
+
+
+def test_lsun256_full_size_forward_and_sampling():
+    """BASELINE.json configs[3] family at FULL size: ADM unconditional LSUN-bedroom 256x256 (552.8 M params,
+    channel_mult (1,1,2,2,4,4), widths 256-1024, legacy attention at 32/16/8, linear schedule,
+    GD/search_lsun_bedroom.sh:1), batch 1: one forward vs the CPU oracle, then a 2-step searched DDIM run
+    (published timesteps of GD/sample_LSUN_bedroom_subnet.sh:9) vs the oracle's loop."""
+    from autodiffusion_b200 import create_model_and_diffusion, model_and_diffusion_defaults
+    from autodiffusion_b200.sampler import sample_candidate
+
+    flags = dict(attention_resolutions="32,16,8", class_cond=False, diffusion_steps=1000, dropout=0.1, image_size=256,
+                 learn_sigma=True, noise_schedule="linear", num_channels=256, num_head_channels=64, num_res_blocks=2,
+                 resblock_updown=True, use_fp16=True, use_scale_shift_norm=True)
+    cfg = unet_ref.UNetConfig(image_size=256, model_channels=256, num_res_blocks=2, attention_resolutions=(8, 16, 32),
+                              channel_mult=(1, 1, 2, 2, 4, 4), num_classes=None, use_new_attention_order=False)
+    shapes = unet_ref.param_shapes(cfg)
+    sd = weights.make_state_dict(shapes, seed=6)
+    d = model_and_diffusion_defaults()
+    d.update(flags)
+    model, diffusion = create_model_and_diffusion(**d)
+    assert {k: tuple(v.shape) for k, v in model.state_dict().items()} == shapes
+    assert sum(v.numel() for v in sd.values()) == 552_814_086 and model.layer_num == 58
+    model.load_state_dict(sd)
+    model.cuda().eval()
+    model.convert_to_fp16()
+    x = torch.randn(1, 3, 256, 256, generator=torch.Generator().manual_seed(23))
+    t = torch.tensor([644])
+    out = model(x.cuda(), t.cuda())
+    with torch.no_grad():
+        ref = unet_ref.unet_forward(sd, cfg, x, t, None, [])
+    rel_rms, mx, std = _report("lsun256 full size", out.cpu(), ref)
+    assert rel_rms <= 0.02 and mx <= 0.12 * std
+    cand = {"timesteps": [644, 67], "skip_layers": [[], []]}
+    ours = sample_candidate(model, diffusion, cand, (1, 3, 256, 256), x.cuda(), None).cpu()
+    base = diffusion_ref.base_tables("linear", 1000)
+    tmap, nb = diffusion_ref.respace(base["alphas_cumprod"], cand["timesteps"])
+    tb = diffusion_ref.diffusion_tables(nb)
+    unet = lambda xx, tt, yy, skip: unet_ref.unet_forward(sd, cfg, xx, tt, None, skip)
+    with torch.no_grad():
+        ref2 = diffusion_ref.ddim_sample_loop(diffusion_ref.make_model_fn(unet, tmap, class_cond=False), x.shape, tb, tmap, x, True,
+                                              model_kwargs={"y": None, "skip_layers": cand["skip_layers"]})
+    p = psnr(ours, ref2)
+    print(f"lsun256 2-step sampling: psnr={p:.2f} dB max_abs={(ours - ref2).abs().max().item():.4g}")
+    assert p >= 30.0

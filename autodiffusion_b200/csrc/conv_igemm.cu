@@ -188,8 +188,13 @@ conv_igemm_kernel(const __grid_constant__ ConvKParams p) {
                 if (is_leader) mbar_arrive_expect_tx(full_bar(stage), 2 * C::STAGE_BYTES);
                 else mbar_arrive_cluster(lead_full);
                 tma_load_4d_2sm(a_dst, &p.tmA[s], lead_full, ch * BLOCK_K, x0 + dx, y0 + dy, img);
-                tma_load_2d_2sm(b_dst, &p.tmW, lead_full, kb + ch * BLOCK_K,
-                                n_tile * BLOCK_N + (int)cta_rank * (BLOCK_N / 2));
+                if (BLOCK_N == 256) {  // two 64-row boxes
+                  tma_load_2d_2sm(b_dst, &p.tmW, lead_full, kb + ch * BLOCK_K, n_tile * BLOCK_N + (int)cta_rank * 128);
+                  tma_load_2d_2sm(b_dst + 8192, &p.tmW, lead_full, kb + ch * BLOCK_K, n_tile * BLOCK_N + (int)cta_rank * 128 + 64);
+                } else {
+                  tma_load_2d_2sm(b_dst, &p.tmW, lead_full, kb + ch * BLOCK_K,
+                                  n_tile * BLOCK_N + (int)cta_rank * (BLOCK_N / 2));
+                }
               } else {
                 mbar_arrive_expect_tx(full_bar(stage), C::STAGE_BYTES);
                 tma_load_4d(a_dst, &p.tmA[s], full_bar(stage), ch * BLOCK_K, x0 + dx, y0 + dy, img);
@@ -756,6 +761,7 @@ int launch(const ConvKParams& kp, cudaStream_t stream) {
 // N tile for a given real Cout; weights are padded to a multiple of it.
 int conv_block_n(int cout) {
   if (cout % 192 == 0) return 192;
+  if (cout % 256 == 0) return 256;
   if (cout % 128 == 0) return 128;
   if (cout <= 16) return 16;
   if (cout <= 64) return 64;
@@ -765,18 +771,18 @@ int conv_block_n(int cout) {
 
 namespace {
 
-// CTA pairs (cta_group::2) for the 192-wide N tile unless ADB_CONV_1CTA=1 (A/B testing).
-// Measured alternatives for the classifier's 128/256/512-channel layers: a 128-wide pair tile is ~18 %
-// SLOWER than the single-CTA 128 tile (the pair's extra handshakes buy only 8 KB less B traffic per stage);
-// a 256-wide pair tile (2 x 32 KB per stage) never completes its first full barrier once a second stage or
-// cluster is in flight - before any MMA is issued - with this protocol or with per-CTA expect_tx / separate
-// A and B barriers; cause not understood, shelved.
+// CTA pairs (cta_group::2) for the 192- and 256-wide N tiles unless ADB_CONV_1CTA=1 (A/B testing).
+// Measured: a 128-wide pair tile is ~18 % SLOWER than the single-CTA 128 tile (the pair's handshakes buy only
+// 8 KB less B traffic per stage). The 256-wide pair tile needs its B half (128 weight rows) fetched as TWO
+// 64-row boxes: a single cta_group::2 TMA box of 112 or 128 rows never completed its mbarrier transaction once a
+// second stage or cluster was in flight (96 rows, the 192-wide tile, is fine) - independent of the barrier protocol.
 int conv_ncta(int block_n) {
   static int force1 = -1;
   if (force1 < 0) {
     const char* e = getenv("ADB_CONV_1CTA");
     force1 = (e && e[0] == '1') ? 1 : 0;
   }
+  if (block_n == 256) return 2;
   return (block_n == 192 && !force1) ? 2 : 1;
 }
 
@@ -826,13 +832,16 @@ int conv_igemm_submit(adb_plan* plan, const adb_conv_desc* d, cudaStream_t strea
     int r = make_tmap_bf16(&kp.tmA[s], sg.act, 4, dims, strides, box);
     if (r != ADB_OK) return r;
   }
-  const int block_n = conv_block_n(d->cout);
+  int block_n = conv_block_n(d->cout);
+  // the 256-wide pair tile pays once there is at least one wave of them; small problems keep the 128-wide tile
+  // (cout_pad is a multiple of 256, hence of 128 as well)
+  if (block_n == 256 && ((M + 2 * BLOCK_M - 1) / (2 * BLOCK_M)) * (d->cout_pad / 256) < num_sms() / 2) block_n = 128;
   const int ncta = conv_ncta(block_n);
   ADB_REQUIRE(d->cout_pad % block_n == 0, "conv_igemm: cout_pad (%d) must be a multiple of the N tile %d (adb_conv_block_n)", d->cout_pad, block_n);
   {
     const uint64_t dims[2] = {(uint64_t)ktot, (uint64_t)d->cout_pad};
     const uint64_t strides[1] = {(uint64_t)ktot * 2};
-    const uint32_t box[2] = {(uint32_t)BLOCK_K, (uint32_t)(block_n / ncta)};
+    const uint32_t box[2] = {(uint32_t)BLOCK_K, (uint32_t)(block_n == 256 ? 64 : block_n / ncta)};
     int r = make_tmap_bf16(&kp.tmW, d->weight, 2, dims, strides, box);
     if (r != ADB_OK) return r;
   }
@@ -888,6 +897,7 @@ int conv_igemm_submit(adb_plan* plan, const adb_conv_desc* d, cudaStream_t strea
   const double flops = 2.0 * (double)M * (double)d->cout * (double)ktot;
   return submit(plan, stream, "conv_igemm", flops, 0.0, [kp, block_n, ncta](cudaStream_t s) -> int {
     switch (block_n) {
+      case 256: return launch<256, 2>(kp, s);
       case 192: return ncta == 2 ? launch<192, 2>(kp, s) : launch<192, 1>(kp, s);
       case 128: return launch<128, 1>(kp, s);
       case 64: return launch<64, 1>(kp, s);

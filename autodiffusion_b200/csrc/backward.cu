@@ -8,6 +8,8 @@
 //
 // The convolutions' and projections' data gradients are ordinary implicit GEMMs with transposed
 // (and spatially flipped) weights and run on conv_igemm.cu; attention is in attention_bwd.cu.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace adb {
@@ -54,8 +56,25 @@ struct GnBwdParams {
 //   dz = dy silu'(z);  dxh = dz A;  dx = rstd (dxh - mean_g(dxh) - xh mean_g(dxh xh))
 // pass 1 (APPLY = false) reduces S1 = sum dxh and S2 = sum dxh xh per (sample, group);
 // pass 2 (APPLY = true) recomputes dxh and writes dx (+ the skip-path gradient `add`).
-template <bool APPLY>
-__global__ void __launch_bounds__(GB_THREADS) gn_bwd_kernel(const GnBwdParams p) {
+// VEC = channels per thread (8: 16-byte accesses, 4: 8-byte accesses and half the per-channel constants in
+// registers -> more resident blocks)
+template <int VEC> struct VecT;
+template <> struct VecT<8> { using T = uint4; };
+template <> struct VecT<4> { using T = uint2; };
+__device__ __forceinline__ void unpackv(const uint4& r, float* f) { unpack8(r, f); }
+__device__ __forceinline__ void unpackv(const uint2& r, float* f) {
+  f[0] = bf16_lo(r.x); f[1] = bf16_hi(r.x);
+  f[2] = bf16_lo(r.y); f[3] = bf16_hi(r.y);
+}
+__device__ __forceinline__ void packv(const float* o, uint4& r) { r = pack8(o); }
+__device__ __forceinline__ void packv(const float* o, uint2& r) {
+  r.x = pack_bf16x2(o[0], o[1]);
+  r.y = pack_bf16x2(o[2], o[3]);
+}
+
+template <bool APPLY, int VEC>
+__global__ void __launch_bounds__(GB_THREADS, VEC == 8 ? 2 : 3) gn_bwd_kernel(const GnBwdParams p) {
+  using LT = typename VecT<VEC>::T;
   extern __shared__ float s_par[];  // [6][C]: r, m0, A, B, k1, k2
   float* s_r = s_par;
   float* s_m0 = s_par + p.C;
@@ -65,7 +84,7 @@ __global__ void __launch_bounds__(GB_THREADS) gn_bwd_kernel(const GnBwdParams p)
   float* s_k2 = s_par + 5 * p.C;
   __shared__ double s_acc[GN_GROUPS][2];
   const int n = blockIdx.y;
-  const int V = p.C / 8;
+  const int V = p.C / VEC;
   const int P = p.H * p.W;
   const int cpg = p.C / GN_GROUPS;
   const double cnt = (double)cpg * (double)P;
@@ -108,21 +127,21 @@ __global__ void __launch_bounds__(GB_THREADS) gn_bwd_kernel(const GnBwdParams p)
 
   if (pl < lanes) {
     for (int v = threadIdx.x % slots; v < V; v += GB_THREADS) {
-      float r[8], m0[8], A[8], B[8], k1[8], k2[8];
+      float r[VEC], m0[VEC], A[VEC], B[VEC], k1[VEC], k2[VEC];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        r[i] = s_r[v * 8 + i];
-        m0[i] = s_m0[v * 8 + i];
-        A[i] = s_A[v * 8 + i];
-        B[i] = s_B[v * 8 + i];
+      for (int i = 0; i < VEC; ++i) {
+        r[i] = s_r[v * VEC + i];
+        m0[i] = s_m0[v * VEC + i];
+        A[i] = s_A[v * VEC + i];
+        B[i] = s_B[v * VEC + i];
         if (APPLY) {
-          k1[i] = s_k1[v * 8 + i];
-          k2[i] = s_k2[v * 8 + i];
+          k1[i] = s_k1[v * VEC + i];
+          k2[i] = s_k2[v * VEC + i];
         }
       }
-      float s1[8], s2[8];
+      float s1[VEC], s2[VEC];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) s1[i] = s2[i] = 0.f;
+      for (int i = 0; i < VEC; ++i) s1[i] = s2[i] = 0.f;
       const bool half_d = p.resample == ADB_RESAMPLE_AVGPOOL2;
       const bool half_a = p.add_mode == ADB_RES_AVGPOOL2;
       const bool has_add = APPLY && p.add_mode != ADB_RES_NONE;
@@ -130,7 +149,7 @@ __global__ void __launch_bounds__(GB_THREADS) gn_bwd_kernel(const GnBwdParams p)
       // U pixels per trip: all of a trip's 16-byte loads (x, dout, add) are issued before any math
       constexpr int U = 4;
       for (int pix0 = p_begin + pl; pix0 < p_end; pix0 += U * lanes) {
-        uint4 xr[U], dr[U], ar[U];
+        LT xr[U], dr[U], ar[U];
         size_t ipix[U];
 #pragma unroll
         for (int u = 0; u < U; ++u) {
@@ -143,18 +162,18 @@ __global__ void __launch_bounds__(GB_THREADS) gn_bwd_kernel(const GnBwdParams p)
             const int y = pc / p.W, xx = pc - y * p.W;
             hpix = (size_t)n * Ph + (size_t)(y >> 1) * Wh + (xx >> 1);
           }
-          xr[u] = __ldg(reinterpret_cast<const uint4*>(p.x + ipix[u] * p.C) + v);
-          dr[u] = __ldg(reinterpret_cast<const uint4*>(p.dout + (half_d ? hpix : ipix[u]) * p.C) + v);
-          if (has_add) ar[u] = __ldg(reinterpret_cast<const uint4*>(p.add + (half_a ? hpix : ipix[u]) * p.C) + v);
+          xr[u] = __ldg(reinterpret_cast<const LT*>(p.x + ipix[u] * p.C) + v);
+          dr[u] = __ldg(reinterpret_cast<const LT*>(p.dout + (half_d ? hpix : ipix[u]) * p.C) + v);
+          if (has_add) ar[u] = __ldg(reinterpret_cast<const LT*>(p.add + (half_a ? hpix : ipix[u]) * p.C) + v);
         }
 #pragma unroll
         for (int u = 0; u < U; ++u) {
           if (pix0 + u * lanes >= p_end) break;
-          float xf[8], df[8], o[8];
-          unpack8(xr[u], xf);
-          unpack8(dr[u], df);
+          float xf[VEC], df[VEC], o[VEC];
+          unpackv(xr[u], xf);
+          unpackv(dr[u], df);
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {
+          for (int i = 0; i < VEC; ++i) {
             const float xh = fmaf(xf[i], r[i], m0[i]);
             const float z = fmaf(xh, A[i], B[i]);
             float dz = df[i] * dscale;
@@ -174,21 +193,23 @@ __global__ void __launch_bounds__(GB_THREADS) gn_bwd_kernel(const GnBwdParams p)
           }
           if (APPLY) {
             if (has_add) {
-              float af[8];
-              unpack8(ar[u], af);
+              float af[VEC];
+              unpackv(ar[u], af);
 #pragma unroll
-              for (int i = 0; i < 8; ++i) o[i] = fmaf(af[i], ascale, o[i]);
+              for (int i = 0; i < VEC; ++i) o[i] = fmaf(af[i], ascale, o[i]);
             }
-            *(reinterpret_cast<uint4*>(p.dx + ipix[u] * p.C) + v) = pack8(o);
+            LT ov;
+            packv(o, ov);
+            *(reinterpret_cast<LT*>(p.dx + ipix[u] * p.C) + v) = ov;
           }
         }
       }
       if (!APPLY) {
-        int g_cur = (v * 8) / cpg;
+        int g_cur = (v * VEC) / cpg;
         double d1 = 0.0, d2 = 0.0;
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const int g = (v * 8 + i) / cpg;
+        for (int i = 0; i < VEC; ++i) {
+          const int g = (v * VEC + i) / cpg;
           if (g != g_cur) {
             atomicAdd(&s_acc[g_cur][0], d1);
             atomicAdd(&s_acc[g_cur][1], d2);
@@ -421,9 +442,22 @@ int gn_backward_submit(adb_plan* plan, const adb_gn_bwd_desc* d, cudaStream_t st
     dim3 grid(p.splits, p.n);
     const size_t smem = 6 * (size_t)p.C * sizeof(float);
     ADB_CUDA(cudaMemsetAsync(p.bstats, 0, (size_t)p.n * GN_GROUPS * 2 * sizeof(double), s));
-    gn_bwd_kernel<false><<<grid, GB_THREADS, smem, s>>>(p);
-    ADB_CUDA(cudaGetLastError());
-    gn_bwd_kernel<true><<<grid, GB_THREADS, smem, s>>>(p);
+    // 4 channels per thread (80 registers, 3 blocks/SM) measured 3.9 TB/s vs 3.5 TB/s for 8 channels per thread
+    // (128 registers, 2 blocks/SM) and 2.9 TB/s for the first version (157 registers, 1 block/SM)
+    static int vec4 = -1;
+    if (vec4 < 0) {
+      const char* e = getenv("ADB_GNB_VEC8");
+      vec4 = (e && e[0] == '1') ? 0 : 1;
+    }
+    if (vec4) {
+      gn_bwd_kernel<false, 4><<<grid, GB_THREADS, smem, s>>>(p);
+      ADB_CUDA(cudaGetLastError());
+      gn_bwd_kernel<true, 4><<<grid, GB_THREADS, smem, s>>>(p);
+    } else {
+      gn_bwd_kernel<false, 8><<<grid, GB_THREADS, smem, s>>>(p);
+      ADB_CUDA(cudaGetLastError());
+      gn_bwd_kernel<true, 8><<<grid, GB_THREADS, smem, s>>>(p);
+    }
     ADB_CUDA(cudaGetLastError());
     return 3;
   });

@@ -261,7 +261,7 @@ class EncoderUNetModel(nn.Module):
                     wproj=ops.pack_conv_weight([layer.proj_out.weight], dev), bproj=f32(layer.proj_out.bias),
                     wqkvt=ops.pack_conv_weight_dgrad(layer.qkv.weight, dev),
                     wprojt=ops.pack_conv_weight_dgrad(layer.proj_out.weight, dev))
-        P["emb_w"] = th.cat(emb_w, 0).to(dev).contiguous()
+        P["emb_w"] = ops.pack_linear_weight_split(th.cat(emb_w, 0), dev)
         P["emb_b"] = th.cat(emb_b, 0).to(dev).contiguous()
         P["emb_total"] = off
         te0, te2 = getattr(self.time_embed, "0"), getattr(self.time_embed, "2")
@@ -343,7 +343,7 @@ class EncoderUNetModel(nn.Module):
         te = ops.timestep_embedding(t_in, mc, plan=plan)
         e1 = ops.linear(te, P["te0_w"], P["te0_b"], plan=plan)
         emb = ops.linear(e1, P["te2_w"], P["te2_b"], silu_in=True, plan=plan)  # no label embedding (unet.py:871)
-        ss_all = ops.linear(emb, P["emb_w"], P["emb_b"], silu_in=True, plan=plan)
+        ss_all = ops.linear_tc(emb, P["emb_w"], P["emb_b"], P["emb_total"], silu_in=True, plan=plan)
         ss_total = P["emb_total"]
 
         tape: List[Callable[[th.Tensor], th.Tensor]] = []  # backward closures, run in reverse

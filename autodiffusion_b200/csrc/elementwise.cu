@@ -359,6 +359,33 @@ int linear_submit(adb_plan* plan, const float* x, const float* w, const float* b
   });
 }
 
+// act(x) (SiLU or identity) split into two bf16 addends: hi = bf16(v), lo = bf16(v - hi). hi + lo carries
+// 16 mantissa bits, so a bf16 tensor-core product over [hi | lo | hi] x [W_hi | W_hi | W_lo] reproduces the
+// fp32 Linear to ~2^-16 relative (the reference keeps its embedding MLP in fp32, fp16_util.py:15-22).
+__global__ void __launch_bounds__(256) split_bf16_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ hi,
+                                                        __nv_bfloat16* __restrict__ lo, size_t total, int silu_in) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    float v = x[i];
+    if (silu_in) v = v / (1.0f + expf(-v));
+    const __nv_bfloat16 h = __float2bfloat16(v);
+    hi[i] = h;
+    lo[i] = __float2bfloat16(v - __bfloat162float(h));
+  }
+}
+
+int split_bf16_submit(adb_plan* plan, const float* x, void* hi, void* lo, size_t total, int silu_in, cudaStream_t stream) {
+  ADB_REQUIRE(x && hi && lo && total > 0, "split_bf16: bad arguments");
+  return submit(plan, stream, "split_bf16", 0.0, 0.0, [=](cudaStream_t s) -> int {
+    size_t blocks = (total + 255) / 256;
+    const size_t cap = (size_t)num_sms() * 8;
+    if (blocks > cap) blocks = cap;
+    split_bf16_kernel<<<(unsigned)blocks, 256, 0, s>>>(x, reinterpret_cast<__nv_bfloat16*>(hi),
+                                                       reinterpret_cast<__nv_bfloat16*>(lo), total, silu_in);
+    ADB_CUDA(cudaGetLastError());
+    return 1;
+  });
+}
+
 int ddim_step_submit(adb_plan* plan, const float* x, const float* model_out, int eps_channels,
                      const float* grad, float* x_prev, float* pred_xstart, int n, int c, int hw,
                      const float* coef, int clip_denoised, cudaStream_t stream) {

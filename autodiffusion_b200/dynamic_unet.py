@@ -425,7 +425,7 @@ class Dynamic_UNetModel(nn.Module):
                     wqkv=ops.pack_conv_weight([layer.qkv.weight], dev), bqkv=f32(layer.qkv.bias),
                     wproj=ops.pack_conv_weight([layer.proj_out.weight], dev), bproj=f32(layer.proj_out.bias),
                 )
-        P["emb_w"] = th.cat(emb_w, 0).to(dev).contiguous()
+        P["emb_w"] = ops.pack_linear_weight_split(th.cat(emb_w, 0), dev)
         P["emb_b"] = th.cat(emb_b, 0).to(dev).contiguous()
         P["emb_total"] = off
         te0, te2 = getattr(self.time_embed, "0"), getattr(self.time_embed, "2")
@@ -538,7 +538,8 @@ class Dynamic_UNetModel(nn.Module):
         te = ops.timestep_embedding(up.t_in, mc, plan=plan)
         e1 = ops.linear(te, P["te0_w"], P["te0_b"], plan=plan)
         emb = ops.linear(e1, P["te2_w"], P["te2_b"], silu_in=True, table=P.get("label"), idx=up.y_in, plan=plan)
-        ss_all = ops.linear(emb, P["emb_w"], P["emb_b"], silu_in=True, plan=plan)
+        # every emb_layers Linear of the forward as ONE tensor-core product (fp32-grade: split-bf16 operands)
+        ss_all = ops.linear_tc(emb, P["emb_w"], P["emb_b"], P["emb_total"], silu_in=True, plan=plan)
         ss_total = P["emb_total"]
 
         def run_res(layer: ResBlock, srcs: List[th.Tensor]) -> th.Tensor:

@@ -34,7 +34,7 @@ __all__ = [
     "stem_conv", "timestep_embedding", "linear", "ddim_step", "pack_uint8", "moments_accumulate",
     "memset0", "nchw_to_nhwc_bf16", "nhwc_to_nchw_f32",
     "attention_backward", "gn_backward", "pool_prepare", "pool_attention", "pool_attention_backward", "pool_merge",
-    "logsoftmax_grad", "pack_conv_weight_dgrad",
+    "logsoftmax_grad", "pack_conv_weight_dgrad", "pack_linear_weight_split", "linear_tc",
 ]
 
 
@@ -494,6 +494,41 @@ def linear(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor], 
     )
     if plan is not None:
         plan.keep(x, weight, bias, table, idx, out)
+    return out
+
+
+def pack_linear_weight_split(weight: torch.Tensor, device=None) -> torch.Tensor:
+    """fp32 Linear weight [nout, k] -> the K-major bf16 operand [nout_pad, 3k] = [W_hi | W_hi | W_lo] of `linear_tc`."""
+    w = weight.detach().float()
+    hi = w.to(torch.bfloat16)
+    lo = (w - hi.float()).to(torch.bfloat16)
+    m = torch.cat([hi, hi, lo], dim=1)
+    bn = conv_block_n(w.shape[0])
+    pad = (-w.shape[0]) % bn
+    if pad:
+        m = torch.cat([m, m.new_zeros(pad, m.shape[1])], dim=0)
+    m = m.contiguous()
+    return m.to(device) if device is not None else m
+
+
+def linear_tc(x: torch.Tensor, w_split: torch.Tensor, bias: Optional[torch.Tensor], nout: int, silu_in: bool = False,
+              out: Optional[torch.Tensor] = None, plan: Optional[Plan] = None) -> torch.Tensor:
+    """out[b, :] = act(x[b, :]) W^T + bias on tensor cores at fp32-grade accuracy: act(x) is split into bf16
+    hi + lo, the weight was split by `pack_linear_weight_split`, and the three cross products that matter run as
+    one implicit GEMM over three K-segments with fp32 accumulation and fp32 output. x fp32 [b, k], k % 8 == 0."""
+    b, k = x.shape
+    assert w_split.shape[1] == 3 * k and k % 8 == 0
+    hi = torch.empty((b, 1, 1, k), dtype=torch.bfloat16, device=x.device)
+    lo = torch.empty_like(hi)
+    _lib.check(_lib.lib().adb_split_bf16(_ph(plan), _dev(x, "x", torch.float32), _dev(hi, "hi", torch.bfloat16),
+                                         _dev(lo, "lo", torch.bfloat16), b * k, int(bool(silu_in)), _stream()),
+               "adb_split_bf16")
+    if plan is not None:
+        plan.keep(x, hi, lo)
+    if out is None:
+        out = torch.empty((b, nout), dtype=torch.float32, device=x.device)
+    conv_igemm([(hi, 1), (lo, 1), (hi, 1)], w_split, bias, nout, out=out.view(b, nout, 1, 1), out_mode=OUT_F32_NCHW,
+               plan=plan)
     return out
 
 

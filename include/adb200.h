@@ -159,6 +159,11 @@ int adb_linear(adb_plan* plan, const float* x, const float* w, const float* bias
                int b, int k, int nout, int silu_in, const float* table, const int64_t* idx,
                adb_stream stream);
 
+/* hi = bf16(act(x)), lo = bf16(act(x) - hi), act = SiLU if silu_in else identity; x fp32 [total].
+ * Feeds the wide emb_layers product (dynamic_unet.py:208-214,259: [B,768] x [768, sum 2*cout]) to adb_conv_igemm as
+ * three K-segments [hi | lo | hi] x [W_hi | W_hi | W_lo] with fp32 output: an fp32-grade Linear on tensor cores. */
+int adb_split_bf16(adb_plan* plan, const float* x, void* hi, void* lo, size_t total, int silu_in, adb_stream stream);
+
 /* ---- fused guidance + DDIM update (gaussian_diffusion.py:328-349,371-393,536-584)
  * coef = {sqrt_recip_acp, sqrt_recipm1_acp, sqrt(1-acp), sqrt(acp_prev), sqrt(1-acp_prev)}
  * (fp32, as the reference rounds them at gather, :920). eps is read from the first 3 of

@@ -312,3 +312,18 @@ def test_errors_are_reported_not_swallowed():
         ops.pack_uint8(torch.zeros(1, 3, 8, 8))  # CPU tensor: no CPU path
     with pytest.raises(AdbError):
         ops.attention(torch.zeros(2 * 100, 3 * 64, dtype=torch.bfloat16, device=DEV), 2, 100, 1, False)
+
+
+def test_linear_tc_matches_fp32_linear():
+    """The emb_layers product on tensor cores with split-bf16 operands vs the fp32 Linear the reference keeps
+    (fp16_util.py:15-22): error <= 2^-13 of the output scale (three bf16 cross products, fp32 accumulation)."""
+    ops = _ops()
+    b, k, n = 37, 768, 35712 // 8
+    x = _rand((b, k), 90, 1.5)
+    w = _rand((n, k), 91, k ** -0.5)
+    bias = 0.1 * _rand((n,), 92)
+    ref = F.linear(F.silu(x), w, bias)
+    out = ops.linear_tc(x.to(DEV), ops.pack_linear_weight_split(w, DEV), bias.to(DEV), n, silu_in=True)
+    torch.cuda.synchronize()
+    assert out.shape == (b, n) and out.dtype == torch.float32
+    _check(out.cpu(), ref, 2 ** -13, "linear_tc (split bf16) vs fp32 linear")

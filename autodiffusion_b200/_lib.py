@@ -182,6 +182,7 @@ SYMBOLS = {
     "adb_pack_uint8": (_I, [_P, _P, _P, _I, _I, _I, _P]),
     "adb_moments_accumulate": (_I, [_P, _P, _I, _I, _P, _P, _P]),
     "adb_memset0": (_I, [_P, _P, C.c_size_t, _P]),
+    "adb_stem_im2col": (_I, [_P, _P, _P, _I, _I, _I, _P]),
     "adb_split_bf16": (_I, [_P, _P, _P, _P, C.c_size_t, _I, _P]),
     "adb_attention_lse": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _P]),
     "adb_attention_backward": (_I, [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _P]),

@@ -269,6 +269,7 @@ class EncoderUNetModel(nn.Module):
         stem = getattr(self.input_blocks[0], "0")
         P["stem_w"], P["stem_b"] = f32(stem.weight), f32(stem.bias)
         P["stem_wt"] = ops.pack_conv_weight_dgrad(stem.weight, dev)
+        P["stem_wp"] = ops.pack_stem_weight(stem.weight, dev) if self.in_channels == 3 else None
         on, pool = getattr(self.out, "0"), getattr(self.out, "2")
         C = self._final_ch
         P["out_g"], P["out_be"] = f32(on.weight), f32(on.bias)
@@ -450,7 +451,10 @@ class EncoderUNetModel(nn.Module):
         # ---------------- forward ----------------
         ch0 = int(self.channel_mult[0] * mc)
         h = ctx.alloc((B, H, W, ch0))
-        ops.stem_conv(x_in, P["stem_w"], P["stem_b"], out=h, plan=plan)
+        if P["stem_wp"] is not None:
+            ops.stem_conv_tc(x_in, P["stem_wp"], P["stem_b"], ch0, out=h, plan=plan, **conv_stats(h))
+        else:
+            ops.stem_conv(x_in, P["stem_w"], P["stem_b"], out=h, plan=plan)
         for layer in self._iter_layers():
             nxt = res_fwd(layer, h) if isinstance(layer, ResBlock) else attn_fwd(layer, h)
             if not want_grad:

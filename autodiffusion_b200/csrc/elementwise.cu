@@ -359,6 +359,60 @@ int linear_submit(adb_plan* plan, const float* x, const float* w, const float* b
   });
 }
 
+// Stem im2col: fp32 NCHW [n,3,h,w] -> bf16 [n,h,w,64], channel k = tap*3 + ci of the 3x3 zero-padded
+// neighbourhood for k < 27, the bf16 rounding RESIDUAL of the same value at 32 + k, zeros elsewhere. One 64-deep
+// tensor-core k-step over [hi | lo] x [W | W] then is the whole input convolution (input_blocks.0.0,
+// dynamic_unet.py:501-503) with ~16 mantissa bits of x kept (the reference feeds x.type(fp16), :693).
+__global__ void __launch_bounds__(256) stem_im2col_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ out,
+                                                         int n, int H, int W) {
+  const size_t P = (size_t)H * W;
+  const size_t total = (size_t)n * P;
+  for (size_t pix = (size_t)blockIdx.x * blockDim.x + threadIdx.x; pix < total; pix += (size_t)gridDim.x * blockDim.x) {
+    const size_t img = pix / P;
+    const int rem = (int)(pix - img * P);
+    const int y = rem / W, xx = rem - y * W;
+    uint32_t hi[16], lo[16];  // 32 bf16 each, packed in pairs
+    float v[28];
+    v[27] = 0.f;
+#pragma unroll
+    for (int tap = 0; tap < 9; ++tap) {
+      const int yy = y + tap / 3 - 1, xs = xx + tap % 3 - 1;
+      const bool ok = yy >= 0 && yy < H && xs >= 0 && xs < W;
+#pragma unroll
+      for (int ci = 0; ci < 3; ++ci)
+        v[tap * 3 + ci] = ok ? __ldg(x + (img * 3 + ci) * P + (size_t)yy * W + xs) : 0.f;
+    }
+#pragma unroll
+    for (int i = 0; i < 14; ++i) {
+      const __nv_bfloat16 h0 = __float2bfloat16(v[2 * i]), h1 = __float2bfloat16(v[2 * i + 1]);
+      __nv_bfloat162 hp;
+      hp.x = h0;
+      hp.y = h1;
+      hi[i] = *reinterpret_cast<uint32_t*>(&hp);
+      lo[i] = pack_bf16x2(v[2 * i] - __bfloat162float(h0), v[2 * i + 1] - __bfloat162float(h1));
+    }
+    hi[14] = hi[15] = lo[14] = lo[15] = 0u;
+    uint4* o = reinterpret_cast<uint4*>(out + pix * 64);
+#pragma unroll
+    for (int g = 0; g < 4; ++g) o[g] = make_uint4(hi[4 * g], hi[4 * g + 1], hi[4 * g + 2], hi[4 * g + 3]);
+#pragma unroll
+    for (int g = 0; g < 4; ++g) o[4 + g] = make_uint4(lo[4 * g], lo[4 * g + 1], lo[4 * g + 2], lo[4 * g + 3]);
+  }
+}
+
+int stem_im2col_submit(adb_plan* plan, const float* x, void* out, int n, int h, int w, cudaStream_t stream) {
+  ADB_REQUIRE(x && out && n > 0 && h > 0 && w > 0, "stem_im2col: bad arguments");
+  return submit(plan, stream, "stem_im2col", 0.0, 0.0, [=](cudaStream_t s) -> int {
+    const size_t total = (size_t)n * h * w;
+    size_t blocks = (total + 255) / 256;
+    const size_t cap = (size_t)num_sms() * 16;
+    if (blocks > cap) blocks = cap;
+    stem_im2col_kernel<<<(unsigned)blocks, 256, 0, s>>>(x, reinterpret_cast<__nv_bfloat16*>(out), n, h, w);
+    ADB_CUDA(cudaGetLastError());
+    return 1;
+  });
+}
+
 // act(x) (SiLU or identity) split into two bf16 addends: hi = bf16(v), lo = bf16(v - hi). hi + lo carries
 // 16 mantissa bits, so a bf16 tensor-core product over [hi | lo | hi] x [W_hi | W_hi | W_lo] reproduces the
 // fp32 Linear to ~2^-16 relative (the reference keeps its embedding MLP in fp32, fp16_util.py:15-22).

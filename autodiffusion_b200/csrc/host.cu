@@ -115,6 +115,7 @@ int timestep_embedding_submit(adb_plan*, const int64_t*, const float*, float*, i
 int linear_submit(adb_plan*, const float*, const float*, const float*, float*, int, int, int, int,
                   const float*, const int64_t*, cudaStream_t);
 int split_bf16_submit(adb_plan*, const float*, void*, void*, size_t, int, cudaStream_t);
+int stem_im2col_submit(adb_plan*, const float*, void*, int, int, int, cudaStream_t);
 int ddim_step_submit(adb_plan*, const float*, const float*, int, const float*, float*, float*, int,
                      int, int, const float*, int, cudaStream_t);
 int pack_uint8_submit(adb_plan*, const float*, uint8_t*, int, int, int, cudaStream_t);
@@ -285,6 +286,10 @@ int adb_linear(adb_plan* plan, const float* x, const float* w, const float* bias
                adb_stream stream) {
   return linear_submit(plan, x, w, bias, out, b, k, nout, silu_in, table, idx,
                        static_cast<cudaStream_t>(stream));
+}
+
+int adb_stem_im2col(adb_plan* plan, const float* x, void* out, int n, int h, int w, adb_stream stream) {
+  return stem_im2col_submit(plan, x, out, n, h, w, static_cast<cudaStream_t>(stream));
 }
 
 int adb_split_bf16(adb_plan* plan, const float* x, void* hi, void* lo, size_t total, int silu_in, adb_stream stream) {

@@ -434,6 +434,7 @@ class Dynamic_UNetModel(nn.Module):
             P["label"] = f32(self.label_emb.weight)
         stem = getattr(self.input_blocks[0], "0")
         P["stem_w"], P["stem_b"] = f32(stem.weight), f32(stem.bias)
+        P["stem_wp"] = ops.pack_stem_weight(stem.weight, dev) if self.in_channels == 3 else None
         on, oc = getattr(self.out, "0"), getattr(self.out, "2")
         P["out_g"], P["out_be"] = f32(on.weight), f32(on.bias)
         P["out_w"], P["out_b"] = ops.pack_conv_weight([oc.weight], dev), f32(oc.bias)
@@ -616,8 +617,11 @@ class Dynamic_UNetModel(nn.Module):
 
         ch0 = int(self.channel_mult[0] * mc)
         h = ctx.alloc((B, H, W, ch0))
-        _forget(h)
-        ops.stem_conv(up.x_in, P["stem_w"], P["stem_b"], out=h, plan=plan)
+        if P["stem_wp"] is not None:  # tensor-core stem; its epilogue also fills the first GroupNorm's sums
+            ops.stem_conv_tc(up.x_in, P["stem_wp"], P["stem_b"], ch0, out=h, plan=plan, **new_stats(h))
+        else:
+            _forget(h)
+            ops.stem_conv(up.x_in, P["stem_w"], P["stem_b"], out=h, plan=plan)
         hs = [h]
         ctx.retain(h)  # one reference for hs, one for the running h
         for blk in list(self.input_blocks)[1:]:
@@ -686,7 +690,8 @@ class Dynamic_UNetModel(nn.Module):
                 srcs = [res(layer, srcs) if isinstance(layer, ResBlock) else attn(layer, srcs[0])]
             return srcs[0]
 
-        h = T(None, int(self.channel_mult[0] * self.model_channels), H, W)  # stem output: no producer stats
+        ch0 = int(self.channel_mult[0] * self.model_channels)
+        h = produce(ch0, H, W) if self.in_channels == 3 else T(None, ch0, H, W)  # stem: same rule as record_forward
         hs = [h]
         for blk in list(self.input_blocks)[1:]:
             h = block(blk, [h])

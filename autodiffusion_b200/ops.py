@@ -35,6 +35,7 @@ __all__ = [
     "memset0", "nchw_to_nhwc_bf16", "nhwc_to_nchw_f32",
     "attention_backward", "gn_backward", "pool_prepare", "pool_attention", "pool_attention_backward", "pool_merge",
     "logsoftmax_grad", "pack_conv_weight_dgrad", "pack_linear_weight_split", "linear_tc",
+    "pack_stem_weight", "stem_conv_tc",
 ]
 
 
@@ -445,6 +446,37 @@ def stem_conv(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor
     if plan is not None:
         plan.keep(x, weight, bias, out)
     return out
+
+
+def pack_stem_weight(weight: torch.Tensor, device=None) -> torch.Tensor:
+    """Stem conv weight [cout, 3, 3, 3] -> bf16 [cout_pad, 64] = [W (tap-major, channel-minor) | 0 x5 | W | 0 x5],
+    the operand matching `adb_stem_im2col`'s [hi | lo] rows."""
+    cout, cin = weight.shape[0], weight.shape[1]
+    assert cin == 3 and tuple(weight.shape[2:]) == (3, 3)
+    w = weight.detach().float().permute(0, 2, 3, 1).reshape(cout, 27)
+    z = w.new_zeros(cout, 5)
+    m = torch.cat([w, z, w, z], dim=1)
+    bn = conv_block_n(cout)
+    pad = (-cout) % bn
+    if pad:
+        m = torch.cat([m, m.new_zeros(pad, 64)], dim=0)
+    m = m.to(torch.bfloat16).contiguous()
+    return m.to(device) if device is not None else m
+
+
+def stem_conv_tc(x: torch.Tensor, w_stem: torch.Tensor, bias: Optional[torch.Tensor], cout: int,
+                 out: Optional[torch.Tensor] = None, plan: Optional[Plan] = None,
+                 stats_out: Optional[torch.Tensor] = None, stats2: Optional[tuple] = None) -> torch.Tensor:
+    """x fp32 NCHW [n,3,h,w] -> bf16 NHWC [n,h,w,cout]: im2col (hi | lo split of the input) + one tensor-core k-step;
+    the epilogue can accumulate the consumer GroupNorm's sums like any other conv (`stats_out`, `stats2`)."""
+    n, cin, h, w = x.shape
+    assert cin == 3
+    col = torch.empty((n, h, w, 64), dtype=torch.bfloat16, device=x.device)
+    _lib.check(_lib.lib().adb_stem_im2col(_ph(plan), _dev(x, "x", torch.float32), _dev(col, "col", torch.bfloat16),
+                                          n, h, w, _stream()), "adb_stem_im2col")
+    if plan is not None:
+        plan.keep(x, col)
+    return conv_igemm([(col, 1)], w_stem, bias, cout, out=out, plan=plan, stats_out=stats_out, stats2=stats2)
 
 
 _FREQS = {}

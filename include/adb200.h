@@ -159,6 +159,11 @@ int adb_linear(adb_plan* plan, const float* x, const float* w, const float* bias
                int b, int k, int nout, int silu_in, const float* table, const int64_t* idx,
                adb_stream stream);
 
+/* Tensor-core form of adb_stem_conv for cin == 3: writes the 3x3 zero-padded neighbourhood of every pixel as a
+ * bf16 row [27 values (tap-major, channel-minor) | 5 zeros | their 27 bf16 rounding residuals | 5 zeros] of
+ * out [n,h,w,64]; adb_conv_igemm over it (taps = 1, cin = 64) with the weight [cout, 27|0|27|0] is the stem conv. */
+int adb_stem_im2col(adb_plan* plan, const float* x, void* out, int n, int h, int w, adb_stream stream);
+
 /* hi = bf16(act(x)), lo = bf16(act(x) - hi), act = SiLU if silu_in else identity; x fp32 [total].
  * Feeds the wide emb_layers product (dynamic_unet.py:208-214,259: [B,768] x [768, sum 2*cout]) to adb_conv_igemm as
  * three K-segments [hi | lo | hi] x [W_hi | W_hi | W_lo] with fp32 output: an fp32-grade Linear on tensor cores. */

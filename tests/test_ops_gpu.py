@@ -327,3 +327,21 @@ def test_linear_tc_matches_fp32_linear():
     torch.cuda.synchronize()
     assert out.shape == (b, n) and out.dtype == torch.float32
     _check(out.cpu(), ref, 2 ** -13, "linear_tc (split bf16) vs fp32 linear")
+
+
+def test_stem_conv_tc_matches_fp32_conv():
+    """Tensor-core stem (im2col with hi|lo split of the input + one 64-deep k-step) vs the fp32 conv of the input
+    with bf16-rounded weights: only the output's bf16 rounding remains (2^-8 of the output scale)."""
+    ops = _ops()
+    n, r, cout = 3, 64, 192
+    x = _rand((n, 3, r, r), 93, 1.3)
+    w = _bf(_rand((cout, 3, 3, 3), 94, 27 ** -0.5))
+    b = 0.1 * _rand((cout,), 95)
+    ref = F.conv2d(x, w, b, padding=1)
+    stats = torch.zeros((n, 32, 2), dtype=torch.float64, device=DEV)
+    out = ops.stem_conv_tc(x.to(DEV), ops.pack_stem_weight(w, DEV), b.to(DEV), cout, stats_out=stats)
+    torch.cuda.synchronize()
+    _check(_nchw(out), ref, 2 ** -8, "stem_conv_tc")
+    got = _nchw(out).double()
+    s_ref = got.reshape(n, 32, -1).sum(-1)
+    assert (stats[:, :, 0].cpu() - s_ref).abs().max().item() <= 1e-3 * s_ref.abs().max().item() + 1e-2

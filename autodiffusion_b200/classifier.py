@@ -275,15 +275,16 @@ class EncoderUNetModel(nn.Module):
         P["out_g"], P["out_be"] = f32(on.weight), f32(on.bias)
         P["pos"] = f32(pool.positional_embedding)
         wq = pool.qkv_proj.weight.detach()  # [3C, C, 1]: rows (q | k | v), new attention order
-        P["pool_wqkv"] = f32(wq[:, :, 0])
+        P["pool_wqkv"] = ops.pack_linear_weight_split(wq[:, :, 0], dev)        # split-bf16 operands of ops.linear_tc
         P["pool_bqkv"] = f32(pool.qkv_proj.bias)
-        P["pool_wqkv_t"] = f32(wq[:, :, 0].t())
+        P["pool_wqkv_t"] = ops.pack_linear_weight_split(wq[:, :, 0].t(), dev)
         P["pool_wkv"] = ops.pack_conv_weight([wq[C:]], dev)
         P["pool_bkv"] = f32(pool.qkv_proj.bias[C:])
         P["pool_wkv_t"] = ops.pack_conv_weight_dgrad(wq[C:], dev)
-        P["pool_wc"] = f32(pool.c_proj.weight[:, :, 0])
+        P["pool_wc"] = ops.pack_linear_weight_split(pool.c_proj.weight[:, :, 0], dev)
         P["pool_bc"] = f32(pool.c_proj.bias)
-        P["pool_wc_t"] = f32(pool.c_proj.weight[:, :, 0].t())
+        P["pool_wc_t"] = ops.pack_linear_weight_split(pool.c_proj.weight[:, :, 0].t(), dev)
+        P["n_out"] = pool.c_proj.weight.shape[0]
         self._packed = P
         self._packed_generation = self._generation
         self._plans.clear()
@@ -466,17 +467,17 @@ class EncoderUNetModel(nn.Module):
         xp, mean = ops.pool_prepare(g, P["pos"], plan=plan)
         ctx.release(g)
         kv = ops.conv_igemm([(xp, 1)], P["pool_wkv"], P["pool_bkv"], 2 * C, plan=plan)
-        qkv0 = ops.linear(mean, P["pool_wqkv"], P["pool_bqkv"], plan=plan)
+        qkv0 = ops.linear_tc(mean, P["pool_wqkv"], P["pool_bqkv"], 3 * C, plan=plan)
         out0, probs = ops.pool_attention(qkv0, kv, plan=plan)
-        logits = ops.linear(out0, P["pool_wc"], P["pool_bc"], plan=plan)
+        logits = ops.linear_tc(out0, P["pool_wc"], P["pool_bc"], P["n_out"], plan=plan)
         if not want_grad:
             return logits
 
         # ---------------- backward (data gradients only) ----------------
         dlog = ops.logsoftmax_grad(logits, y_in, scale, plan=plan)
-        dout0 = ops.linear(dlog, P["pool_wc_t"], None, plan=plan)
+        dout0 = ops.linear_tc(dlog, P["pool_wc_t"], None, C, plan=plan)
         dqkv0, dkv = ops.pool_attention_backward(dout0, probs, qkv0, kv, plan=plan)
-        dmean = ops.linear(dqkv0, P["pool_wqkv_t"], None, plan=plan)
+        dmean = ops.linear_tc(dqkv0, P["pool_wqkv_t"], None, C, plan=plan)
         dxp = ops.conv_igemm([(dkv, 1)], P["pool_wkv_t"], None, C, plan=plan)
         dg = ops.pool_merge(dxp, dmean, plan=plan)
         d = ctx.alloc((n, hh, ww, C))
@@ -549,3 +550,21 @@ class ClassifierGuidance:
 
     def record(self, plan: ops.Plan, x_in, t_in, y_in, grad_out):
         return self.classifier.record_guidance(plan, x_in, t_in, y_in, grad_out, self.classifier_scale)
+
+    def shared_plan(self, x_in, t_in, y_in, grad_out) -> ops.Plan:
+        """The recorded forward + input-gradient pass over these exact buffers, recorded once and reused by every
+        candidate's schedule (all SchedulePlans of one model geometry share x / t / y / grad buffers)."""
+        clf = self.classifier
+        if clf._packed_generation != clf._generation:
+            clf._pack()  # clears clf._plans; the shared plans below are dropped with them
+            clf._shared = {}
+        key = (x_in.data_ptr(), t_in.data_ptr(), y_in.data_ptr(), grad_out.data_ptr(), tuple(x_in.shape), self.classifier_scale)
+        shared = clf.__dict__.setdefault("_shared", {})
+        plan = shared.get(key)
+        if plan is None:
+            with th.no_grad():
+                plan = ops.Plan()
+                self.record(plan, x_in, t_in, y_in, grad_out)
+                plan.run()  # first run outside any capture: sets kernel attributes, validates the schedule
+            shared[key] = plan
+        return plan

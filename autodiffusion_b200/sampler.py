@@ -98,7 +98,13 @@ class SchedulePlan:
         self.final = self.x  # x_0 ends up in the shared input buffer
         self.coefs = [ddim_coefficients(active_diffusion, i) for i in self._order]
         self.t_values = [int(self.timestep_map[i]) for i in self._order]
-        self.grad = th.zeros(self.shape, dtype=th.float32, device=dev) if cond_fn is not None else None
+        self.grad = None
+        if cond_fn is not None:  # one guidance-gradient buffer per model geometry, shared like the IO buffers
+            grads = model.__dict__.setdefault("_guidance_grad", {})
+            key = (self.shape, str(dev))
+            if key not in grads:
+                grads[key] = th.zeros(self.shape, dtype=th.float32, device=dev)
+            self.grad = grads[key]
         self.u8 = th.empty((batch, hw, hw, model.in_channels), dtype=th.uint8, device=dev) if pack_uint8 else None
         self.launches = sum(up.launches for up in self.steps) + self.K + (1 if pack_uint8 else 0)
         # native classifier guidance: forward + input-gradient recorded once over the shared x / t / y buffers
@@ -106,10 +112,8 @@ class SchedulePlan:
         if isinstance(cond_fn, ClassifierGuidance):
             if self.y is None:  # unconditional UNet guided by a classifier: labels still drive the guidance
                 self.y = th.zeros((batch,), dtype=th.int64, device=dev)
-            with th.no_grad():
-                self.guidance = ops.Plan()
-                cond_fn.record(self.guidance, self.x, self.t_in, self.y, self.grad)
-                self.launches += self.K * self.guidance.run()
+            self.guidance = cond_fn.shared_plan(self.x, self.t_in, self.y, self.grad)
+            self.launches += self.K * self.guidance.launches_per_run
         self.graph: Optional[th.cuda.CUDAGraph] = None
         if (cond_fn is None or self.guidance is not None) and use_graph:
             th.cuda.current_stream().synchronize()

@@ -30,7 +30,9 @@ import torch.distributed as dist
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 
-from autodiffusion_b200 import create_model_and_diffusion, model_and_diffusion_defaults  # noqa: E402
+from autodiffusion_b200 import (classifier_defaults, create_classifier, create_model_and_diffusion,  # noqa: E402
+                                model_and_diffusion_defaults)
+from autodiffusion_b200.classifier import ClassifierGuidance  # noqa: E402
 from autodiffusion_b200.evaluator import CandidateEvaluator, FIDStatistics  # noqa: E402
 
 ADM_FLAGS = dict(attention_resolutions="32,16,8", class_cond=True, diffusion_steps=1000, dropout=0.1, image_size=64,
@@ -67,6 +69,7 @@ def main():
     ap.add_argument("--feature_dim", type=int, default=2048)
     ap.add_argument("--seed", type=int, default=0)
     ap.add_argument("--small", action="store_true", help="64-channel 1-res-block UNet (functional check)")
+    ap.add_argument("--guided", action="store_true", help="classifier guidance (native depth-4 noisy classifier, scale 1.0)")
     args = ap.parse_args()
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -94,6 +97,21 @@ def main():
                 p.copy_(0.02 * th.randn(p.shape, generator=g))
     model.to(dev).eval()
     model.convert_to_fp16()
+    cond_fn = None
+    if args.guided:
+        cd = classifier_defaults()
+        cd.update(classifier_depth=4 if not args.small else 1, classifier_width=128 if not args.small else 64)
+        clf = create_classifier(**cd)
+        with th.no_grad():
+            for name, p in clf.named_parameters():
+                if p.dim() > 1:
+                    p.copy_(th.randn(p.shape, generator=g) / p[0].numel() ** 0.5)
+                elif name.endswith("weight"):
+                    p.copy_(1.0 + 0.1 * th.randn(p.shape, generator=g))
+                else:
+                    p.copy_(0.02 * th.randn(p.shape, generator=g))
+        clf.to(dev).eval()
+        cond_fn = ClassifierGuidance(clf, 1.0)
 
     d = args.feature_dim
     proj = (th.randn(3 * 64 * 64, d, generator=th.Generator().manual_seed(7)) * (3.0 / (3 * 64 * 64) ** 0.5)).to(dev)
@@ -106,7 +124,8 @@ def main():
     ref_stats = FIDStatistics(0.05 * rs.randn(d), a @ a.T * 0.05 + 0.02 * np.eye(d))
 
     ev = CandidateEvaluator(model, diffusion, feature_fn, ref_stats, batch_size=args.batch_size,
-                            num_samples=args.num_samples, seed=args.seed, max_cached_plans=args.candidates + 1)
+                            num_samples=args.num_samples, seed=args.seed, max_cached_plans=args.candidates + 1,
+                            cond_fn=cond_fn)
     rng = random.Random(args.seed)
     population = [draw_candidate(rng, args.time_step, model.layer_num, args.max_prun, args.mask_pool)
                   for _ in range(args.candidates)]
@@ -117,12 +136,16 @@ def main():
         dist.barrier()
     th.cuda.synchronize()
     t0 = time.time()
-    fids, t_sample, t_fid, t_plan = [], 0.0, 0.0, 0.0
-    for cand in population:
-        fids.append(ev.get_cand_fid(cand))
-        t_plan += ev.last_times["reset_time"]
-        t_sample += ev.last_times["sample_time"]
-        t_fid += ev.last_times["fid_time"]
+    t_sample, t_fid, t_plan = 0.0, 0.0, 0.0
+    pending, times = [], []
+    for cand in population:  # the host-side FID of candidate i overlaps the sampling of candidate i+1
+        pending.append(ev.submit_cand_fid(cand))
+        times.append(ev.last_times)
+    fids = [f.result() for f in pending]
+    for tm in times:
+        t_plan += tm["reset_time"]
+        t_sample += tm["sample_time"]
+        t_fid += tm["fid_time"]
     if world > 1:
         dist.barrier()
     th.cuda.synchronize()
@@ -141,9 +164,9 @@ def main():
             "metric": "population evaluation, candidates/s", "value": n / wall, "unit": "candidates/s",
             "images_per_s": n * args.num_samples / wall, "n_gpus": world, "candidates": n,
             "num_samples": args.num_samples, "batch_size": args.batch_size, "ddim_steps": args.time_step,
-            "feature_dim": d, "wall_s": wall,
+            "feature_dim": d, "wall_s": wall, "guided": bool(args.guided),
             "split_s": {"plan_build": round(t_plan, 3), "sampling_plus_allreduce": round(t_sample, 3),
-                        "host_sqrtm_fid": round(t_fid, 3)},
+                        "host_sqrtm_fid_overlapped": round(t_fid, 3)},
             "fid_first3": [round(x, 4) for x in fids[:3]],
             "note": "random-init weights, random-projection features (no Inception graph offline): FID values "
                     "exercise the statistic only",

@@ -105,3 +105,17 @@ def test_fid_statistics_matches_reference_fixture():
         a = FIDStatistics(*fid_ref.compute_statistics(g[f"{name}/f1"]))
         b = FIDStatistics(*fid_ref.compute_statistics(g[f"{name}/f2"]))
         assert abs(a.frechet_distance(b) - float(g[f"{name}/fid"])) <= 1e-6 * float(g[f"{name}/fid"])
+
+
+def test_eigh_form_of_the_frechet_distance_matches_sqrtm():
+    """The symmetric-eigenproblem form (fid_method="eigh") against the reference's sqrtm arithmetic."""
+    from autodiffusion_b200.evaluator import FIDStatistics
+
+    rs = np.random.RandomState(0)
+    d = 96
+    a, b = rs.randn(d, d) / d ** 0.5, rs.randn(d, d) / d ** 0.5
+    f1 = FIDStatistics(0.1 * rs.randn(d), a @ a.T + 0.1 * np.eye(d))
+    f2 = FIDStatistics(0.1 * rs.randn(d), b @ b.T + 0.1 * np.eye(d))
+    x, y = f1.frechet_distance(f2), f1.frechet_distance_eigh(f2)
+    assert abs(x - y) <= 1e-9 * abs(x)
+    assert abs(x - fid_ref.frechet_distance(f1.mu, f1.sigma, f2.mu, f2.sigma)) <= 1e-9 * abs(x)

@@ -142,6 +142,16 @@ class MomentAccumulator:
         return mu, sigma
 
 
+class _RemoteFid:
+    """Placeholder for a candidate whose host-side FID another rank computes (`CandidateEvaluator.resolve`)."""
+
+    def __init__(self, owner: int):
+        self.owner = owner
+
+    def result(self):
+        raise RuntimeError(f"this candidate's FID is computed on rank {self.owner}: use CandidateEvaluator.resolve(futures)")
+
+
 def batch_seed(seed: int, cand_key: str, batch_index: int) -> int:
     """Noise/label seed of one batch: a function of (global seed, candidate, batch index) only, so a
     candidate's images do not depend on how many ranks share the work (the reference seeds every
@@ -166,7 +176,7 @@ class CandidateEvaluator:
                  batch_size: int = 100, num_samples: int = 1000, image_size: int = 64, class_cond: bool = True,
                  clip_denoised: bool = True, cond_fn: Optional[Callable] = None, seed: int = 0,
                  rank: Optional[int] = None, world_size: Optional[int] = None, group=None, max_cached_plans: int = 8,
-                 fid_method: str = "sqrtm", fid_threads: Optional[int] = None):
+                 fid_method: str = "sqrtm", fid_threads: Optional[int] = None, shard_fid: bool = True):
         self.model = model
         self.base_diffusion = base_diffusion
         self.feature_fn = feature_fn
@@ -195,6 +205,11 @@ class CandidateEvaluator:
 
         local_world = int(os.environ.get("LOCAL_WORLD_SIZE", "1"))
         self.fid_threads = fid_threads if fid_threads is not None else max(1, (os.cpu_count() or 1) // max(1, local_world))
+        # The host-side sqrtm (several seconds at d=2048) is the serial term once sampling is sharded: every rank
+        # holds the all-reduced moments, so candidate number i is finished by rank i % world only and the values
+        # are exchanged in `resolve` (one tiny all-reduce per batch of candidates).
+        self.shard_fid = shard_fid
+        self._seq = 0
 
     # ---- plan cache keyed by what the launch schedule depends on ----
     def _plan_for(self, cand, batch: int) -> SchedulePlan:
@@ -221,7 +236,19 @@ class CandidateEvaluator:
 
     def get_cand_fid(self, cand=None, args=None) -> float:
         """…progressive.py:369-445: sample, reduce, FID - blocking, like the reference call."""
-        return self.submit_cand_fid(cand, args).result()
+        return self.resolve([self.submit_cand_fid(cand, args)])[0]
+
+    def resolve(self, futures) -> list:
+        """FID values of `submit_cand_fid` futures, in order, on every rank. Each rank waits for the candidates it
+        owns; with more than one rank the values are exchanged by one all-reduce of len(futures) doubles (every
+        rank must call this with the futures of the same candidates - they do: all ranks walk the same population)."""
+        vals = [0.0 if isinstance(f, _RemoteFid) else float(f.result()) for f in futures]
+        if any(isinstance(f, _RemoteFid) for f in futures) or (self.shard_fid and self.world_size > 1 and futures):
+            nccl = dist.get_backend(self.group) == "nccl"
+            t = th.tensor(vals, dtype=th.float64, device=self.model._device() if nccl else "cpu")
+            dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group)
+            vals = t.cpu().tolist()
+        return vals
 
     def submit_cand_fid(self, cand=None, args=None) -> Future:
         """Same work as `get_cand_fid`, but only the device part (sampling, moments, all-reduce, D2H of the
@@ -256,6 +283,12 @@ class CandidateEvaluator:
             acc = self._acc
             acc.reset()
         acc.all_reduce(self.group)
+        seq = self._seq
+        self._seq += 1
+        if self.shard_fid and self.world_size > 1 and seq % self.world_size != self.rank:
+            th.cuda.current_stream().synchronize() if acc.buf.is_cuda else None
+            self.last_times = dict(reset_time=reset_time, sample_time=time.time() - t0, fid_time=0.0)
+            return _RemoteFid(seq % self.world_size)
         host = self._host_bufs.pop() if self._host_bufs and self._host_bufs[-1].numel() == acc.buf.numel() \
             else th.empty(acc.buf.numel(), dtype=th.float64).pin_memory()
         host.copy_(acc.buf, non_blocking=True)

@@ -142,8 +142,10 @@ class EvolutionSearcher:
 
     def join(self):
         """Resolve every deferred FID (in submission order) and emit its log line."""
-        for cand, fut in list(self._pending.items()):
-            self.vis_dict[cand]["fid"] = fut.result()
+        resolve = getattr(self.evaluator, "resolve", None)
+        fids = resolve(list(self._pending.values())) if callable(resolve) else [f.result() for f in self._pending.values()]
+        for (cand, fut), fid in zip(list(self._pending.items()), fids):
+            self.vis_dict[cand]["fid"] = fid
             self.log("cand: {}, fid: {}".format(cand, self.vis_dict[cand]["fid"]))
             del self._pending[cand]
 

@@ -141,7 +141,7 @@ def main():
     for cand in population:  # the host-side FID of candidate i overlaps the sampling of candidate i+1
         pending.append(ev.submit_cand_fid(cand))
         times.append(ev.last_times)
-    fids = [f.result() for f in pending]
+    fids = ev.resolve(pending)  # each rank finishes the host-side FID of every world-th candidate
     for tm in times:
         t_plan += tm["reset_time"]
         t_sample += tm["sample_time"]

@@ -119,3 +119,39 @@ def test_eigh_form_of_the_frechet_distance_matches_sqrtm():
     x, y = f1.frechet_distance(f2), f1.frechet_distance_eigh(f2)
     assert abs(x - y) <= 1e-9 * abs(x)
     assert abs(x - fid_ref.frechet_distance(f1.mu, f1.sigma, f2.mu, f2.sigma)) <= 1e-9 * abs(x)
+
+
+def _resolve_worker(rank, world, port, tmp):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from concurrent.futures import Future
+
+    from autodiffusion_b200.evaluator import CandidateEvaluator, _RemoteFid
+
+    ev = object.__new__(CandidateEvaluator)  # only the exchange logic: no model, no device
+    ev.shard_fid, ev.world_size, ev.rank, ev.group = True, world, rank, None
+    futs = []
+    for seq in range(5):  # candidate `seq` is finished by rank seq % world (submit_cand_fid's rule)
+        if seq % world == rank:
+            f = Future()
+            f.set_result(seq + 0.25)
+            futs.append(f)
+        else:
+            futs.append(_RemoteFid(seq % world))
+    np.save(os.path.join(tmp, f"v{rank}.npy"), np.array(ev.resolve(futs)))
+    dist.destroy_process_group()
+
+
+def test_sharded_host_fid_values_reach_every_rank(tmp_path):
+    """world size 2, gloo: each rank computes the host FID of every other candidate; resolve() exchanges them."""
+    world, port = 2, 30100 + (os.getpid() % 500)
+    mp.spawn(_resolve_worker, args=(world, port, str(tmp_path)), nprocs=world, join=True)
+    for r in range(world):
+        assert np.load(tmp_path / f"v{r}.npy").tolist() == [0.25, 1.25, 2.25, 3.25, 4.25]
+
+
+def test_remote_fid_placeholder_refuses_a_direct_result():
+    from autodiffusion_b200.evaluator import _RemoteFid
+
+    with pytest.raises(RuntimeError):
+        _RemoteFid(1).result()

@@ -20,7 +20,7 @@ LIB_PATH = LIB_DIR / "libadb200.so"
 HEADER = _PKG.parent / "include" / "adb200.h"
 
 SOURCES = ["host.cu", "conv_igemm.cu", "attention.cu", "attention2.cu", "groupnorm.cu", "elementwise.cu", "moments.cu",
-           "attention_bwd.cu", "backward.cu"]
+           "attention_bwd.cu", "backward.cu", "attention_sd.cu", "sd_ops.cu"]
 
 NVCC_FLAGS = [
     "-O3",
@@ -105,6 +105,18 @@ class ConvDesc(C.Structure):
         ("stats2_out", C.c_void_p),
         ("stats2_cpg", C.c_int),
         ("stats2_choff", C.c_int),
+        ("bias_stride", C.c_int),
+        ("seg_stride", C.c_int * 3),
+    ]
+
+
+class AttnSdDesc(C.Structure):
+    _fields_ = [
+        ("q", C.c_void_p), ("q_width", C.c_int), ("q_col0", C.c_int),
+        ("kv", C.c_void_p), ("kv_width", C.c_int), ("k_col0", C.c_int), ("v_col0", C.c_int),
+        ("out", C.c_void_p),
+        ("b", C.c_int), ("heads", C.c_int), ("d_head", C.c_int), ("d_pad", C.c_int),
+        ("tq", C.c_int), ("tk_rows", C.c_int), ("tk_valid", C.c_int),
     ]
 
 
@@ -192,6 +204,11 @@ SYMBOLS = {
     "adb_pool_attention_backward": (_I, [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _P]),
     "adb_pool_merge": (_I, [_P, _P, _P, _P, _I, _I, _I, _P]),
     "adb_logsoftmax_grad": (_I, [_P, _P, _P, _P, _I, _I, C.c_float, _P]),
+    "adb_attention_sd": (_I, [_P, C.POINTER(AttnSdDesc), _P]),
+    "adb_layernorm": (_I, [_P, _P, _P, _P, _P, _I, _I, C.c_float, _P]),
+    "adb_geglu": (_I, [_P, _P, _P, _I, _I, _P]),
+    "adb_cfg_ddim_step": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, C.c_float, C.POINTER(C.c_float), _P]),
+    "adb_pad_context": (_I, [_P, _P, _P, _I, _I, _I, _I, _P]),
 }
 
 _lib = None

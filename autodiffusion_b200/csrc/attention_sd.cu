@@ -1,0 +1,349 @@
+// attention_sd.cu — fused softmax attention for the Stable-Diffusion transformer blocks: separate Q and
+// K/V matrices (self- and cross-attention), head dims 40 / 80 / 160 stored in 64-column chunks, key masking.
+//
+// Replaces CrossAttention.forward between its projections (reference: "Stable Diffusion"/ldm/modules/attention.py:
+// 170-194): out = softmax(q k^T * dim_head^-0.5) v per (batch, head), heads laid out as (h d) along channels.
+//
+// Layout contract (chosen by the weight packer, autodiffusion_b200/sd_unet.py): every head occupies DP = 64*NC
+// columns of the projection outputs; columns [d, DP) are exactly zero (zero weight rows, the projections have no
+// bias), so they add nothing to q.k and produce zeros in the output, whose consumer (to_out) has zero weight
+// columns there. The kernel therefore needs no per-d variants: QK^T runs ceil(d/16) 16-deep k-steps, PV writes
+// 64-column chunks (the last one n_last <= 64 wide).
+//
+// Same skeleton as attention2.cu (P kept in TMEM over S, 64-key tiles, double-buffered S, lazy rescaling); see
+// that file for the barrier protocol. What differs: NC chunks of Q/K/V per tile, the Q and K/V tensor maps are
+// different matrices with different rows per batch element, keys >= tk_valid are masked to -inf (77 context
+// tokens inside a 128-row padded context), scale is a parameter.
+#include <stdlib.h>
+#include <string.h>
+
+#include "common.cuh"
+
+namespace adb {
+
+namespace {
+
+constexpr int AT_THREADS = 192;
+constexpr int BM = 128;
+constexpr int KT = 64;
+constexpr int CH = 64;                    // columns per head-dim chunk = one 128-byte swizzle row
+constexpr int Q_CHUNK_BYTES = BM * CH * 2;   // 16 KiB
+constexpr int KV_CHUNK_BYTES = KT * CH * 2;  // 8 KiB
+constexpr int O_COL = 128;
+
+__device__ __forceinline__ float ex2_approx_sd(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+struct AttnSdParams {
+  CUtensorMap tmQ;   // box {64, 128} over the Q matrix [b*tq, q_width]
+  CUtensorMap tmKV;  // box {64, 64} over the K/V matrix [b*tk_rows, kv_width]
+  __nv_bfloat16* out;  // [b*tq, heads*DP]
+  int tq;        // queries per batch element
+  int tk_rows;   // K/V rows per batch element in the K/V matrix (>= tk_valid)
+  int tk_valid;  // keys that take part in the softmax
+  int heads;
+  int q_col0, k_col0, v_col0;  // column of head 0 in the Q / K / V matrices (head h is DP*h further)
+  int ksteps;    // 16-deep k-steps of q.k: ceil(d/16)
+  int n_last;    // width of the last PV chunk (multiple of 16)
+  float sc;      // d^-0.5 * log2(e)
+};
+
+template <int NC>
+struct SdCfg {
+  static constexpr int STAGES = (NC == 1) ? 4 : 3;
+  static constexpr int Q_BYTES = NC * Q_CHUNK_BYTES;
+  static constexpr int STAGE_BYTES = 2 * NC * KV_CHUNK_BYTES;
+  static constexpr int SMEM_BYTES = Q_BYTES + STAGES * STAGE_BYTES + 1024;
+  static constexpr int TMEM_COLS = (O_COL + NC * CH <= 256) ? 256 : 512;
+  static constexpr int MIN_CTAS = (NC == 1) ? 2 : 1;
+};
+
+template <int NC>
+__global__ void __launch_bounds__(AT_THREADS, SdCfg<NC>::MIN_CTAS) attention_sd_kernel(const __grid_constant__ AttnSdParams p) {
+  using C = SdCfg<NC>;
+  constexpr int STAGES = C::STAGES;
+  constexpr int B_Q = 0;
+  constexpr int B_KV_FULL = 1;
+  constexpr int B_KV_EMPTY = B_KV_FULL + STAGES;
+  constexpr int B_S_FULL = B_KV_EMPTY + STAGES;
+  constexpr int B_P_FULL = B_S_FULL + 2;
+  constexpr int B_PV_DONE = B_P_FULL + 2;
+  constexpr int NUM_BARS = B_PV_DONE + 2;
+  constexpr int DP = NC * CH;
+
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t bars[NUM_BARS];
+  __shared__ uint32_t tmem_slot_s;
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t q_smem = smem_base;
+  auto k_smem = [&](int st) { return smem_base + C::Q_BYTES + st * C::STAGE_BYTES; };
+  auto v_smem = [&](int st) { return k_smem(st) + NC * KV_CHUNK_BYTES; };
+  const uint32_t bar0 = smem_u32(bars);
+  auto bar = [&](int i) { return bar0 + 8u * i; };
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int bh = blockIdx.y;
+  const int b = bh / p.heads;
+  const int h = bh - b * p.heads;
+  const int q0 = blockIdx.x * BM;
+  const int qrow_base = b * p.tq;
+  const int krow_base = b * p.tk_rows;
+  const int qc = p.q_col0 + h * DP;
+  const int kc = p.k_col0 + h * DP;
+  const int vc = p.v_col0 + h * DP;
+  const int nkt = (p.tk_valid + KT - 1) / KT;
+
+  if (warp == 4 && lane == 0) {
+    tma_prefetch_desc(&p.tmQ);
+    tma_prefetch_desc(&p.tmKV);
+    for (int i = 0; i < NUM_BARS; ++i) mbar_init(bar(i), (i == B_P_FULL || i == B_P_FULL + 1) ? 4 : 1);
+    fence_mbar_init();
+  }
+  if (warp == 5) {
+    tmem_alloc(smem_u32(&tmem_slot_s), C::TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(&tmem_slot_s);
+
+  if (warp == 4) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      mbar_arrive_expect_tx(bar(B_Q), C::Q_BYTES);
+#pragma unroll
+      for (int c = 0; c < NC; ++c) tma_load_2d(q_smem + c * Q_CHUNK_BYTES, &p.tmQ, bar(B_Q), qc + c * CH, qrow_base + q0);
+      for (int j = 0; j < nkt; ++j) {
+        const int st = j % STAGES;
+        const uint32_t use = (uint32_t)(j / STAGES);
+        mbar_wait(bar(B_KV_EMPTY + st), (use & 1u) ^ 1u);
+        mbar_arrive_expect_tx(bar(B_KV_FULL + st), C::STAGE_BYTES);
+#pragma unroll
+        for (int c = 0; c < NC; ++c) {
+          tma_load_2d(k_smem(st) + c * KV_CHUNK_BYTES, &p.tmKV, bar(B_KV_FULL + st), kc + c * CH, krow_base + j * KT);
+          tma_load_2d(v_smem(st) + c * KV_CHUNK_BYTES, &p.tmKV, bar(B_KV_FULL + st), vc + c * CH, krow_base + j * KT);
+        }
+      }
+    }
+  } else if (warp == 5) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      constexpr uint32_t idesc_s = umma_idesc_bf16(BM, KT, 0, 0);
+      constexpr uint32_t idesc_o = umma_idesc_bf16(BM, CH, 0, 1);  // B = V, MN-major (as stored)
+      const uint32_t idesc_o_last = umma_idesc_bf16(BM, p.n_last, 0, 1);
+      auto issue_s = [&](int j) {
+        const int st = j % STAGES;
+        mbar_wait(bar(B_KV_FULL + st), (uint32_t)(j / STAGES) & 1u);
+        tc_fence_after();
+        for (int kk = 0; kk < p.ksteps; ++kk) {
+          const int c = kk >> 2, w = kk & 3;
+          const uint64_t a_desc = umma_desc_kmajor_sw128(q_smem + c * Q_CHUNK_BYTES) + 2u * w;
+          const uint64_t b_desc = umma_desc_kmajor_sw128(k_smem(st) + c * KV_CHUNK_BYTES) + 2u * w;
+          umma_bf16_ss(tmem_base + (j & 1) * KT, a_desc, b_desc, idesc_s, kk != 0);
+        }
+        umma_commit(bar(B_S_FULL + (j & 1)));
+      };
+      mbar_wait(bar(B_Q), 0);
+      issue_s(0);
+      for (int j = 0; j < nkt; ++j) {
+        if (j + 1 < nkt) issue_s(j + 1);
+        const int st = j % STAGES;
+        mbar_wait(bar(B_P_FULL + (j & 1)), (uint32_t)(j >> 1) & 1u);  // P_j in TMEM (and O rescaled)
+        tc_fence_after();
+#pragma unroll
+        for (int c = 0; c < NC; ++c) {
+          const uint32_t idesc = (c == NC - 1) ? idesc_o_last : idesc_o;
+#pragma unroll
+          for (int kk = 0; kk < KT / 16; ++kk) {
+            const uint64_t b_desc = umma_desc_mnmajor_sw128(v_smem(st) + c * KV_CHUNK_BYTES + kk * 2048, 1024);
+            umma_bf16_ts(tmem_base + O_COL + c * CH, tmem_base + (j & 1) * KT + 8 * kk, b_desc, idesc, (j | kk) != 0);
+          }
+        }
+        umma_commit(bar(B_KV_EMPTY + st));
+        umma_commit(bar(B_PV_DONE + (j & 1)));
+      }
+    }
+  } else {
+    // ===================== softmax (warps 0..3): one query row per thread =====================
+    const int quarter = warp & 3;
+    const int row = quarter * 32 + lane;
+    const uint32_t lane_addr = tmem_base + ((uint32_t)(quarter * 32) << 16);
+    const float sc = p.sc;
+    const int ocols = (NC - 1) * CH + p.n_last;  // O columns the PV product writes
+    float m_run = -INFINITY;
+    float l_run = 0.f;
+    for (int j = 0; j < nkt; ++j) {
+      const uint32_t s_addr = lane_addr + (j & 1) * KT;
+      mbar_wait(bar(B_S_FULL + (j & 1)), (uint32_t)(j >> 1) & 1u);
+      tc_fence_after();
+      uint32_t sr[KT];
+      tmem_ld_32x32b_x32(s_addr, sr);
+      tmem_ld_32x32b_x32(s_addr + 32, sr + 32);
+      tmem_wait_ld();
+      const int kvalid = p.tk_valid - j * KT;  // keys of this tile inside the sequence (warp-uniform)
+      if (kvalid < KT) {
+#pragma unroll
+        for (int i = 0; i < KT; ++i)
+          if (i >= kvalid) sr[i] = 0xff800000u;  // -inf
+      }
+      float mxs[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) mxs[i] = __uint_as_float(sr[i]);
+#pragma unroll
+      for (int i = 8; i < KT; ++i) mxs[i & 7] = fmaxf(mxs[i & 7], __uint_as_float(sr[i]));
+      const float mx = fmaxf(fmaxf(fmaxf(mxs[0], mxs[1]), fmaxf(mxs[2], mxs[3])),
+                             fmaxf(fmaxf(mxs[4], mxs[5]), fmaxf(mxs[6], mxs[7])));
+      // sc > 0: max and scaling commute. Lazy rescaling as in attention2.cu (threshold 8 in log2 units).
+      const float m_tile = mx * sc;
+      const bool jump = m_tile > m_run + 8.0f;
+      float alpha = 1.0f;
+      float m_new = m_run;
+      if (__any_sync(0xffffffffu, jump)) {
+        m_new = fmaxf(m_run, m_tile);
+        alpha = ex2_approx_sd(m_run - m_new);
+        if (j > 0) {
+          mbar_wait(bar(B_PV_DONE + ((j - 1) & 1)), (uint32_t)((j - 1) >> 1) & 1u);
+          tc_fence_after();
+#pragma unroll 1
+          for (int c = 0; c < DP; c += 32) {
+            if (c >= ocols) break;
+            uint32_t v[32];
+            tmem_ld_32x32b_x32(lane_addr + O_COL + c, v);
+            tmem_wait_ld();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) * alpha);
+            tmem_st_32x32b_x32(lane_addr + O_COL + c, v);
+          }
+        }
+      }
+      float ps[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) ps[i] = 0.f;
+#pragma unroll
+      for (int i = 0; i < KT / 2; ++i) {
+        const float p0 = ex2_approx_sd(fmaf(__uint_as_float(sr[2 * i]), sc, -m_new));
+        const float p1 = ex2_approx_sd(fmaf(__uint_as_float(sr[2 * i + 1]), sc, -m_new));
+        ps[(2 * i) & 7] += p0;
+        ps[(2 * i + 1) & 7] += p1;
+        sr[i] = pack_bf16x2(p0, p1);
+      }
+      const float ps0 = (ps[0] + ps[1]) + (ps[2] + ps[3]);
+      const float ps1 = (ps[4] + ps[5]) + (ps[6] + ps[7]);
+      tmem_st_32x32b_x32(s_addr, sr);
+      l_run = l_run * alpha + (ps0 + ps1);
+      m_run = m_new;
+      tmem_wait_st();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar(B_P_FULL + (j & 1)));
+    }
+    mbar_wait(bar(B_PV_DONE + ((nkt - 1) & 1)), (uint32_t)((nkt - 1) >> 1) & 1u);
+    tc_fence_after();
+    const float inv = 1.0f / l_run;
+    const bool ok = (q0 + row) < p.tq;
+    __nv_bfloat16* orow = p.out + ((size_t)(qrow_base + q0 + row)) * ((size_t)p.heads * DP) + h * DP;
+#pragma unroll 1
+    for (int c = 0; c < DP; c += 32) {
+      uint32_t v[32];
+      if (c < ocols) {
+        tmem_ld_32x32b_x32(lane_addr + O_COL + c, v);
+        tmem_wait_ld();
+      }
+#pragma unroll
+      for (int i = 0; i < 32; ++i)
+        if (c + i >= ocols) v[i] = 0u;  // columns the PV product never wrote: the head's zero padding
+      if (ok) {
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          uint4 o;
+          o.x = pack_bf16x2(__uint_as_float(v[g * 8 + 0]) * inv, __uint_as_float(v[g * 8 + 1]) * inv);
+          o.y = pack_bf16x2(__uint_as_float(v[g * 8 + 2]) * inv, __uint_as_float(v[g * 8 + 3]) * inv);
+          o.z = pack_bf16x2(__uint_as_float(v[g * 8 + 4]) * inv, __uint_as_float(v[g * 8 + 5]) * inv);
+          o.w = pack_bf16x2(__uint_as_float(v[g * 8 + 6]) * inv, __uint_as_float(v[g * 8 + 7]) * inv);
+          *reinterpret_cast<uint4*>(orow + c + g * 8) = o;
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 5) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, C::TMEM_COLS);
+  }
+}
+
+template <int NC>
+int launch_attn_sd(const AttnSdParams& ap, int b, cudaStream_t stream) {
+  using C = SdCfg<NC>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    ADB_CUDA(cudaFuncSetAttribute(attention_sd_kernel<NC>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+    attr_set = true;
+  }
+  dim3 grid((ap.tq + BM - 1) / BM, b * ap.heads);
+  attention_sd_kernel<NC><<<grid, AT_THREADS, C::SMEM_BYTES, stream>>>(ap);
+  ADB_CUDA(cudaGetLastError());
+  return 1;
+}
+
+}  // namespace
+
+int attention_sd_submit(adb_plan* plan, const adb_attn_sd_desc* d, cudaStream_t stream) {
+  ADB_REQUIRE(d && d->q && d->kv && d->out && d->b > 0 && d->heads > 0, "attention_sd: bad arguments");
+  ADB_REQUIRE(d->d_head > 0 && d->d_head <= 192 && d->d_pad % 64 == 0 && d->d_pad >= d->d_head && d->d_pad <= 192,
+              "attention_sd: head dim %d (padded %d) unsupported", d->d_head, d->d_pad);
+  ADB_REQUIRE(d->tq > 0 && d->tk_valid > 0 && d->tk_rows >= d->tk_valid, "attention_sd: bad sequence lengths");
+  ADB_REQUIRE(d->q_width % 8 == 0 && d->kv_width % 8 == 0, "attention_sd: matrix widths must be multiples of 8");
+  const int nc = d->d_pad / 64;
+  AttnSdParams ap;
+  memset(&ap, 0, sizeof(ap));
+  {
+    const uint64_t dims[2] = {(uint64_t)d->q_width, (uint64_t)d->b * d->tq};
+    const uint64_t strides[1] = {(uint64_t)d->q_width * 2};
+    const uint32_t box[2] = {64, 128};
+    int r = make_tmap_bf16(&ap.tmQ, d->q, 2, dims, strides, box);
+    if (r != ADB_OK) return r;
+  }
+  {
+    const uint64_t dims[2] = {(uint64_t)d->kv_width, (uint64_t)d->b * d->tk_rows};
+    const uint64_t strides[1] = {(uint64_t)d->kv_width * 2};
+    const uint32_t box[2] = {64, 64};
+    int r = make_tmap_bf16(&ap.tmKV, d->kv, 2, dims, strides, box);
+    if (r != ADB_OK) return r;
+  }
+  ap.out = reinterpret_cast<__nv_bfloat16*>(d->out);
+  ap.tq = d->tq;
+  ap.tk_rows = d->tk_rows;
+  ap.tk_valid = d->tk_valid;
+  ap.heads = d->heads;
+  ap.q_col0 = d->q_col0;
+  ap.k_col0 = d->k_col0;
+  ap.v_col0 = d->v_col0;
+  ap.ksteps = (d->d_head + 15) / 16;
+  static int full_n = -1;
+  if (full_n < 0) {
+    const char* e = getenv("ADB_ATTN_SD_FULLN");
+    full_n = (e && e[0] == '1') ? 1 : 0;
+  }
+  const int rem = d->d_head - (nc - 1) * 64;           // real columns in the last chunk
+  ap.n_last = full_n ? 64 : ((rem + 15) / 16) * 16;
+  ap.sc = (float)(1.4426950408889634 / sqrt((double)d->d_head));
+  const double flops = 4.0 * (double)d->b * d->heads * (double)d->tq * (double)d->tk_valid * d->d_head;
+  const int b = d->b;
+  return submit(plan, stream, "attention_sd", flops, 0.0, [ap, b, nc](cudaStream_t s) -> int {
+    switch (nc) {
+      case 1: return launch_attn_sd<1>(ap, b, s);
+      case 2: return launch_attn_sd<2>(ap, b, s);
+      default: return launch_attn_sd<3>(ap, b, s);
+    }
+  });
+}
+
+}  // namespace adb

@@ -45,11 +45,13 @@ struct ConvKParams {
   int seg_cin[3];
   int seg_chunks[3];
   int seg_kbase[3];
+  int seg_stride[3];  // 2: 3x3 stride-2 pad-1 segment; tmA[s] is then the 5-D view [n, h, 2, w, 2*cin] of the input
   int nseg;
   int M, cout, H, W;
   int m_tiles, n_tiles;
   int k_iters;
   const float* bias;
+  int bias_stride;  // floats between consecutive images' bias rows (0: one shared row)
   const __nv_bfloat16* residual;
   int res_mode;
   void* out;
@@ -179,6 +181,11 @@ conv_igemm_kernel(const __grid_constant__ ConvKParams p) {
             const int dy = (taps == 9) ? (tap / 3 - 1) : 0;
             const int dx = (taps == 9) ? (tap % 3 - 1) : 0;
             const int kb = p.seg_kbase[s] + tap * p.seg_cin[s];
+            // stride 2 (Downsample.op): input row 2y+dy is row-pair y + (dy < 0 ? -1 : 0), parity (dy != 0) of the
+            // [n, h, 2, w, 2*cin] view; same along x, where the parity selects the upper cin channels of a pixel pair
+            const bool s2 = p.seg_stride[s] == 2;
+            const int sy = dy < 0 ? -1 : 0, py = dy != 0 ? 1 : 0;
+            const int sx = dx < 0 ? -1 : 0, pxc = dx != 0 ? p.seg_cin[s] : 0;
             for (int ch = 0; ch < chunks; ++ch) {
               mbar_wait(empty_bar(stage), phase ^ 1u);
               const uint32_t a_dst = smem_base + stage * C::STAGE_BYTES;
@@ -187,7 +194,8 @@ conv_igemm_kernel(const __grid_constant__ ConvKParams p) {
                 const uint32_t lead_full = mapa_shared(full_bar(stage), 0);
                 if (is_leader) mbar_arrive_expect_tx(full_bar(stage), 2 * C::STAGE_BYTES);
                 else mbar_arrive_cluster(lead_full);
-                tma_load_4d_2sm(a_dst, &p.tmA[s], lead_full, ch * BLOCK_K, x0 + dx, y0 + dy, img);
+                if (s2) tma_load_5d_2sm(a_dst, &p.tmA[s], lead_full, pxc + ch * BLOCK_K, x0 + sx, py, y0 + sy, img);
+                else tma_load_4d_2sm(a_dst, &p.tmA[s], lead_full, ch * BLOCK_K, x0 + dx, y0 + dy, img);
                 if (BLOCK_N == 256) {  // two 64-row boxes
                   tma_load_2d_2sm(b_dst, &p.tmW, lead_full, kb + ch * BLOCK_K, n_tile * BLOCK_N + (int)cta_rank * 128);
                   tma_load_2d_2sm(b_dst + 8192, &p.tmW, lead_full, kb + ch * BLOCK_K, n_tile * BLOCK_N + (int)cta_rank * 128 + 64);
@@ -197,7 +205,8 @@ conv_igemm_kernel(const __grid_constant__ ConvKParams p) {
                 }
               } else {
                 mbar_arrive_expect_tx(full_bar(stage), C::STAGE_BYTES);
-                tma_load_4d(a_dst, &p.tmA[s], full_bar(stage), ch * BLOCK_K, x0 + dx, y0 + dy, img);
+                if (s2) tma_load_5d(a_dst, &p.tmA[s], full_bar(stage), pxc + ch * BLOCK_K, x0 + sx, py, y0 + sy, img);
+                else tma_load_4d(a_dst, &p.tmA[s], full_bar(stage), ch * BLOCK_K, x0 + dx, y0 + dy, img);
                 tma_load_2d(b_dst, &p.tmW, full_bar(stage), kb + ch * BLOCK_K, n_tile * BLOCK_N);
               }
               if (++stage == STAGES) {
@@ -344,7 +353,7 @@ conv_igemm_kernel(const __grid_constant__ ConvKParams p) {
           tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * BLOCK_N + c, v);
           float4 bv[8];
           if (p.bias != nullptr) {
-            const float4* b4 = reinterpret_cast<const float4*>(p.bias + col0);
+            const float4* b4 = reinterpret_cast<const float4*>(p.bias + (size_t)img * p.bias_stride + col0);
 #pragma unroll
             for (int j = 0; j < 8; ++j) bv[j] = __ldg(b4 + j);
           } else {
@@ -484,8 +493,9 @@ conv_igemm_kernel(const __grid_constant__ ConvKParams p) {
         float4 bv[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) bv[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+        const float* bias_row = p.bias + (row_ok ? (size_t)img * p.bias_stride : 0);
         if (p.bias != nullptr && ncols == 32) {
-          const float4* b4 = reinterpret_cast<const float4*>(p.bias + col0);
+          const float4* b4 = reinterpret_cast<const float4*>(bias_row + col0);
 #pragma unroll
           for (int j = 0; j < 8; ++j) bv[j] = __ldg(b4 + j);
         }
@@ -513,7 +523,7 @@ conv_igemm_kernel(const __grid_constant__ ConvKParams p) {
         if (p.bias != nullptr && ncols != 32) {
 #pragma unroll
           for (int i = 0; i < 32; ++i)
-            if (i < ncols) f[i] += __ldg(p.bias + col0 + i);
+            if (i < ncols) f[i] += __ldg(bias_row + col0 + i);
         }
         if (p.out_mode == ADB_OUT_BF16_NHWC) {
           // residual: 8-channel vectors lie fully inside cout (cout % 8 == 0)
@@ -825,11 +835,23 @@ int conv_igemm_submit(adb_plan* plan, const adb_conv_desc* d, cudaStream_t strea
     kp.seg_kbase[s] = ktot;
     ktot += sg.taps * sg.cin;
     kp.k_iters += sg.taps * kp.seg_chunks[s];
-    const uint64_t dims[4] = {(uint64_t)sg.cin, (uint64_t)d->w, (uint64_t)d->h, (uint64_t)d->n};
-    const uint64_t strides[3] = {(uint64_t)sg.cin * 2, (uint64_t)d->w * sg.cin * 2,
-                                 (uint64_t)P * sg.cin * 2};
-    const uint32_t box[4] = {(uint32_t)BLOCK_K, (uint32_t)bw, (uint32_t)bh, (uint32_t)bn};
-    int r = make_tmap_bf16(&kp.tmA[s], sg.act, 4, dims, strides, box);
+    kp.seg_stride[s] = d->seg_stride[s] == 2 ? 2 : 1;
+    int r;
+    if (kp.seg_stride[s] == 2) {
+      ADB_REQUIRE(sg.taps == 9 && sg.cin % BLOCK_K == 0, "conv_igemm: a stride-2 segment needs taps = 9 and cin %% 64 == 0");
+      // input [n, 2h, 2w, cin] viewed as [n, h, 2, w, 2*cin]: a pixel pair along x is one row of 2*cin channels
+      const uint64_t dims[5] = {(uint64_t)2 * sg.cin, (uint64_t)d->w, 2, (uint64_t)d->h, (uint64_t)d->n};
+      const uint64_t strides[4] = {(uint64_t)2 * sg.cin * 2, (uint64_t)2 * d->w * sg.cin * 2,
+                                   (uint64_t)4 * d->w * sg.cin * 2, (uint64_t)4 * P * sg.cin * 2};
+      const uint32_t box[5] = {(uint32_t)BLOCK_K, (uint32_t)bw, 1u, (uint32_t)bh, (uint32_t)bn};
+      r = make_tmap_bf16(&kp.tmA[s], sg.act, 5, dims, strides, box);
+    } else {
+      const uint64_t dims[4] = {(uint64_t)sg.cin, (uint64_t)d->w, (uint64_t)d->h, (uint64_t)d->n};
+      const uint64_t strides[3] = {(uint64_t)sg.cin * 2, (uint64_t)d->w * sg.cin * 2,
+                                   (uint64_t)P * sg.cin * 2};
+      const uint32_t box[4] = {(uint32_t)BLOCK_K, (uint32_t)bw, (uint32_t)bh, (uint32_t)bn};
+      r = make_tmap_bf16(&kp.tmA[s], sg.act, 4, dims, strides, box);
+    }
     if (r != ADB_OK) return r;
   }
   int block_n = conv_block_n(d->cout);
@@ -873,6 +895,9 @@ int conv_igemm_submit(adb_plan* plan, const adb_conv_desc* d, cudaStream_t strea
   kp.m_tiles = (int)((M + BLOCK_M - 1) / BLOCK_M);
   kp.n_tiles = (d->cout_pad + block_n - 1) / block_n;
   kp.bias = d->bias;
+  kp.bias_stride = d->bias != nullptr ? d->bias_stride : 0;
+  ADB_REQUIRE(kp.bias_stride == 0 || (kp.bias_stride >= d->cout && kp.bias_stride % 4 == 0 && P % 32 == 0),
+              "conv_igemm: per-image bias needs bias_stride >= cout, %% 4 == 0 and h*w %% 32 == 0");
   kp.residual = reinterpret_cast<const __nv_bfloat16*>(d->residual);
   kp.res_mode = d->res_mode;
   kp.out = d->out;

@@ -120,6 +120,12 @@ int ddim_step_submit(adb_plan*, const float*, const float*, int, const float*, f
                      int, int, const float*, int, cudaStream_t);
 int pack_uint8_submit(adb_plan*, const float*, uint8_t*, int, int, int, cudaStream_t);
 int moments_submit(adb_plan*, const float*, int, int, double*, double*, cudaStream_t);
+int attention_sd_submit(adb_plan*, const adb_attn_sd_desc*, cudaStream_t);
+int layernorm_submit(adb_plan*, const void*, const float*, const float*, void*, int, int, float, cudaStream_t);
+int geglu_submit(adb_plan*, const void*, void*, int, int, cudaStream_t);
+int cfg_ddim_step_submit(adb_plan*, const float*, const float*, float*, float*, int, int, int, float, const float*,
+                         cudaStream_t);
+int pad_context_submit(adb_plan*, const float*, void*, int, int, int, int, cudaStream_t);
 
 }  // namespace adb
 
@@ -311,6 +317,28 @@ int adb_pack_uint8(adb_plan* plan, const float* sample, uint8_t* out, int n, int
 int adb_moments_accumulate(adb_plan* plan, const float* feats, int n, int d, double* sum_x,
                            double* sum_xx, adb_stream stream) {
   return moments_submit(plan, feats, n, d, sum_x, sum_xx, static_cast<cudaStream_t>(stream));
+}
+
+int adb_attention_sd(adb_plan* plan, const adb_attn_sd_desc* d, adb_stream stream) {
+  return attention_sd_submit(plan, d, static_cast<cudaStream_t>(stream));
+}
+
+int adb_layernorm(adb_plan* plan, const void* x, const float* gamma, const float* beta, void* out, int rows, int c,
+                  float eps, adb_stream stream) {
+  return layernorm_submit(plan, x, gamma, beta, out, rows, c, eps, static_cast<cudaStream_t>(stream));
+}
+
+int adb_geglu(adb_plan* plan, const void* x, void* out, int rows, int inner, adb_stream stream) {
+  return geglu_submit(plan, x, out, rows, inner, static_cast<cudaStream_t>(stream));
+}
+
+int adb_cfg_ddim_step(adb_plan* plan, const float* x, const float* eps, float* x_prev, float* pred_x0, int n,
+                      int chw, int cfg, float scale, const float coef[4], adb_stream stream) {
+  return cfg_ddim_step_submit(plan, x, eps, x_prev, pred_x0, n, chw, cfg, scale, coef, static_cast<cudaStream_t>(stream));
+}
+
+int adb_pad_context(adb_plan* plan, const float* ctx, void* out, int n, int t, int c, int t_pad, adb_stream stream) {
+  return pad_context_submit(plan, ctx, out, n, t, c, t_pad, static_cast<cudaStream_t>(stream));
 }
 
 int adb_memset0(adb_plan* plan, void* ptr, size_t bytes, adb_stream stream) {

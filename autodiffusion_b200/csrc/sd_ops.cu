@@ -1,0 +1,203 @@
+// sd_ops.cu — the memory-bound pieces of the Stable-Diffusion transformer blocks and its sampler step.
+//
+// Reference ("Stable Diffusion"/ldm/...): nn.LayerNorm in BasicTransformerBlock (modules/attention.py:205-216),
+// GEGLU (modules/attention.py:37-44), p_sample_ddim with classifier-free guidance (models/diffusion/ddim.py:177-217).
+// All HBM-bound: 16-byte vector loads, one pass over the data, statistics in registers.
+#include <math.h>
+#include <string.h>
+
+#include "common.cuh"
+
+namespace adb {
+
+namespace {
+
+constexpr int LN_MAX_VEC = 8;  // 16-byte vectors per lane: c <= 32 * 8 * 8 = 2048
+
+__device__ __forceinline__ void unpack8(const uint4& v, float* f) {
+  f[0] = bf16_lo(v.x); f[1] = bf16_hi(v.x);
+  f[2] = bf16_lo(v.y); f[3] = bf16_hi(v.y);
+  f[4] = bf16_lo(v.z); f[5] = bf16_hi(v.z);
+  f[6] = bf16_lo(v.w); f[7] = bf16_hi(v.w);
+}
+
+// One warp per token row; the row stays in registers between the mean, the variance and the normalise pass.
+template <int NV>
+__global__ void __launch_bounds__(256) layernorm_kernel(const uint4* __restrict__ x, const float* __restrict__ gamma,
+                                                        const float* __restrict__ beta, uint4* __restrict__ out,
+                                                        int rows, int nvec, float eps) {
+  const int lane = threadIdx.x & 31;
+  const int warps_per_block = blockDim.x >> 5;
+  const float inv_c = 1.0f / (float)(nvec * 8);
+  for (int row = blockIdx.x * warps_per_block + (threadIdx.x >> 5); row < rows; row += gridDim.x * warps_per_block) {
+    const uint4* xr = x + (size_t)row * nvec;
+    float f[NV][8];
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int vi = lane + 32 * i;
+      if (vi < nvec) {
+        const uint4 v = __ldg(xr + vi);
+        unpack8(v, f[i]);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) s += f[i][k];
+      }
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
+    const float mean = s * inv_c;
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      if (lane + 32 * i < nvec) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const float dlt = f[i][k] - mean;
+          q = fmaf(dlt, dlt, q);
+        }
+      }
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) q += __shfl_xor_sync(0xffffffffu, q, off);
+    const float rstd = rsqrtf(q * inv_c + eps);
+    uint4* orow = out + (size_t)row * nvec;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int vi = lane + 32 * i;
+      if (vi < nvec) {
+        const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma) + 2 * vi);
+        const float4 g1 = __ldg(reinterpret_cast<const float4*>(gamma) + 2 * vi + 1);
+        const float4 b0 = __ldg(reinterpret_cast<const float4*>(beta) + 2 * vi);
+        const float4 b1 = __ldg(reinterpret_cast<const float4*>(beta) + 2 * vi + 1);
+        uint4 o;
+        o.x = pack_bf16x2(fmaf((f[i][0] - mean) * rstd, g0.x, b0.x), fmaf((f[i][1] - mean) * rstd, g0.y, b0.y));
+        o.y = pack_bf16x2(fmaf((f[i][2] - mean) * rstd, g0.z, b0.z), fmaf((f[i][3] - mean) * rstd, g0.w, b0.w));
+        o.z = pack_bf16x2(fmaf((f[i][4] - mean) * rstd, g1.x, b1.x), fmaf((f[i][5] - mean) * rstd, g1.y, b1.y));
+        o.w = pack_bf16x2(fmaf((f[i][6] - mean) * rstd, g1.z, b1.z), fmaf((f[i][7] - mean) * rstd, g1.w, b1.w));
+        orow[vi] = o;
+      }
+    }
+  }
+}
+
+__device__ __forceinline__ float gelu_erf(float g) { return 0.5f * g * (1.0f + erff(g * 0.70710678118654752f)); }
+
+// out[r, j] = a[r, j] * gelu(gate[r, j]); a = x[:, :inner], gate = x[:, inner:]
+__global__ void __launch_bounds__(256) geglu_kernel(const uint4* __restrict__ x, uint4* __restrict__ out, size_t total_vec,
+                                                    int inner_vec) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total_vec; i += (size_t)gridDim.x * blockDim.x) {
+    const size_t r = i / inner_vec;
+    const size_t j = i - r * inner_vec;
+    const uint4 av = __ldg(x + r * 2 * inner_vec + j);
+    const uint4 gv = __ldg(x + r * 2 * inner_vec + inner_vec + j);
+    float a[8], g[8];
+    unpack8(av, a);
+    unpack8(gv, g);
+    uint4 o;
+    o.x = pack_bf16x2(a[0] * gelu_erf(g[0]), a[1] * gelu_erf(g[1]));
+    o.y = pack_bf16x2(a[2] * gelu_erf(g[2]), a[3] * gelu_erf(g[3]));
+    o.z = pack_bf16x2(a[4] * gelu_erf(g[4]), a[5] * gelu_erf(g[5]));
+    o.w = pack_bf16x2(a[6] * gelu_erf(g[6]), a[7] * gelu_erf(g[7]));
+    out[i] = o;
+  }
+}
+
+struct CfgCoef {
+  float v[4];
+};
+
+// Every operation of ddim.py:187-216 keeps its own fp32 rounding (explicit _rn intrinsics: no FMA contraction).
+__global__ void __launch_bounds__(256) cfg_ddim_step_kernel(const float* __restrict__ x, const float* __restrict__ eps,
+                                                            float* __restrict__ x_prev, float* __restrict__ pred_x0,
+                                                            size_t total, int cfg, float scale, CfgCoef cf) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    float e = eps[i];
+    if (cfg) {
+      const float eu = e;
+      const float ec = eps[total + i];
+      e = __fadd_rn(eu, __fmul_rn(scale, __fsub_rn(ec, eu)));
+    }
+    const float x0 = __fdiv_rn(__fsub_rn(x[i], __fmul_rn(cf.v[0], e)), cf.v[1]);
+    const float dir = __fmul_rn(cf.v[3], e);
+    x_prev[i] = __fadd_rn(__fmul_rn(cf.v[2], x0), dir);
+    if (pred_x0 != nullptr) pred_x0[i] = x0;
+  }
+}
+
+__global__ void __launch_bounds__(256) pad_context_kernel(const float* __restrict__ ctx, __nv_bfloat16* __restrict__ out,
+                                                          int n, int t, int c, int t_pad) {
+  const size_t total = (size_t)n * t_pad * c;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const size_t row = i / c;
+    const int col = (int)(i - row * c);
+    const int img = (int)(row / t_pad);
+    const int tok = (int)(row - (size_t)img * t_pad);
+    out[i] = __float2bfloat16(tok < t ? ctx[((size_t)img * t + tok) * c + col] : 0.0f);
+  }
+}
+
+unsigned grid_for(size_t work_items, int per_block) {
+  size_t blocks = (work_items + per_block - 1) / per_block;
+  const size_t cap = (size_t)num_sms() * 16;
+  if (blocks > cap) blocks = cap;
+  return blocks ? (unsigned)blocks : 1u;
+}
+
+}  // namespace
+
+int layernorm_submit(adb_plan* plan, const void* x, const float* gamma, const float* beta, void* out, int rows, int c,
+                     float eps, cudaStream_t stream) {
+  ADB_REQUIRE(x && gamma && beta && out && rows > 0, "layernorm: bad arguments");
+  ADB_REQUIRE(c > 0 && c % 8 == 0 && c <= 32 * 8 * LN_MAX_VEC, "layernorm: c = %d unsupported (multiple of 8, <= 2048)", c);
+  const int nvec = c / 8;
+  const double bytes = 4.0 * (double)rows * c;  // 2 B read + 2 B written per element
+  return submit(plan, stream, "layernorm", 0.0, bytes, [=](cudaStream_t s) -> int {
+    const unsigned grid = grid_for((size_t)rows, 8);
+    const uint4* xi = reinterpret_cast<const uint4*>(x);
+    uint4* oo = reinterpret_cast<uint4*>(out);
+    if (nvec <= 64) layernorm_kernel<2><<<grid, 256, 0, s>>>(xi, gamma, beta, oo, rows, nvec, eps);
+    else if (nvec <= 96) layernorm_kernel<3><<<grid, 256, 0, s>>>(xi, gamma, beta, oo, rows, nvec, eps);
+    else if (nvec <= 160) layernorm_kernel<5><<<grid, 256, 0, s>>>(xi, gamma, beta, oo, rows, nvec, eps);
+    else layernorm_kernel<LN_MAX_VEC><<<grid, 256, 0, s>>>(xi, gamma, beta, oo, rows, nvec, eps);
+    ADB_CUDA(cudaGetLastError());
+    return 1;
+  });
+}
+
+int geglu_submit(adb_plan* plan, const void* x, void* out, int rows, int inner, cudaStream_t stream) {
+  ADB_REQUIRE(x && out && rows > 0 && inner > 0 && inner % 8 == 0, "geglu: bad arguments");
+  const double bytes = 2.0 * 3.0 * (double)rows * inner;  // two bf16 reads + one bf16 write per output element
+  return submit(plan, stream, "geglu", 0.0, bytes, [=](cudaStream_t s) -> int {
+    const size_t total_vec = (size_t)rows * (inner / 8);
+    geglu_kernel<<<grid_for(total_vec, 256), 256, 0, s>>>(reinterpret_cast<const uint4*>(x), reinterpret_cast<uint4*>(out),
+                                                         total_vec, inner / 8);
+    ADB_CUDA(cudaGetLastError());
+    return 1;
+  });
+}
+
+int cfg_ddim_step_submit(adb_plan* plan, const float* x, const float* eps, float* x_prev, float* pred_x0, int n, int chw,
+                         int cfg, float scale, const float coef[4], cudaStream_t stream) {
+  ADB_REQUIRE(x && eps && x_prev && n > 0 && chw > 0 && coef, "cfg_ddim_step: bad arguments");
+  CfgCoef cf;
+  for (int i = 0; i < 4; ++i) cf.v[i] = coef[i];
+  const size_t total = (size_t)n * chw;
+  const double bytes = 4.0 * (double)total * (cfg ? 4.0 : 3.0);
+  return submit(plan, stream, "cfg_ddim_step", 0.0, bytes, [=](cudaStream_t s) -> int {
+    cfg_ddim_step_kernel<<<grid_for(total, 256), 256, 0, s>>>(x, eps, x_prev, pred_x0, total, cfg, scale, cf);
+    ADB_CUDA(cudaGetLastError());
+    return 1;
+  });
+}
+
+int pad_context_submit(adb_plan* plan, const float* ctx, void* out, int n, int t, int c, int t_pad, cudaStream_t stream) {
+  ADB_REQUIRE(ctx && out && n > 0 && t > 0 && c > 0 && t_pad >= t, "pad_context: bad arguments");
+  return submit(plan, stream, "pad_context", 0.0, 0.0, [=](cudaStream_t s) -> int {
+    pad_context_kernel<<<grid_for((size_t)n * t_pad * c, 256), 256, 0, s>>>(ctx, reinterpret_cast<__nv_bfloat16*>(out), n, t,
+                                                                           c, t_pad);
+    ADB_CUDA(cudaGetLastError());
+    return 1;
+  });
+}
+
+}  // namespace adb

@@ -36,6 +36,7 @@ __all__ = [
     "attention_backward", "gn_backward", "pool_prepare", "pool_attention", "pool_attention_backward", "pool_merge",
     "logsoftmax_grad", "pack_conv_weight_dgrad", "pack_linear_weight_split", "linear_tc",
     "pack_stem_weight", "stem_conv_tc",
+    "attention_sd", "layernorm", "geglu", "cfg_ddim_step", "pad_context",
 ]
 
 
@@ -156,23 +157,33 @@ def conv_igemm(
     stats_out: optional zeroed fp64 [n,32,2]; the epilogue adds the output's GroupNorm sums to it.
     stats2: optional (fp64 [n,32,2], cpg, channel offset) - sums for a consumer GroupNorm over a concat."""
     act0 = segs[0][0]
-    n, h, w = act0.shape[0], act0.shape[1], act0.shape[2]
+    s0 = segs[0][2] if len(segs[0]) > 2 else 1  # a third tuple entry is the segment's stride (1 or 2)
+    n, h, w = act0.shape[0], act0.shape[1] // s0, act0.shape[2] // s0
     d = _lib.ConvDesc()
     d.n, d.h, d.w = n, h, w
     d.cout = cout
     d.cout_pad = weight.shape[0]
     d.nseg = len(segs)
     ktot = 0
-    for i, (act, taps) in enumerate(segs):
-        assert act.shape[:3] == (n, h, w), "all K-segments share the output geometry"
+    for i, sg in enumerate(segs):
+        act, taps = sg[0], sg[1]
+        stride = sg[2] if len(sg) > 2 else 1
+        assert act.shape[:3] == (n, h * stride, w * stride), "all K-segments share the output geometry"
         d.seg[i].act = _dev(act, f"seg{i}.act", torch.bfloat16)
         d.seg[i].cin = act.shape[3]
         d.seg[i].taps = taps
+        d.seg_stride[i] = stride
         ktot += taps * act.shape[3]
     if weight.shape[1] != ktot:
         raise ValueError(f"packed weight K={weight.shape[1]} does not match segments K={ktot}")
     d.weight = _dev(weight, "weight", torch.bfloat16)
-    d.bias = _opt(bias, "bias", torch.float32)
+    if bias is not None and bias.dim() == 2:  # per-image bias rows [n, cout]; may be a column slice (row stride > cout)
+        if not bias.is_cuda or bias.dtype != torch.float32 or bias.stride(1) != 1 or bias.shape[0] != n:
+            raise ValueError("per-image bias must be a CUDA fp32 [n, cout] tensor or row-strided view of one")
+        d.bias = bias.data_ptr()
+        d.bias_stride = bias.stride(0)
+    else:
+        d.bias = _opt(bias, "bias", torch.float32)
     d.residual = _opt(residual, "residual", torch.bfloat16)
     d.res_mode = res_mode
     if out is None:
@@ -626,3 +637,83 @@ def nchw_to_nhwc_bf16(x: torch.Tensor) -> torch.Tensor:
 
 def nhwc_to_nchw_f32(x: torch.Tensor) -> torch.Tensor:
     return x.float().permute(0, 3, 1, 2).contiguous()
+
+
+# ---- Stable-Diffusion-v1 family ----
+def attention_sd(q: torch.Tensor, kv: torch.Tensor, b: int, heads: int, d_head: int, d_pad: int, tq: int, tk_rows: int,
+                 tk_valid: int, q_col0: int, k_col0: int, v_col0: int, out: Optional[torch.Tensor] = None,
+                 plan: Optional[Plan] = None) -> torch.Tensor:
+    """softmax(q k^T d_head^-0.5) v per (batch, head) with heads padded to d_pad columns (include/adb200.h).
+    q: bf16 [b*tq, q_width]; kv: bf16 [b*tk_rows, kv_width] (may be `q` itself) -> bf16 [b*tq, heads*d_pad]."""
+    q2, kv2 = q.reshape(b * tq, -1), kv.reshape(b * tk_rows, -1)
+    if out is None:
+        out = torch.empty((b * tq, heads * d_pad), dtype=torch.bfloat16, device=q.device)
+    d = _lib.AttnSdDesc()
+    d.q, d.q_width, d.q_col0 = _dev(q2, "q", torch.bfloat16), q2.shape[1], q_col0
+    d.kv, d.kv_width, d.k_col0, d.v_col0 = _dev(kv2, "kv", torch.bfloat16), kv2.shape[1], k_col0, v_col0
+    d.out = _dev(out, "out", torch.bfloat16)
+    d.b, d.heads, d.d_head, d.d_pad = b, heads, d_head, d_pad
+    d.tq, d.tk_rows, d.tk_valid = tq, tk_rows, tk_valid
+    _lib.check(_lib.lib().adb_attention_sd(_ph(plan), C.byref(d), _stream()), "adb_attention_sd")
+    if plan is not None:
+        plan.keep(q, kv, out)
+    return out
+
+
+def layernorm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: float = 1e-5,
+              out: Optional[torch.Tensor] = None, plan: Optional[Plan] = None) -> torch.Tensor:
+    """nn.LayerNorm over the last dim of a bf16 [..., c] tensor."""
+    c = x.shape[-1]
+    rows = x.numel() // c
+    if out is None:
+        out = torch.empty_like(x)
+    _lib.check(_lib.lib().adb_layernorm(_ph(plan), _dev(x, "x", torch.bfloat16), _dev(gamma, "gamma", torch.float32),
+                                        _dev(beta, "beta", torch.float32), _dev(out, "out", torch.bfloat16), rows, c,
+                                        float(eps), _stream()), "adb_layernorm")
+    if plan is not None:
+        plan.keep(x, gamma, beta, out)
+    return out
+
+
+def geglu(x: torch.Tensor, out: Optional[torch.Tensor] = None, plan: Optional[Plan] = None) -> torch.Tensor:
+    """x bf16 [..., 2*inner] -> x[..., :inner] * gelu(x[..., inner:]) (exact GELU)."""
+    inner = x.shape[-1] // 2
+    rows = x.numel() // (2 * inner)
+    if out is None:
+        out = torch.empty(x.shape[:-1] + (inner,), dtype=torch.bfloat16, device=x.device)
+    _lib.check(_lib.lib().adb_geglu(_ph(plan), _dev(x, "x", torch.bfloat16), _dev(out, "out", torch.bfloat16), rows, inner,
+                                    _stream()), "adb_geglu")
+    if plan is not None:
+        plan.keep(x, out)
+    return out
+
+
+def cfg_ddim_step(x: torch.Tensor, eps: torch.Tensor, coef: Sequence[float], scale: float = 1.0, cfg: bool = False,
+                  x_prev: Optional[torch.Tensor] = None, pred_x0: Optional[torch.Tensor] = None,
+                  plan: Optional[Plan] = None) -> torch.Tensor:
+    """p_sample_ddim with eta = 0 and optional classifier-free guidance (ddim.py:184-216); eps is [2n, ...] with the
+    unconditional half first when cfg. coef = (sqrt(1-a_t), sqrt(a_t), sqrt(a_prev), sqrt(1-a_prev)) as fp32 values."""
+    n = x.shape[0]
+    chw = x.numel() // n
+    assert eps.numel() == (2 if cfg else 1) * x.numel()
+    if x_prev is None:
+        x_prev = torch.empty_like(x)
+    cf = (C.c_float * 4)(*[float(v) for v in coef])
+    _lib.check(_lib.lib().adb_cfg_ddim_step(_ph(plan), _dev(x, "x", torch.float32), _dev(eps, "eps", torch.float32),
+                                            _dev(x_prev, "x_prev", torch.float32), _opt(pred_x0, "pred_x0", torch.float32),
+                                            n, chw, int(bool(cfg)), float(scale), cf, _stream()), "adb_cfg_ddim_step")
+    if plan is not None:
+        plan.keep(x, eps, x_prev, pred_x0)
+    return x_prev
+
+
+def pad_context(ctx: torch.Tensor, t_pad: int, out: Optional[torch.Tensor] = None, plan: Optional[Plan] = None) -> torch.Tensor:
+    """fp32 [n, t, c] -> bf16 [n, t_pad, c], rows t.. zero."""
+    n, t, c = ctx.shape
+    if out is None:
+        out = torch.empty((n, t_pad, c), dtype=torch.bfloat16, device=ctx.device)
+    _lib.check(_lib.lib().adb_pad_context(_ph(plan), _dev(ctx, "ctx", torch.float32), _dev(out, "out", torch.bfloat16), n, t, c,
+                                          t_pad, _stream()), "adb_pad_context")
+    if plan is not None:
+        plan.keep(ctx, out)
+    return out

@@ -1,0 +1,224 @@
+"""Searched-timestep DDIM sampling with classifier-free guidance for the Stable-Diffusion family.
+
+Drop-in for `ldm.models.diffusion.ddim.DDIMSampler` as the search calls it (reference:
+/root/reference/examples/"Stable Diffusion"/ldm/models/diffusion/ddim.py:13-217 and scripts/search_ea.py:504-538):
+`DDIMSampler(model).sample(S, batch_size, shape, conditioning, eta=0, x_T, unconditional_guidance_scale,
+unconditional_conditioning, sampled_timestep)` -> (samples, intermediates). `model` is anything with the attributes
+the reference sampler reads from LatentDiffusion (num_timesteps, betas, alphas_cumprod, alphas_cumprod_prev, device,
+apply_model); `LatentDiffusionUNet` below provides them around `sd_unet.UNetModel` with the v1 schedule.
+
+When the model is ours, a whole candidate - context K/V projections once, then per searched step one batched
+[uncond | cond] UNet forward and the fused CFG + DDIM update - is recorded into one launch plan and captured in
+one CUDA graph (`CandidatePlan`); any other `apply_model` goes through the generic loop with the same fused update.
+"""
+from __future__ import annotations
+
+import os
+from typing import Dict, List, Optional, Sequence
+
+import numpy as np
+import torch as th
+
+from . import ops
+from .sd_unet import CTX_ROWS, UNetModel
+
+
+def make_beta_schedule(schedule, n_timestep, linear_start=1e-4, linear_end=2e-2, cosine_s=8e-3):
+    """ldm/modules/diffusionmodules/util.py:21-43 ("linear" is what v1-inference*.yaml uses)."""
+    if schedule != "linear":
+        raise NotImplementedError(f"schedule '{schedule}' is not used by the Stable-Diffusion search")
+    betas = th.linspace(linear_start ** 0.5, linear_end ** 0.5, n_timestep, dtype=th.float64) ** 2
+    return betas.numpy()
+
+
+def ddim_tables(alphas_cumprod: th.Tensor, ddim_timesteps: Sequence[int]):
+    """make_ddim_sampling_parameters (util.py:63-75) at eta = 0, as fp32 tensors:
+    alphas = acp[steps], alphas_prev = [acp[0]] + acp[steps[:-1]], sqrt(1 - alphas)."""
+    steps = [int(t) for t in ddim_timesteps]
+    acp = alphas_cumprod.detach().float().cpu()
+    alphas = acp[steps]
+    alphas_prev = th.tensor([acp[0].item()] + acp[steps[:-1]].tolist(), dtype=th.float32)
+    return alphas, alphas_prev, th.sqrt(1.0 - alphas)
+
+
+def ddim_coefficients(alphas, alphas_prev, sqrt_one_minus_alphas, index: int):
+    """The four fp32 scalars p_sample_ddim broadcasts at `index` (ddim.py:199-213, sigma_t = 0):
+    sqrt(1 - a_t), sqrt(a_t), sqrt(a_prev), sqrt(1 - a_prev) - each rounded to fp32 like the reference's tensor ops."""
+    a_t = np.float32(alphas[index])
+    a_prev = np.float32(alphas_prev[index])
+    return (float(np.float32(sqrt_one_minus_alphas[index])), float(np.sqrt(a_t)), float(np.sqrt(a_prev)),
+            float(np.sqrt(np.float32(1.0) - a_prev)))
+
+
+class LatentDiffusionUNet:
+    """What DDIMSampler needs from LatentDiffusion (ldm/models/diffusion/ddpm.py:117-134 register_schedule;
+    apply_model -> DiffusionWrapper 'crossattn' -> unet(x, t, context=c), ddpm.py:1410-1417) around our UNet.
+    The text encoder and the VAE are outside the searched path (scripts/search_ea.py:519-525,539)."""
+
+    def __init__(self, unet: UNetModel, timesteps: int = 1000, linear_start: float = 0.00085, linear_end: float = 0.0120):
+        self.unet = unet
+        betas = make_beta_schedule("linear", timesteps, linear_start, linear_end)
+        acp = np.cumprod(1.0 - betas, axis=0)
+        self.num_timesteps = int(timesteps)
+        self.parameterization = "eps"
+        dev = unet._device()
+        self.betas = th.tensor(betas, dtype=th.float32, device=dev)
+        self.alphas_cumprod = th.tensor(acp, dtype=th.float32, device=dev)
+        self.alphas_cumprod_prev = th.tensor(np.append(1.0, acp[:-1]), dtype=th.float32, device=dev)
+
+    @property
+    def device(self):
+        return self.unet._device()
+
+    def apply_model(self, x_noisy, t, cond):
+        if isinstance(cond, dict):
+            cond = th.cat(cond["c_crossattn"], 1)
+        return self.unet(x_noisy, t, context=cond)
+
+
+class CandidatePlan:
+    """One searched candidate (sorted timesteps) as ONE recorded schedule / CUDA graph at a fixed batch:
+    pad + project the contexts once, then for every step (descending): t, [x | x] -> eps_uncond, eps_cond -> fused
+    CFG + DDIM update written back into both halves of the UNet's input buffer."""
+
+    def __init__(self, unet: UNetModel, alphas_cumprod: th.Tensor, sampled_timestep: Sequence[int], batch: int, shape,
+                 scale: float, cfg: bool, ctx_tokens: int = 77, use_graph: Optional[bool] = None):
+        dev = unet._device()
+        if dev.type != "cuda":
+            raise RuntimeError("CandidatePlan needs the model on a CUDA device (no CPU path)")
+        C, H, W = shape
+        self.unet, self.B, self.cfg, self.scale = unet, batch, bool(cfg), float(scale)
+        self.steps = sorted(int(t) for t in sampled_timestep)  # ddim.py:93-94
+        self.alphas, self.alphas_prev, self.s1m = ddim_tables(alphas_cumprod, self.steps)
+        n = batch * (2 if cfg else 1)
+        self.x2 = th.zeros((n, C, H, W), dtype=th.float32, device=dev)
+        self.t_in = th.zeros((n,), dtype=th.int64, device=dev)
+        self.ctx = th.zeros((n, ctx_tokens, unet.context_dim), dtype=th.float32, device=dev)  # [uncond | cond]
+        self.eps = th.empty((n, unet.out_channels, H, W), dtype=th.float32, device=dev)
+        self.x = self.x2[:batch]
+        self.plan_ctx = ops.Plan()
+        cpad = ops.pad_context(self.ctx, CTX_ROWS, plan=self.plan_ctx)
+        kvs = unet.record_context(self.plan_ctx, cpad)
+        self.plan_fwd = ops.Plan()  # one forward; every step replays it (t_in / x2 are updated in between)
+        unet.record_forward(self.plan_fwd, self.x2, self.t_in, kvs, self.eps, ctx_tokens=ctx_tokens)
+        self.coefs = [ddim_coefficients(self.alphas, self.alphas_prev, self.s1m, i) for i in range(len(self.steps))]
+        with th.no_grad():
+            self.launches = self.plan_ctx.run()
+            per_fwd = self.plan_fwd.run()
+        self.launches += len(self.steps) * (per_fwd + 1)
+        self.launches_per_forward = per_fwd
+        if use_graph is None:
+            use_graph = os.environ.get("ADB_NO_GRAPH", "0") != "1"
+        self.graph: Optional[th.cuda.CUDAGraph] = None
+        if use_graph:
+            th.cuda.current_stream().synchronize()
+            g = th.cuda.CUDAGraph()
+            with th.cuda.graph(g):
+                self._chain()
+            self.graph = g
+
+    def _chain(self):
+        self.plan_ctx.run()
+        for i, step in enumerate(reversed(self.steps)):
+            index = len(self.steps) - i - 1
+            self.t_in.fill_(step)
+            self.plan_fwd.run()
+            ops.cfg_ddim_step(self.x, self.eps, self.coefs[index], scale=self.scale, cfg=self.cfg, x_prev=self.x)
+            if self.cfg:
+                self.x2[self.B:].copy_(self.x)
+
+    @th.no_grad()
+    def run(self, x_T: th.Tensor, cond: th.Tensor, uncond: Optional[th.Tensor]) -> th.Tensor:
+        """-> x_0 latents (a view of the plan's buffer; clone to keep)."""
+        self.x.copy_(x_T, non_blocking=True)
+        if self.cfg:
+            self.x2[self.B:].copy_(x_T, non_blocking=True)
+            self.ctx[:self.B].copy_(uncond, non_blocking=True)
+            self.ctx[self.B:].copy_(cond, non_blocking=True)
+        else:
+            self.ctx.copy_(cond, non_blocking=True)
+        self.unet.gpu_launches += self.launches
+        if self.graph is not None:
+            self.graph.replay()
+        else:
+            self._chain()
+        return self.x
+
+
+class DDIMSampler(object):
+    """ddim.py:13-217 restricted to what the search calls: eta = 0, no mask / x0 / score corrector / quantisation."""
+
+    def __init__(self, model, schedule="linear", **kwargs):
+        self.model = model
+        self.ddpm_num_timesteps = model.num_timesteps
+        self.schedule = schedule
+        self._plans: Dict[tuple, CandidatePlan] = {}
+
+    def make_schedule(self, ddim_num_steps, ddim_discretize="uniform", ddim_eta=0.0, verbose=True, sampled_timestep=None):
+        if ddim_eta != 0.0:
+            raise NotImplementedError("eta != 0 is not used by the search (scripts/search_ea.py: ddim_eta default 0.0)")
+        if sampled_timestep is None:  # make_ddim_timesteps, util.py:46-61
+            if ddim_discretize != "uniform":
+                raise NotImplementedError(ddim_discretize)
+            c = round(self.ddpm_num_timesteps / ddim_num_steps)
+            self.ddim_timesteps = np.asarray(list(range(0, self.ddpm_num_timesteps, c))) + 1
+        else:
+            self.ddim_timesteps = sampled_timestep
+        acp = self.model.alphas_cumprod
+        assert acp.shape[0] == self.ddpm_num_timesteps, "alphas have to be defined for each timestep"
+        self.ddim_alphas, self.ddim_alphas_prev, self.ddim_sqrt_one_minus_alphas = ddim_tables(acp, list(self.ddim_timesteps))
+        self.ddim_sigmas = th.zeros_like(self.ddim_alphas)
+
+    @th.no_grad()
+    def sample(self, S, batch_size, shape, conditioning=None, callback=None, normals_sequence=None, img_callback=None,
+               quantize_x0=False, eta=0.0, mask=None, x0=None, temperature=1.0, noise_dropout=0.0, score_corrector=None,
+               corrector_kwargs=None, verbose=True, x_T=None, log_every_t=100, unconditional_guidance_scale=1.0,
+               unconditional_conditioning=None, sampled_timestep=None, **kwargs):
+        if mask is not None or x0 is not None or score_corrector is not None or quantize_x0 or noise_dropout > 0.0:
+            raise NotImplementedError("inpainting / score correction / quantisation are not on the searched path")
+        if conditioning is not None and not isinstance(conditioning, dict) and conditioning.shape[0] != batch_size:
+            print(f"Warning: Got {conditioning.shape[0]} conditionings but batch-size is {batch_size}")
+        if sampled_timestep is not None:
+            sampled_timestep = sorted(int(t) for t in sampled_timestep)
+        self.make_schedule(ddim_num_steps=S, ddim_eta=eta, verbose=verbose, sampled_timestep=sampled_timestep)
+        C, H, W = shape
+        dev = self.model.device
+        img = th.randn((batch_size, C, H, W), device=dev) if x_T is None else x_T
+        cfg = not (unconditional_conditioning is None or unconditional_guidance_scale == 1.0)  # ddim.py:184
+        unet = getattr(self.model, "unet", None)
+        intermediates = {"x_inter": [img], "pred_x0": [img]}
+        if isinstance(unet, UNetModel) and not isinstance(conditioning, dict) and callback is None and img_callback is None:
+            steps = [int(t) for t in self.ddim_timesteps]
+            key = (tuple(steps), batch_size, C, H, W, float(unconditional_guidance_scale), cfg, conditioning.shape[1])
+            plan = self._plans.get(key)
+            if plan is None:
+                if len(self._plans) >= 4:
+                    self._plans.pop(next(iter(self._plans)))
+                plan = CandidatePlan(unet, self.model.alphas_cumprod, steps, batch_size, (C, H, W),
+                                     unconditional_guidance_scale, cfg, ctx_tokens=conditioning.shape[1])
+                self._plans[key] = plan
+            out = plan.run(img, conditioning, unconditional_conditioning).clone()
+            return out, intermediates
+        # generic apply_model: the reference's loop (ddim.py:143-172) with the fused update
+        steps = np.asarray(self.ddim_timesteps)
+        total = steps.shape[0]
+        for i, step in enumerate(np.flip(steps)):
+            index = total - i - 1
+            ts = th.full((batch_size,), int(step), device=dev, dtype=th.long)
+            if cfg:
+                eps = self.model.apply_model(th.cat([img] * 2), th.cat([ts] * 2),
+                                             th.cat([unconditional_conditioning, conditioning]))
+            else:
+                eps = self.model.apply_model(img, ts, conditioning)
+            pred = th.empty_like(img)
+            img = ops.cfg_ddim_step(img.contiguous(), eps.float().contiguous(),
+                                    ddim_coefficients(self.ddim_alphas, self.ddim_alphas_prev, self.ddim_sqrt_one_minus_alphas, index),
+                                    scale=unconditional_guidance_scale, cfg=cfg, pred_x0=pred)
+            if callback:
+                callback(i)
+            if img_callback:
+                img_callback(pred, i)
+            if index % log_every_t == 0 or index == total - 1:
+                intermediates["x_inter"].append(img)
+                intermediates["pred_x0"].append(pred)
+        return img, intermediates

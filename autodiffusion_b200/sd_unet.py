@@ -1,0 +1,558 @@
+"""Stable-Diffusion-v1 UNet (ResBlocks + SpatialTransformer blocks with text cross-attention) on the sm_100a kernels.
+
+Drop-in for `ldm.modules.diffusionmodules.openaimodel.UNetModel` as `configs/stable-diffusion/v1-inference_coco.yaml:
+29-44` builds it (reference: /root/reference/examples/"Stable Diffusion"/ldm/modules/diffusionmodules/openaimodel.py:
+413-742 and ldm/modules/attention.py:152-260): same constructor arguments, same `state_dict()` keys and shapes
+(reference checkpoints load), `forward(x, timesteps, context)` with fp32 NCHW in / out. Inside, one forward is a
+recorded launch plan over bf16 NHWC activations (see dynamic_unet.py for the ADM twin):
+
+  * every conv / Linear of the torso is `conv_igemm` (tcgen05 implicit GEMM): 3x3, 1x1, the stride-2 Downsample.op
+    through a 5-D TMA view, the ResBlock's 1x1 skip folded into its second conv as extra K-segments over the
+    never-materialised concat, residual adds in the epilogue;
+  * `h = h + emb_out[..., None, None]` (openaimodel.py:272) is the first conv's per-image bias: all 22 `emb_layers`
+    Linears run as one fp32-grade tensor-core product whose bias already contains the conv biases;
+  * GroupNorm sums come from the producing conv's epilogue where the consumer reads a single tensor;
+  * attention heads (dim 40 / 80 / 160) are laid out in 64-column chunks by zero-padding the projection weights,
+    so one kernel (`csrc/attention_sd.cu`) serves every head size; q, k, v of the self-attention are one GEMM;
+  * the context's K / V projections do not depend on x_t or t: `record_context` computes them once per batch of
+    prompts and all sampled steps reuse them (the reference recomputes them every step, attention.py:176-177).
+
+No CPU or PyTorch fallback: tensors must be on a CUDA device.
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import torch as th
+import torch.nn as nn
+
+from . import ops
+from .dynamic_unet import _Ctx, _Pool
+
+CTX_ROWS = 128  # the 77 context tokens live in a 128-row zero-padded buffer (one GEMM tile per prompt)
+
+
+@dataclass
+class _Blk:
+    kind: str  # conv_in | res | st | down | up
+    name: str
+    cin: int = 0
+    cout: int = 0
+    heads: int = 0
+    d_head: int = 0
+
+
+def _pad64(d: int) -> int:
+    return (d + 63) // 64 * 64
+
+
+class _Node(nn.Module):
+    """Bare container so parameters get the reference's dotted names."""
+
+
+def _set_param(root: nn.Module, name: str, value: th.Tensor):
+    parts = name.split(".")
+    m = root
+    for p in parts[:-1]:
+        if not hasattr(m, p):
+            m.add_module(p, _Node())
+        m = getattr(m, p)
+    m.register_parameter(parts[-1], nn.Parameter(value))
+
+
+class UNetModel(nn.Module):
+    """Constructor signature = openaimodel.py:443-470. Supported: the spatial-transformer configuration the
+    Stable-Diffusion search uses (use_spatial_transformer=True, context_dim set, num_classes=None,
+    resblock_updown=False, use_scale_shift_norm=False, conv_resample=True, num_head_channels=-1)."""
+
+    def __init__(self, image_size, in_channels, model_channels, out_channels, num_res_blocks, attention_resolutions,
+                 dropout=0, channel_mult=(1, 2, 4, 8), conv_resample=True, dims=2, num_classes=None, use_checkpoint=False,
+                 use_fp16=False, num_heads=-1, num_head_channels=-1, num_heads_upsample=-1, use_scale_shift_norm=False,
+                 resblock_updown=False, use_new_attention_order=False, use_spatial_transformer=False, transformer_depth=1,
+                 context_dim=None, n_embed=None, legacy=True):
+        super().__init__()
+        if use_spatial_transformer:
+            assert context_dim is not None, "Fool!! You forgot to include the dimension of your cross-attention conditioning..."
+        if context_dim is not None:
+            assert use_spatial_transformer, "Fool!! You forgot to use the spatial transformer for your cross-attention conditioning..."
+            context_dim = int(context_dim) if not isinstance(context_dim, (list, tuple)) else list(context_dim)
+        if not use_spatial_transformer or isinstance(context_dim, list):
+            raise NotImplementedError("only the SpatialTransformer (text-conditioned) configuration is on the evaluator path")
+        if dims != 2 or num_classes is not None or resblock_updown or use_scale_shift_norm or not conv_resample \
+                or n_embed is not None or num_head_channels != -1:
+            raise NotImplementedError("configuration not used by the Stable-Diffusion search (v1-inference_coco.yaml:29-44)")
+        if num_heads == -1:
+            raise AssertionError("Either num_heads or num_head_channels has to be set")
+        self.image_size = image_size
+        self.in_channels = in_channels
+        self.model_channels = model_channels
+        self.out_channels = out_channels
+        self.num_res_blocks = num_res_blocks
+        self.attention_resolutions = tuple(attention_resolutions)
+        self.dropout = dropout
+        self.channel_mult = tuple(channel_mult)
+        self.num_classes = None
+        self.num_heads = num_heads
+        self.transformer_depth = transformer_depth
+        self.context_dim = context_dim
+        self.dtype = th.float16 if use_fp16 else th.float32
+
+        mc = model_channels
+        inp: List[List[_Blk]] = [[_Blk("conv_in", "input_blocks.0.0", in_channels, mc)]]
+        chans = [mc]
+        ch, ds = mc, 1
+        for level, mult in enumerate(self.channel_mult):
+            for _ in range(num_res_blocks):
+                n = len(inp)
+                layers = [_Blk("res", f"input_blocks.{n}.0", ch, mult * mc)]
+                ch = mult * mc
+                if ds in self.attention_resolutions:
+                    layers.append(_Blk("st", f"input_blocks.{n}.1", ch, ch, num_heads, ch // num_heads))
+                inp.append(layers)
+                chans.append(ch)
+            if level != len(self.channel_mult) - 1:
+                inp.append([_Blk("down", f"input_blocks.{len(inp)}.0", ch, ch)])
+                chans.append(ch)
+                ds *= 2
+        middle = [_Blk("res", "middle_block.0", ch, ch), _Blk("st", "middle_block.1", ch, ch, num_heads, ch // num_heads),
+                  _Blk("res", "middle_block.2", ch, ch)]
+        out: List[List[_Blk]] = []
+        stack = list(chans)
+        for level, mult in list(enumerate(self.channel_mult))[::-1]:
+            for i in range(num_res_blocks + 1):
+                ich = stack.pop()
+                n = len(out)
+                layers = [_Blk("res", f"output_blocks.{n}.0", ch + ich, mc * mult)]
+                ch = mc * mult
+                if ds in self.attention_resolutions:
+                    layers.append(_Blk("st", f"output_blocks.{n}.{len(layers)}", ch, ch, num_heads, ch // num_heads))
+                if level and i == num_res_blocks:
+                    layers.append(_Blk("up", f"output_blocks.{n}.{len(layers)}", ch, ch))
+                    ds //= 2
+                out.append(layers)
+        self._arch = (inp, middle, out)
+        self._final_ch = ch
+        self._levels = len(self.channel_mult) - 1
+        self._make_parameters()
+
+        self._generation = 0
+        self._packed_generation = -1
+        self._packed: Dict[str, object] = {}
+        self._plans: Dict[tuple, object] = {}
+        self._pool: Optional[_Pool] = None
+        self.gpu_launches = 0
+
+    # ---- parameters under the reference's names ----
+    def _blocks(self):
+        inp, middle, out = self._arch
+        for layers in inp:
+            yield from layers
+        yield from middle
+        for layers in out:
+            yield from layers
+
+    def _make_parameters(self):
+        g = th.Generator().manual_seed(0)
+        ted, cd = self.model_channels * 4, self.context_dim
+
+        def w(name, *shape, zero=False):
+            fan_in = 1
+            for d in shape[1:]:
+                fan_in *= d
+            bound = 1.0 / math.sqrt(fan_in)
+            t = th.zeros(shape) if zero else (th.rand(shape, generator=g) * 2 - 1) * bound
+            _set_param(self, name, t)
+
+        def lin(name, i, o, bias=True, zero=False):
+            w(name + ".weight", o, i, zero=zero)
+            if bias:
+                w(name + ".bias", o, zero=True)
+
+        def conv(name, i, o, k, zero=False):
+            w(name + ".weight", o, i, k, k, zero=zero)
+            w(name + ".bias", o, zero=True)
+
+        def norm(name, c):
+            _set_param(self, name + ".weight", th.ones(c))
+            _set_param(self, name + ".bias", th.zeros(c))
+
+        lin("time_embed.0", self.model_channels, ted)
+        lin("time_embed.2", ted, ted)
+        for b in self._blocks():
+            if b.kind == "conv_in":
+                conv(b.name, b.cin, b.cout, 3)
+            elif b.kind == "res":
+                norm(b.name + ".in_layers.0", b.cin)
+                conv(b.name + ".in_layers.2", b.cin, b.cout, 3)
+                lin(b.name + ".emb_layers.1", ted, b.cout)
+                norm(b.name + ".out_layers.0", b.cout)
+                conv(b.name + ".out_layers.3", b.cout, b.cout, 3, zero=True)  # zero_module, openaimodel.py:227-229
+                if b.cin != b.cout:
+                    conv(b.name + ".skip_connection", b.cin, b.cout, 1)
+            elif b.kind == "st":
+                inner = b.heads * b.d_head
+                norm(b.name + ".norm", b.cin)
+                conv(b.name + ".proj_in", b.cin, inner, 1)
+                for d in range(self.transformer_depth):
+                    t = f"{b.name}.transformer_blocks.{d}"
+                    for a, kdim in (("attn1", inner), ("attn2", cd)):
+                        lin(f"{t}.{a}.to_q", inner, inner, bias=False)
+                        lin(f"{t}.{a}.to_k", kdim, inner, bias=False)
+                        lin(f"{t}.{a}.to_v", kdim, inner, bias=False)
+                        lin(f"{t}.{a}.to_out.0", inner, inner)
+                    lin(f"{t}.ff.net.0.proj", inner, inner * 8)
+                    lin(f"{t}.ff.net.2", inner * 4, inner)
+                    for k in ("norm1", "norm2", "norm3"):
+                        norm(f"{t}.{k}", inner)
+                conv(b.name + ".proj_out", inner, b.cin, 1, zero=True)  # zero_module, attention.py:239-243
+            elif b.kind == "down":
+                conv(b.name + ".op", b.cin, b.cout, 3)
+            elif b.kind == "up":
+                conv(b.name + ".conv", b.cin, b.cout, 3)
+        norm("out.0", self._final_ch)
+        conv("out.2", self.model_channels, self.out_channels, 3, zero=True)
+
+    # ---- API parity helpers ----
+    def convert_to_fp16(self):
+        """openaimodel.py:692-699 casts the torso to fp16; here masters stay fp32, tensor-core operands are bf16."""
+        self.dtype = th.float16
+
+    def convert_to_fp32(self):
+        self.dtype = th.float32
+
+    def _apply(self, fn, *args, **kwargs):
+        r = super()._apply(fn, *args, **kwargs)
+        self._invalidate()
+        return r
+
+    def load_state_dict(self, *args, **kwargs):
+        r = super().load_state_dict(*args, **kwargs)
+        self._invalidate()
+        return r
+
+    def refresh_weights(self):
+        self._invalidate()
+
+    def _invalidate(self):
+        if hasattr(self, "_generation"):
+            self._generation += 1
+
+    def _device(self):
+        return self.get_parameter("out.0.weight").device
+
+    # ---- weight packing ----
+    def _pack(self):
+        dev = self._device()
+        sd = {k: v.detach() for k, v in self.named_parameters()}
+        f32 = lambda t: t.to(device=dev, dtype=th.float32).contiguous()
+        lin_w = lambda t: ops.pack_conv_weight([t[:, :, None, None]], dev)
+        P: Dict[str, object] = {}
+        emb_w, emb_b, off = [], [], 0
+        for b in self._blocks():
+            n = b.name
+            if b.kind == "conv_in":
+                P["stem_w"], P["stem_b"] = f32(sd[n + ".weight"]), f32(sd[n + ".bias"])
+            elif b.kind == "res":
+                q = {"w1": ops.pack_conv_weight([sd[n + ".in_layers.2.weight"]], dev), "emb_off": off,
+                     "g1": f32(sd[n + ".in_layers.0.weight"]), "be1": f32(sd[n + ".in_layers.0.bias"]),
+                     "g2": f32(sd[n + ".out_layers.0.weight"]), "be2": f32(sd[n + ".out_layers.0.bias"]),
+                     "w2_raw": sd[n + ".out_layers.3.weight"], "ws_raw": None}
+                b2 = sd[n + ".out_layers.3.bias"].float()
+                if b.cin != b.cout:
+                    q["ws_raw"] = sd[n + ".skip_connection.weight"]
+                    b2 = b2 + sd[n + ".skip_connection.bias"].float()
+                q["b2"] = f32(b2)
+                # conv bias folded into the embedding Linear's bias: conv(x) + b_conv + emb_out == conv(x) + (emb_out + b_conv)
+                emb_w.append(sd[n + ".emb_layers.1.weight"].float())
+                emb_b.append(sd[n + ".emb_layers.1.bias"].float() + sd[n + ".in_layers.2.bias"].float())
+                off += b.cout
+                P[n] = q
+            elif b.kind == "st":
+                H, d = b.heads, b.d_head
+                dp = _pad64(d)
+                inner = H * d
+
+                def rows(wt):  # [H*d, in] -> [H*dp, in], zero rows in every head's padding
+                    o = wt.new_zeros(H, dp, wt.shape[1])
+                    o[:, :d] = wt.reshape(H, d, -1)
+                    return o.reshape(H * dp, -1)
+
+                def cols(wt):  # [out, H*d] -> [out, H*dp]
+                    o = wt.new_zeros(wt.shape[0], H, dp)
+                    o[:, :, :d] = wt.reshape(wt.shape[0], H, d)
+                    return o.reshape(wt.shape[0], H * dp)
+
+                q = {"g": f32(sd[n + ".norm.weight"]), "be": f32(sd[n + ".norm.bias"]),
+                     "w_in": ops.pack_conv_weight([sd[n + ".proj_in.weight"]], dev), "b_in": f32(sd[n + ".proj_in.bias"]),
+                     "w_out": ops.pack_conv_weight([sd[n + ".proj_out.weight"]], dev), "b_out": f32(sd[n + ".proj_out.bias"]),
+                     "dp": dp, "blocks": []}
+                for k in range(self.transformer_depth):
+                    t = f"{n}.transformer_blocks.{k}"
+                    a1, a2 = t + ".attn1", t + ".attn2"
+                    q["blocks"].append({
+                        "ln": [(f32(sd[f"{t}.norm{i}.weight"]), f32(sd[f"{t}.norm{i}.bias"])) for i in (1, 2, 3)],
+                        "wqkv": lin_w(th.cat([rows(sd[a1 + ".to_q.weight"].float()), rows(sd[a1 + ".to_k.weight"].float()),
+                                              rows(sd[a1 + ".to_v.weight"].float())], 0)),
+                        "wo1": lin_w(cols(sd[a1 + ".to_out.0.weight"].float())), "bo1": f32(sd[a1 + ".to_out.0.bias"]),
+                        "wq2": lin_w(rows(sd[a2 + ".to_q.weight"].float())),
+                        "wkv2": lin_w(th.cat([rows(sd[a2 + ".to_k.weight"].float()), rows(sd[a2 + ".to_v.weight"].float())], 0)),
+                        "wo2": lin_w(cols(sd[a2 + ".to_out.0.weight"].float())), "bo2": f32(sd[a2 + ".to_out.0.bias"]),
+                        "wff1": lin_w(sd[t + ".ff.net.0.proj.weight"].float()), "bff1": f32(sd[t + ".ff.net.0.proj.bias"]),
+                        "wff2": lin_w(sd[t + ".ff.net.2.weight"].float()), "bff2": f32(sd[t + ".ff.net.2.bias"]),
+                    })
+                P[n] = q
+            elif b.kind == "down":
+                P[n] = {"w": ops.pack_conv_weight([sd[n + ".op.weight"]], dev), "b": f32(sd[n + ".op.bias"])}
+            elif b.kind == "up":
+                P[n] = {"w": ops.pack_conv_weight([sd[n + ".conv.weight"]], dev), "b": f32(sd[n + ".conv.bias"])}
+        P["emb_w"] = ops.pack_linear_weight_split(th.cat(emb_w, 0), dev)
+        P["emb_b"] = th.cat(emb_b, 0).to(dev).contiguous()
+        P["emb_total"] = off
+        for k in ("time_embed.0", "time_embed.2"):
+            P[k + ".w"], P[k + ".b"] = f32(sd[k + ".weight"]), f32(sd[k + ".bias"])
+        P["out_g"], P["out_be"] = f32(sd["out.0.weight"]), f32(sd["out.0.bias"])
+        P["out_w"], P["out_b"] = ops.pack_conv_weight([sd["out.2.weight"]], dev), f32(sd["out.2.bias"])
+        P["w2_cache"] = {}
+        self._packed = P
+        self._packed_generation = self._generation
+        self._plans.clear()
+
+    def _w2_for(self, b: _Blk, split: Tuple[int, ...]) -> th.Tensor:
+        """Second conv of a ResBlock with the 1x1 skip appended along K, split at the concat boundary."""
+        q = self._packed[b.name]
+        cache = self._packed["w2_cache"]
+        key = (b.name, split)
+        if key not in cache:
+            mats = [q["w2_raw"]]
+            if q["ws_raw"] is not None:
+                o = 0
+                for c in split:
+                    mats.append(q["ws_raw"][:, o:o + c])
+                    o += c
+                assert o == q["ws_raw"].shape[1]
+            cache[key] = ops.pack_conv_weight(mats, self._device())
+        return cache[key]
+
+    def _ready(self):
+        if self._device().type != "cuda":
+            raise RuntimeError("UNetModel runs on a CUDA device only: move it with .to('cuda') (autodiffusion_b200 has no CPU path)")
+        if self._packed_generation != self._generation:
+            self._pack()
+        if self._pool is None or self._pool.device != self._device():
+            self._pool = _Pool(self._device())
+
+    def st_blocks(self) -> List[_Blk]:
+        return [b for b in self._blocks() if b.kind == "st"]
+
+    # ---- recording ----
+    def record_context(self, plan: ops.Plan, ctx_pad: th.Tensor) -> Dict[str, List[th.Tensor]]:
+        """K / V projections of the (padded, bf16) context for every cross-attention layer:
+        ctx_pad [n, 128, context_dim] -> {block name: [kv per transformer depth]}, kv = bf16 [n*128, 2*heads*d_pad].
+        Independent of x_t and t (attention.py:176-177): computed once per batch of prompts."""
+        self._ready()
+        n = ctx_pad.shape[0]
+        assert ctx_pad.shape[1] == CTX_ROWS and ctx_pad.shape[2] == self.context_dim
+        cv = ctx_pad.view(n, 8, CTX_ROWS // 8, self.context_dim)
+        out: Dict[str, List[th.Tensor]] = {}
+        for b in self.st_blocks():
+            q = self._packed[b.name]
+            width = 2 * b.heads * q["dp"]
+            out[b.name] = [ops.conv_igemm([(cv, 1)], blk["wkv2"], None, width, plan=plan).view(n * CTX_ROWS, width)
+                           for blk in q["blocks"]]
+        return out
+
+    def record_forward(self, plan: ops.Plan, x_in: th.Tensor, t_in: th.Tensor, kvs: Dict[str, List[th.Tensor]],
+                       out: th.Tensor, ctx_tokens: int = 77):
+        """Record one forward: x_in fp32 [n, in_channels, H, W], t_in int64 [n], kvs from `record_context` for the
+        same n -> out fp32 [n, out_channels, H, W] (openaimodel.py:710-742)."""
+        self._ready()
+        P = self._packed
+        B, _, H, W = x_in.shape
+        dev = self._device()
+        ctx = _Ctx(self._pool, plan)
+        mc = self.model_channels
+        scratch = th.empty((B, 32, 2), dtype=th.float64, device=dev)
+        n_slots = 6 * sum(1 for _ in self._blocks()) + 8
+        arena = th.empty((n_slots, B, 32, 2), dtype=th.float64, device=dev)
+        plan.keep(scratch, arena, x_in, t_in, out)
+        ops.memset0(arena, plan=plan)
+        slot = [0]
+        produced: Dict[int, th.Tensor] = {}
+        ctx.on_alloc = lambda t: produced.pop(t.data_ptr(), None)
+
+        def new_stats(t: th.Tensor):
+            if t.shape[3] % 32 != 0 or (t.shape[1] * t.shape[2]) % 32 != 0:
+                return {}
+            st = arena[slot[0]]
+            slot[0] += 1
+            produced[t.data_ptr()] = st
+            return {"stats_out": st}
+
+        def gn(srcs, gamma, beta, out_t, eps, silu):
+            st = produced.get(srcs[0].data_ptr()) if len(srcs) == 1 else None
+            ops.groupnorm(srcs[0], gamma, beta, src1=srcs[1] if len(srcs) > 1 else None, out=out_t, eps=eps, silu=silu,
+                          stats=st if st is not None else scratch, stats_ready=st is not None, plan=plan)
+
+        te = ops.timestep_embedding(t_in, mc, plan=plan)
+        e1 = ops.linear(te, P["time_embed.0.w"], P["time_embed.0.b"], plan=plan)
+        emb = ops.linear(e1, P["time_embed.2.w"], P["time_embed.2.b"], silu_in=True, plan=plan)
+        emb_all = ops.linear_tc(emb, P["emb_w"], P["emb_b"], P["emb_total"], silu_in=True, plan=plan)  # [B, sum cout]
+
+        def run_res(b: _Blk, srcs: List[th.Tensor]) -> th.Tensor:
+            q = P[b.name]
+            n, h, w = srcs[0].shape[:3]
+            g1 = ctx.alloc((n, h, w, b.cin))
+            gn(srcs, q["g1"], q["be1"], g1, 1e-5, True)
+            c1 = ctx.alloc((n, h, w, b.cout))
+            ops.conv_igemm([(g1, 9)], q["w1"], emb_all[:, q["emb_off"]:q["emb_off"] + b.cout], b.cout, out=c1, plan=plan,
+                           **new_stats(c1))
+            ctx.release(g1)
+            g2 = ctx.alloc((n, h, w, b.cout))
+            gn([c1], q["g2"], q["be2"], g2, 1e-5, True)
+            ctx.release(c1)
+            o = ctx.alloc((n, h, w, b.cout))
+            if q["ws_raw"] is not None:
+                w2 = self._w2_for(b, tuple(s.shape[3] for s in srcs))
+                ops.conv_igemm([(g2, 9)] + [(s, 1) for s in srcs], w2, q["b2"], b.cout, out=o, plan=plan, **new_stats(o))
+            else:
+                assert len(srcs) == 1
+                ops.conv_igemm([(g2, 9)], self._w2_for(b, ()), q["b2"], b.cout, out=o, residual=srcs[0],
+                               res_mode=ops.RES_SAME, plan=plan, **new_stats(o))
+            ctx.release(g2)
+            return o
+
+        def run_st(b: _Blk, x: th.Tensor) -> th.Tensor:
+            q = P[b.name]
+            n, h, w, c = x.shape
+            t = h * w
+            Hh, d, dp = b.heads, b.d_head, q["dp"]
+            inner, aw = Hh * d, Hh * dp
+            g = ctx.alloc((n, h, w, c))
+            gn([x], q["g"], q["be"], g, 1e-6, False)
+            cur = ctx.alloc((n, h, w, inner))
+            ops.conv_igemm([(g, 1)], q["w_in"], q["b_in"], inner, out=cur, plan=plan)
+            ctx.release(g)
+            for k, blk in enumerate(q["blocks"]):
+                # x = attn1(norm1(x)) + x
+                l = ctx.alloc((n, h, w, inner))
+                ops.layernorm(cur, *blk["ln"][0], out=l, plan=plan)
+                qkv = ctx.alloc((n, h, w, 3 * aw))
+                ops.conv_igemm([(l, 1)], blk["wqkv"], None, 3 * aw, out=qkv, plan=plan)
+                ctx.release(l)
+                a = ctx.alloc((n, h, w, aw))
+                ops.attention_sd(qkv, qkv, n, Hh, d, dp, t, t, t, 0, aw, 2 * aw, out=a.view(n * t, aw), plan=plan)
+                ctx.release(qkv)
+                nxt = ctx.alloc((n, h, w, inner))
+                ops.conv_igemm([(a, 1)], blk["wo1"], blk["bo1"], inner, out=nxt, residual=cur, res_mode=ops.RES_SAME, plan=plan)
+                ctx.release(a)
+                ctx.release(cur)
+                cur = nxt
+                # x = attn2(norm2(x), context) + x
+                l = ctx.alloc((n, h, w, inner))
+                ops.layernorm(cur, *blk["ln"][1], out=l, plan=plan)
+                qq = ctx.alloc((n, h, w, aw))
+                ops.conv_igemm([(l, 1)], blk["wq2"], None, aw, out=qq, plan=plan)
+                ctx.release(l)
+                a = ctx.alloc((n, h, w, aw))
+                ops.attention_sd(qq, kvs[b.name][k], n, Hh, d, dp, t, CTX_ROWS, ctx_tokens, 0, 0, aw, out=a.view(n * t, aw),
+                                 plan=plan)
+                ctx.release(qq)
+                nxt = ctx.alloc((n, h, w, inner))
+                ops.conv_igemm([(a, 1)], blk["wo2"], blk["bo2"], inner, out=nxt, residual=cur, res_mode=ops.RES_SAME, plan=plan)
+                ctx.release(a)
+                ctx.release(cur)
+                cur = nxt
+                # x = ff(norm3(x)) + x, GEGLU feed-forward
+                l = ctx.alloc((n, h, w, inner))
+                ops.layernorm(cur, *blk["ln"][2], out=l, plan=plan)
+                f = ctx.alloc((n, h, w, 8 * inner))
+                ops.conv_igemm([(l, 1)], blk["wff1"], blk["bff1"], 8 * inner, out=f, plan=plan)
+                ctx.release(l)
+                gg = ctx.alloc((n, h, w, 4 * inner))
+                ops.geglu(f, out=gg, plan=plan)
+                ctx.release(f)
+                nxt = ctx.alloc((n, h, w, inner))
+                ops.conv_igemm([(gg, 1)], blk["wff2"], blk["bff2"], inner, out=nxt, residual=cur, res_mode=ops.RES_SAME, plan=plan)
+                ctx.release(gg)
+                ctx.release(cur)
+                cur = nxt
+            o = ctx.alloc((n, h, w, c))
+            ops.conv_igemm([(cur, 1)], q["w_out"], q["b_out"], c, out=o, residual=x, res_mode=ops.RES_SAME, plan=plan,
+                           **new_stats(o))
+            ctx.release(cur)
+            return o
+
+        def run_block(layers: Sequence[_Blk], srcs: List[th.Tensor]) -> th.Tensor:
+            """Consumes one reference to each tensor in srcs; returns a tensor the caller owns."""
+            for b in layers:
+                if b.kind == "res":
+                    o = run_res(b, srcs)
+                elif b.kind == "st":
+                    o = run_st(b, srcs[0])
+                elif b.kind == "down":
+                    x = srcs[0]
+                    o = ctx.alloc((x.shape[0], x.shape[1] // 2, x.shape[2] // 2, b.cout))
+                    ops.conv_igemm([(x, 9, 2)], P[b.name]["w"], P[b.name]["b"], b.cout, out=o, plan=plan, **new_stats(o))
+                else:  # up: F.interpolate(nearest, 2x) then conv3x3 (openaimodel.py:109-118)
+                    x = srcs[0]
+                    u = ctx.alloc((x.shape[0], x.shape[1] * 2, x.shape[2] * 2, b.cin))
+                    ops.resample2x(x, ops.RESAMPLE_NEAREST2, out=u, plan=plan)
+                    o = ctx.alloc((x.shape[0], x.shape[1] * 2, x.shape[2] * 2, b.cout))
+                    ops.conv_igemm([(u, 9)], P[b.name]["w"], P[b.name]["b"], b.cout, out=o, plan=plan, **new_stats(o))
+                    ctx.release(u)
+                for s in srcs:
+                    ctx.release(s)
+                srcs = [o]
+            return srcs[0]
+
+        inp, middle, outb = self._arch
+        h = ctx.alloc((B, H, W, mc))
+        ops.stem_conv(x_in, P["stem_w"], P["stem_b"], out=h, plan=plan)
+        hs = [h]
+        ctx.retain(h)
+        for layers in inp[1:]:
+            h = run_block(layers, [h])
+            hs.append(h)
+            ctx.retain(h)
+        h = run_block(middle, [h])
+        for layers in outb:
+            h = run_block(layers, [h, hs.pop()])  # th.cat([h, hs.pop()], dim=1), openaimodel.py:735
+        g = ctx.alloc(tuple(h.shape))
+        gn([h], P["out_g"], P["out_be"], g, 1e-5, True)
+        ctx.release(h)
+        ops.conv_igemm([(g, 9)], P["out_w"], P["out_b"], self.out_channels, out=out, out_mode=ops.OUT_F32_NCHW, plan=plan)
+        ctx.release(g)
+
+    # ---- reference call signature ----
+    @th.no_grad()
+    def forward(self, x, timesteps=None, context=None, y=None, **kwargs):
+        """openaimodel.py:710-742. x fp32 [n, C, H, W], timesteps [n], context fp32 [n, tokens <= 128, context_dim]."""
+        assert (y is not None) == (self.num_classes is not None), "must specify y if and only if the model is class-conditional"
+        assert timesteps is not None and timesteps.shape == (x.shape[0],)
+        if context is None:
+            raise NotImplementedError("the SpatialTransformer blocks of this configuration need a context")
+        self._ready()
+        n, _, H, W = x.shape
+        tokens = context.shape[1]
+        key = (n, H, W, tokens)
+        entry = self._plans.get(key)
+        if entry is None:
+            dev = self._device()
+            x_in = th.zeros((n, self.in_channels, H, W), dtype=th.float32, device=dev)
+            t_in = th.zeros((n,), dtype=th.int64, device=dev)
+            c_in = th.zeros((n, tokens, self.context_dim), dtype=th.float32, device=dev)
+            out = th.empty((n, self.out_channels, H, W), dtype=th.float32, device=dev)
+            plan = ops.Plan()
+            cpad = ops.pad_context(c_in, CTX_ROWS, plan=plan)
+            kvs = self.record_context(plan, cpad)
+            self.record_forward(plan, x_in, t_in, kvs, out, ctx_tokens=tokens)
+            entry = (plan, x_in, t_in, c_in, out)
+            self._plans[key] = entry
+        plan, x_in, t_in, c_in, out = entry
+        x_in.copy_(x.float())
+        t_in.copy_(timesteps.to(th.int64))
+        c_in.copy_(context.float())
+        self.gpu_launches += plan.run()
+        return out.clone()

@@ -94,6 +94,13 @@ typedef struct {
                            (dynamic_unet.py:699) with groups of stats2_cpg channels */
   int stats2_cpg;
   int stats2_choff;
+  /* ---- appended for the Stable-Diffusion UNet ("Stable Diffusion"/ldm/modules/diffusionmodules/openaimodel.py) ---- */
+  int bias_stride;      /* 0: bias[co]. > 0: per-image bias rows, bias[img * bias_stride + co] - the ResBlock's
+                           `h = h + emb_out[..., None, None]` (openaimodel.py:272) folded into the first conv's
+                           epilogue (conv bias pre-added into the embedding Linear's bias) */
+  int seg_stride[3];    /* 0 or 1: unit stride. 2: segment s is a 3x3 stride-2 pad-1 convolution (Downsample.op,
+                           openaimodel.py:147-149): its `act` is [n, 2h, 2w, cin], output pixel (y, x) reads input
+                           rows 2y-1..2y+1, columns 2x-1..2x+1 */
 } adb_conv_desc;
 
 /* N tile the kernel uses for `cout` output channels; `cout_pad` must be a multiple of it. */
@@ -254,6 +261,50 @@ int adb_pool_merge(adb_plan* plan, const void* dxp, const float* dmean, void* dh
  * log_softmax(logits)[range(n), y].sum() * scale (…progressive.py:387-390). */
 int adb_logsoftmax_grad(adb_plan* plan, const float* logits, const int64_t* y, float* dlogits, int n, int k,
                         float scale, adb_stream stream);
+
+/* ==== Stable-Diffusion-v1 family (BASELINE configs[4]); paths relative to
+ * /root/reference/examples/"Stable Diffusion"/ ==== */
+
+/* Fused softmax attention between the projections of CrossAttention.forward (ldm/modules/attention.py:170-194):
+ * out = softmax(q k^T * d_head^-0.5) v per (batch, head), self- or cross-attention.
+ * Every head occupies d_pad (multiple of 64, <= 192) columns of the q / k / v matrices and of `out`; columns
+ * [d_head, d_pad) of q, k, v must be zero (zero-padded projection weights) and come out zero.
+ * q   : bf16 [b*tq, q_width], head h at columns q_col0 + h*d_pad
+ * kv  : bf16 [b*tk_rows, kv_width], K of head h at k_col0 + h*d_pad, V at v_col0 + h*d_pad; only the first
+ *       tk_valid of the tk_rows rows of a batch element are keys (77 context tokens in a 128-row padded buffer)
+ * out : bf16 [b*tq, heads*d_pad] */
+typedef struct {
+  const void* q;
+  int q_width, q_col0;
+  const void* kv;
+  int kv_width, k_col0, v_col0;
+  void* out;
+  int b, heads, d_head, d_pad;
+  int tq, tk_rows, tk_valid;
+} adb_attn_sd_desc;
+int adb_attention_sd(adb_plan* plan, const adb_attn_sd_desc* d, adb_stream stream);
+
+/* nn.LayerNorm(c) over the channels of every token (BasicTransformerBlock.norm1/2/3, attention.py:205-207):
+ * x, out bf16 [rows, c]; gamma, beta fp32 [c]; c % 8 == 0, c <= 2048. Two-pass statistics in fp32 registers. */
+int adb_layernorm(adb_plan* plan, const void* x, const float* gamma, const float* beta, void* out, int rows, int c,
+                  float eps, adb_stream stream);
+
+/* GEGLU gate (attention.py:37-44): out[r, j] = x[r, j] * gelu(x[r, inner + j]), exact (erf) GELU;
+ * x bf16 [rows, 2*inner], out bf16 [rows, inner]; inner % 8 == 0. */
+int adb_geglu(adb_plan* plan, const void* x, void* out, int rows, int inner, adb_stream stream);
+
+/* Classifier-free-guidance combine + DDIM update of p_sample_ddim with eta = 0 (ldm/models/diffusion/ddim.py:
+ * 184-216): e_t = e_u + scale * (e_c - e_u); pred_x0 = (x - coef[0] * e_t) / coef[1];
+ * x_prev = coef[2] * pred_x0 + coef[3] * e_t, with coef = {sqrt(1-a_t), sqrt(a_t), sqrt(a_prev), sqrt(1-a_prev)}
+ * in fp32 and every intermediate rounded as the reference's separate fp32 tensor ops round it (bit-exact given eps).
+ * eps: fp32 [2n, chw], unconditional half first (torch.cat([uncond, cond]), :187-189); with scale == 1 or
+ * cfg == 0 eps is [n, chw] and used as is. x_prev may alias x. pred_x0 may be NULL. */
+int adb_cfg_ddim_step(adb_plan* plan, const float* x, const float* eps, float* x_prev, float* pred_x0, int n,
+                      int chw, int cfg, float scale, const float coef[4], adb_stream stream);
+
+/* fp32 [n, t, c] -> bf16 [n, t_pad, c_pad] zero-padded: the text context (77 x 768) into the 128-row buffer the
+ * K/V projection GEMMs and adb_attention_sd read. */
+int adb_pad_context(adb_plan* plan, const float* ctx, void* out, int n, int t, int c, int t_pad, adb_stream stream);
 
 #ifdef __cplusplus
 }

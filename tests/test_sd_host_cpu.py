@@ -1,0 +1,68 @@
+"""CPU: host-side logic of the Stable-Diffusion family - parameter names / shapes equal the reference's state_dict
+(via the oracle's inventory, itself checked against the reference in make_sd_golden.py), schedule tables bit-exact
+against the reference's recorded ones, no-CPU-path errors."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import sd_unet_ref as R
+from tests.util import golden
+
+
+def _build(cfg):
+    from autodiffusion_b200.sd_unet import UNetModel
+
+    return UNetModel(image_size=32, in_channels=cfg.in_channels, out_channels=cfg.out_channels, model_channels=cfg.model_channels,
+                     attention_resolutions=list(cfg.attention_resolutions), num_res_blocks=cfg.num_res_blocks,
+                     channel_mult=list(cfg.channel_mult), num_heads=cfg.num_heads, use_spatial_transformer=True,
+                     transformer_depth=cfg.transformer_depth, context_dim=cfg.context_dim, use_checkpoint=True, legacy=False)
+
+
+@pytest.mark.parametrize("cfg", [R.SDConfig(model_channels=64, context_dim=128), R.SDConfig(model_channels=128, num_res_blocks=1)])
+def test_state_dict_matches_reference_inventory(cfg):
+    m = _build(cfg)
+    ours = {k: tuple(v.shape) for k, v in m.state_dict().items()}
+    assert ours == R.param_shapes(cfg)
+    m.load_state_dict(R.make_weights(cfg, seed=1))  # strict
+
+
+def test_zero_modules_start_at_zero():
+    m = _build(R.SDConfig(model_channels=64, context_dim=128))
+    sd = m.state_dict()
+    assert sd["out.2.weight"].abs().max() == 0 and sd["input_blocks.1.0.out_layers.3.weight"].abs().max() == 0
+    assert sd["input_blocks.1.1.proj_out.weight"].abs().max() == 0 and sd["input_blocks.1.0.in_layers.2.weight"].abs().max() > 0
+
+
+def test_unsupported_configurations_raise():
+    from autodiffusion_b200.sd_unet import UNetModel
+
+    kw = dict(image_size=32, in_channels=4, out_channels=4, model_channels=64, attention_resolutions=[4, 2, 1], num_res_blocks=2,
+              channel_mult=[1, 2, 4, 4], num_heads=8)
+    with pytest.raises(NotImplementedError):
+        UNetModel(**kw)  # AttentionBlock variant: not the SD configuration
+    with pytest.raises(AssertionError):
+        UNetModel(**kw, use_spatial_transformer=True)  # the reference's assert: context_dim missing
+    with pytest.raises(NotImplementedError):
+        UNetModel(**kw, use_spatial_transformer=True, context_dim=128, use_scale_shift_norm=True)
+
+
+def test_cpu_model_refuses_to_run():
+    m = _build(R.SDConfig(model_channels=64, context_dim=128))
+    with pytest.raises(RuntimeError):
+        m(torch.zeros(1, 4, 64, 64), torch.zeros(1, dtype=torch.long), context=torch.zeros(1, 77, 128))
+
+
+def test_schedule_tables_and_coefficients_bit_exact():
+    from autodiffusion_b200.sd_ddim import ddim_coefficients, ddim_tables, make_beta_schedule
+
+    g = golden("sd_small.npz")
+    acp = torch.tensor(np.cumprod(1.0 - make_beta_schedule("linear", 1000, 0.00085, 0.0120), axis=0), dtype=torch.float32)
+    assert torch.equal(acp, R.sd_alphas_cumprod())
+    steps = sorted(g["cand"].tolist())
+    a, ap, s1m = ddim_tables(acp, steps)
+    assert np.array_equal(a.numpy(), g["ddim_alphas"]) and np.array_equal(ap.numpy(), g["ddim_alphas_prev"])
+    assert np.array_equal(s1m.numpy(), g["ddim_s1m"])
+    for i in range(len(steps)):
+        c = ddim_coefficients(a, ap, s1m, i)
+        want = (s1m[i].item(), a[i].sqrt().item(), ap[i].sqrt().item(), (1.0 - ap[i]).sqrt().item())
+        assert c == want  # the fp32 values torch computes in p_sample_ddim

@@ -116,7 +116,7 @@ class AttnSdDesc(C.Structure):
         ("kv", C.c_void_p), ("kv_width", C.c_int), ("k_col0", C.c_int), ("v_col0", C.c_int),
         ("out", C.c_void_p),
         ("b", C.c_int), ("heads", C.c_int), ("d_head", C.c_int), ("d_pad", C.c_int),
-        ("tq", C.c_int), ("tk_rows", C.c_int), ("tk_valid", C.c_int),
+        ("tq", C.c_int), ("tk_rows", C.c_int), ("tk_valid", C.c_int), ("v_ones", C.c_int),
     ]
 
 

@@ -48,20 +48,42 @@ struct AttnSdParams {
   int q_col0, k_col0, v_col0;  // column of head 0 in the Q / K / V matrices (head h is DP*h further)
   int ksteps;    // 16-deep k-steps of q.k: ceil(d/16)
   int n_last;    // width of the last PV chunk (multiple of 16)
+  int d_head;    // real head dim: output columns [d_head, DP) are written as zeros
   float sc;      // d^-0.5 * log2(e)
 };
 
+__device__ __forceinline__ float fmax3(float a, float b, float c) {
+  float d;
+  asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));  // one FMNMX3 on sm_100
+  return d;
+}
+
+// 2^x on the FMA pipe (Cody-Waite split + degree-3 polynomial, relative error 1.1e-4 - below the 2^-9 rounding of the
+// bf16 P it feeds): every 4th probability takes this path so the 16-lane MUFU unit is not the only exp engine.
+__device__ __forceinline__ float ex2_poly(float x) {
+  x = fmaxf(x, -120.0f);
+  const float t = x + 12582912.0f;  // 1.5 * 2^23: the low mantissa bits of t hold round(x)
+  const float f = x - (t - 12582912.0f);  // [-0.5, 0.5]
+  float q = fmaf(f, 0.05459282f, 0.24221784f);
+  q = fmaf(q, f, 0.6933686f);
+  q = fmaf(q, f, 1.0f);
+  return __int_as_float(__float_as_int(q) + (__float_as_int(t) << 23));
+}
+
 template <int NC>
 struct SdCfg {
-  static constexpr int STAGES = (NC == 1) ? 4 : 3;
+  static constexpr int STAGES = (NC == 1) ? 4 : (NC == 2 ? 2 : 3);
   static constexpr int Q_BYTES = NC * Q_CHUNK_BYTES;
   static constexpr int STAGE_BYTES = 2 * NC * KV_CHUNK_BYTES;
   static constexpr int SMEM_BYTES = Q_BYTES + STAGES * STAGE_BYTES + 1024;
   static constexpr int TMEM_COLS = (O_COL + NC * CH <= 256) ? 256 : 512;
-  static constexpr int MIN_CTAS = (NC == 1) ? 2 : 1;
+  static constexpr int MIN_CTAS = (NC <= 2) ? 2 : 1;  // NC = 2: 32 KB Q + 2 x 32 KB stages -> two CTAs per SM
 };
 
-template <int NC>
+// ONES: column d_head of V is 1.0 in every key row (the packer puts it there through the V projection's bias), so
+// the PV product accumulates the softmax denominator in O[:, d_head] - the 64 row-sum FADDs per thread and tile
+// disappear from the exp-bound softmax loop, and the denominator is consistent with the bf16-rounded P.
+template <int NC, bool ONES, bool POLY>
 __global__ void __launch_bounds__(AT_THREADS, SdCfg<NC>::MIN_CTAS) attention_sd_kernel(const __grid_constant__ AttnSdParams p) {
   using C = SdCfg<NC>;
   constexpr int STAGES = C::STAGES;
@@ -191,13 +213,19 @@ __global__ void __launch_bounds__(AT_THREADS, SdCfg<NC>::MIN_CTAS) attention_sd_
         for (int i = 0; i < KT; ++i)
           if (i >= kvalid) sr[i] = 0xff800000u;  // -inf
       }
+      // 8 independent chains of 3-input maxima: 64 values in 28 + 4 FMNMX3
       float mxs[8];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) mxs[i] = __uint_as_float(sr[i]);
+      for (int i = 0; i < 8; ++i) mxs[i] = fmax3(__uint_as_float(sr[i]), __uint_as_float(sr[8 + i]), __uint_as_float(sr[16 + i]));
 #pragma unroll
-      for (int i = 8; i < KT; ++i) mxs[i & 7] = fmaxf(mxs[i & 7], __uint_as_float(sr[i]));
-      const float mx = fmaxf(fmaxf(fmaxf(mxs[0], mxs[1]), fmaxf(mxs[2], mxs[3])),
-                             fmaxf(fmaxf(mxs[4], mxs[5]), fmaxf(mxs[6], mxs[7])));
+      for (int i = 0; i < 8; ++i) mxs[i] = fmax3(mxs[i], __uint_as_float(sr[24 + i]), __uint_as_float(sr[32 + i]));
+#pragma unroll
+      for (int i = 0; i < 8; ++i) mxs[i] = fmax3(mxs[i], __uint_as_float(sr[40 + i]), __uint_as_float(sr[48 + i]));
+#pragma unroll
+      for (int i = 0; i < 4; ++i) mxs[i] = fmax3(mxs[i], mxs[4 + i], __uint_as_float(sr[56 + i]));
+#pragma unroll
+      for (int i = 0; i < 4; ++i) mxs[i] = fmaxf(mxs[i], __uint_as_float(sr[60 + i]));
+      const float mx = fmaxf(fmaxf(mxs[0], mxs[1]), fmaxf(mxs[2], mxs[3]));
       // sc > 0: max and scaling commute. Lazy rescaling as in attention2.cu (threshold 8 in log2 units).
       const float m_tile = mx * sc;
       const bool jump = m_tile > m_run + 8.0f;
@@ -221,21 +249,32 @@ __global__ void __launch_bounds__(AT_THREADS, SdCfg<NC>::MIN_CTAS) attention_sd_
           }
         }
       }
-      float ps[8];
+      if (ONES) {
 #pragma unroll
-      for (int i = 0; i < 8; ++i) ps[i] = 0.f;
+        for (int i = 0; i < KT / 2; ++i) {
+          const float p0 = ex2_approx_sd(fmaf(__uint_as_float(sr[2 * i]), sc, -m_new));
+          const float x1 = fmaf(__uint_as_float(sr[2 * i + 1]), sc, -m_new);
+          const float p1 = (POLY && (i & 1)) ? ex2_poly(x1) : ex2_approx_sd(x1);
+          sr[i] = pack_bf16x2(p0, p1);
+        }
+        tmem_st_32x32b_x32(s_addr, sr);
+      } else {
+        float ps[8];
 #pragma unroll
-      for (int i = 0; i < KT / 2; ++i) {
-        const float p0 = ex2_approx_sd(fmaf(__uint_as_float(sr[2 * i]), sc, -m_new));
-        const float p1 = ex2_approx_sd(fmaf(__uint_as_float(sr[2 * i + 1]), sc, -m_new));
-        ps[(2 * i) & 7] += p0;
-        ps[(2 * i + 1) & 7] += p1;
-        sr[i] = pack_bf16x2(p0, p1);
+        for (int i = 0; i < 8; ++i) ps[i] = 0.f;
+#pragma unroll
+        for (int i = 0; i < KT / 2; ++i) {
+          const float p0 = ex2_approx_sd(fmaf(__uint_as_float(sr[2 * i]), sc, -m_new));
+          const float p1 = ex2_approx_sd(fmaf(__uint_as_float(sr[2 * i + 1]), sc, -m_new));
+          ps[(2 * i) & 7] += p0;
+          ps[(2 * i + 1) & 7] += p1;
+          sr[i] = pack_bf16x2(p0, p1);
+        }
+        const float ps0 = (ps[0] + ps[1]) + (ps[2] + ps[3]);
+        const float ps1 = (ps[4] + ps[5]) + (ps[6] + ps[7]);
+        tmem_st_32x32b_x32(s_addr, sr);
+        l_run = l_run * alpha + (ps0 + ps1);
       }
-      const float ps0 = (ps[0] + ps[1]) + (ps[2] + ps[3]);
-      const float ps1 = (ps[4] + ps[5]) + (ps[6] + ps[7]);
-      tmem_st_32x32b_x32(s_addr, sr);
-      l_run = l_run * alpha + (ps0 + ps1);
       m_run = m_new;
       tmem_wait_st();
       tc_fence_before();
@@ -244,6 +283,15 @@ __global__ void __launch_bounds__(AT_THREADS, SdCfg<NC>::MIN_CTAS) attention_sd_
     }
     mbar_wait(bar(B_PV_DONE + ((nkt - 1) & 1)), (uint32_t)((nkt - 1) >> 1) & 1u);
     tc_fence_after();
+    if (ONES) {  // the denominator accumulated by the tensor core in O[:, d_head]
+      uint32_t lv[16];
+      tmem_ld_32x32b_x16(lane_addr + O_COL + (p.d_head & ~15), lv);
+      tmem_wait_ld();
+      l_run = __uint_as_float(lv[0]);
+#pragma unroll
+      for (int i = 1; i < 16; ++i)
+        if (i == (p.d_head & 15)) l_run = __uint_as_float(lv[i]);
+    }
     const float inv = 1.0f / l_run;
     const bool ok = (q0 + row) < p.tq;
     __nv_bfloat16* orow = p.out + ((size_t)(qrow_base + q0 + row)) * ((size_t)p.heads * DP) + h * DP;
@@ -256,7 +304,7 @@ __global__ void __launch_bounds__(AT_THREADS, SdCfg<NC>::MIN_CTAS) attention_sd_
       }
 #pragma unroll
       for (int i = 0; i < 32; ++i)
-        if (c + i >= ocols) v[i] = 0u;  // columns the PV product never wrote: the head's zero padding
+        if (c + i >= p.d_head) v[i] = 0u;  // the head's padding columns (never written, or the ones column)
       if (ok) {
 #pragma unroll
         for (int g = 0; g < 4; ++g) {
@@ -279,16 +327,16 @@ __global__ void __launch_bounds__(AT_THREADS, SdCfg<NC>::MIN_CTAS) attention_sd_
   }
 }
 
-template <int NC>
+template <int NC, bool ONES, bool POLY>
 int launch_attn_sd(const AttnSdParams& ap, int b, cudaStream_t stream) {
   using C = SdCfg<NC>;
   static bool attr_set = false;
   if (!attr_set) {
-    ADB_CUDA(cudaFuncSetAttribute(attention_sd_kernel<NC>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+    ADB_CUDA(cudaFuncSetAttribute(attention_sd_kernel<NC, ONES, POLY>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
     attr_set = true;
   }
   dim3 grid((ap.tq + BM - 1) / BM, b * ap.heads);
-  attention_sd_kernel<NC><<<grid, AT_THREADS, C::SMEM_BYTES, stream>>>(ap);
+  attention_sd_kernel<NC, ONES, POLY><<<grid, AT_THREADS, C::SMEM_BYTES, stream>>>(ap);
   ADB_CUDA(cudaGetLastError());
   return 1;
 }
@@ -332,16 +380,33 @@ int attention_sd_submit(adb_plan* plan, const adb_attn_sd_desc* d, cudaStream_t 
     const char* e = getenv("ADB_ATTN_SD_FULLN");
     full_n = (e && e[0] == '1') ? 1 : 0;
   }
-  const int rem = d->d_head - (nc - 1) * 64;           // real columns in the last chunk
+  const int ones = d->v_ones ? 1 : 0;
+  ADB_REQUIRE(!ones || d->d_pad > d->d_head, "attention_sd: v_ones needs a padding column (d_pad > d_head)");
+  const int rem = d->d_head + ones - (nc - 1) * 64;    // columns of the last chunk the PV product must cover
   ap.n_last = full_n ? 64 : ((rem + 15) / 16) * 16;
+  ap.d_head = d->d_head;
   ap.sc = (float)(1.4426950408889634 / sqrt((double)d->d_head));
   const double flops = 4.0 * (double)d->b * d->heads * (double)d->tq * (double)d->tk_valid * d->d_head;
   const int b = d->b;
-  return submit(plan, stream, "attention_sd", flops, 0.0, [ap, b, nc](cudaStream_t s) -> int {
-    switch (nc) {
-      case 1: return launch_attn_sd<1>(ap, b, s);
-      case 2: return launch_attn_sd<2>(ap, b, s);
-      default: return launch_attn_sd<3>(ap, b, s);
+  // ADB_ATTN_POLY=1: a quarter of the exponentials of long key sequences go to the FMA pipe. Off by default: measured
+  // at T = 4096, d = 40 the kernel is latency-bound (XU pipe 48 % busy, issue slots 55 %), and the extra FMA-pipe
+  // instructions made it 8 % slower (3.73 vs 3.37 ms at batch 64).
+  static int poly_on = -1;
+  if (poly_on < 0) {
+    const char* e = getenv("ADB_ATTN_POLY");
+    poly_on = (e && e[0] == '1') ? 1 : 0;
+  }
+  const int poly = (ones && poly_on && d->tk_valid >= 1024) ? 1 : 0;
+  return submit(plan, stream, "attention_sd", flops, 0.0, [ap, b, nc, ones, poly](cudaStream_t s) -> int {
+    switch (nc * 4 + ones * 2 + poly) {
+      case 4: return launch_attn_sd<1, false, false>(ap, b, s);
+      case 6: return launch_attn_sd<1, true, false>(ap, b, s);
+      case 7: return launch_attn_sd<1, true, true>(ap, b, s);
+      case 8: return launch_attn_sd<2, false, false>(ap, b, s);
+      case 10: return launch_attn_sd<2, true, false>(ap, b, s);
+      case 11: return launch_attn_sd<2, true, true>(ap, b, s);
+      case 12: return launch_attn_sd<3, false, false>(ap, b, s);
+      default: return launch_attn_sd<3, true, false>(ap, b, s);
     }
   });
 }

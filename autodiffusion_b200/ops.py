@@ -642,7 +642,7 @@ def nhwc_to_nchw_f32(x: torch.Tensor) -> torch.Tensor:
 # ---- Stable-Diffusion-v1 family ----
 def attention_sd(q: torch.Tensor, kv: torch.Tensor, b: int, heads: int, d_head: int, d_pad: int, tq: int, tk_rows: int,
                  tk_valid: int, q_col0: int, k_col0: int, v_col0: int, out: Optional[torch.Tensor] = None,
-                 plan: Optional[Plan] = None) -> torch.Tensor:
+                 plan: Optional[Plan] = None, v_ones: bool = False) -> torch.Tensor:
     """softmax(q k^T d_head^-0.5) v per (batch, head) with heads padded to d_pad columns (include/adb200.h).
     q: bf16 [b*tq, q_width]; kv: bf16 [b*tk_rows, kv_width] (may be `q` itself) -> bf16 [b*tq, heads*d_pad]."""
     q2, kv2 = q.reshape(b * tq, -1), kv.reshape(b * tk_rows, -1)
@@ -654,6 +654,7 @@ def attention_sd(q: torch.Tensor, kv: torch.Tensor, b: int, heads: int, d_head: 
     d.out = _dev(out, "out", torch.bfloat16)
     d.b, d.heads, d.d_head, d.d_pad = b, heads, d_head, d_pad
     d.tq, d.tk_rows, d.tk_valid = tq, tk_rows, tk_valid
+    d.v_ones = int(bool(v_ones))
     _lib.check(_lib.lib().adb_attention_sd(_ph(plan), C.byref(d), _stream()), "adb_attention_sd")
     if plan is not None:
         plan.keep(q, kv, out)

@@ -284,7 +284,16 @@ class UNetModel(nn.Module):
                     o[:, :, :d] = wt.reshape(wt.shape[0], H, d)
                     return o.reshape(wt.shape[0], H * dp)
 
-                q = {"g": f32(sd[n + ".norm.weight"]), "be": f32(sd[n + ".norm.bias"]),
+                # softmax denominators from the tensor core: V gets a column of ones in every head's padding (through the
+                # V projection's bias), csrc/attention_sd.cu accumulates sum_j P_ij in O[:, d] (v_ones)
+                ones = dp > d
+                v_bias = th.zeros(H, dp)
+                if ones:
+                    v_bias[:, d] = 1.0
+                v_bias = v_bias.reshape(-1)
+                q = {"g": f32(sd[n + ".norm.weight"]), "be": f32(sd[n + ".norm.bias"]), "ones": ones,
+                     "bqkv": f32(th.cat([th.zeros(2 * H * dp), v_bias])) if ones else None,
+                     "bkv2": f32(th.cat([th.zeros(H * dp), v_bias])) if ones else None,
                      "w_in": ops.pack_conv_weight([sd[n + ".proj_in.weight"]], dev), "b_in": f32(sd[n + ".proj_in.bias"]),
                      "w_out": ops.pack_conv_weight([sd[n + ".proj_out.weight"]], dev), "b_out": f32(sd[n + ".proj_out.bias"]),
                      "dp": dp, "blocks": []}
@@ -359,7 +368,7 @@ class UNetModel(nn.Module):
         for b in self.st_blocks():
             q = self._packed[b.name]
             width = 2 * b.heads * q["dp"]
-            out[b.name] = [ops.conv_igemm([(cv, 1)], blk["wkv2"], None, width, plan=plan).view(n * CTX_ROWS, width)
+            out[b.name] = [ops.conv_igemm([(cv, 1)], blk["wkv2"], q["bkv2"], width, plan=plan).view(n * CTX_ROWS, width)
                            for blk in q["blocks"]]
         return out
 
@@ -439,10 +448,11 @@ class UNetModel(nn.Module):
                 l = ctx.alloc((n, h, w, inner))
                 ops.layernorm(cur, *blk["ln"][0], out=l, plan=plan)
                 qkv = ctx.alloc((n, h, w, 3 * aw))
-                ops.conv_igemm([(l, 1)], blk["wqkv"], None, 3 * aw, out=qkv, plan=plan)
+                ops.conv_igemm([(l, 1)], blk["wqkv"], q["bqkv"], 3 * aw, out=qkv, plan=plan)
                 ctx.release(l)
                 a = ctx.alloc((n, h, w, aw))
-                ops.attention_sd(qkv, qkv, n, Hh, d, dp, t, t, t, 0, aw, 2 * aw, out=a.view(n * t, aw), plan=plan)
+                ops.attention_sd(qkv, qkv, n, Hh, d, dp, t, t, t, 0, aw, 2 * aw, out=a.view(n * t, aw), plan=plan,
+                                 v_ones=q["ones"])
                 ctx.release(qkv)
                 nxt = ctx.alloc((n, h, w, inner))
                 ops.conv_igemm([(a, 1)], blk["wo1"], blk["bo1"], inner, out=nxt, residual=cur, res_mode=ops.RES_SAME, plan=plan)
@@ -457,7 +467,7 @@ class UNetModel(nn.Module):
                 ctx.release(l)
                 a = ctx.alloc((n, h, w, aw))
                 ops.attention_sd(qq, kvs[b.name][k], n, Hh, d, dp, t, CTX_ROWS, ctx_tokens, 0, 0, aw, out=a.view(n * t, aw),
-                                 plan=plan)
+                                 plan=plan, v_ones=q["ones"])
                 ctx.release(qq)
                 nxt = ctx.alloc((n, h, w, inner))
                 ops.conv_igemm([(a, 1)], blk["wo2"], blk["bo2"], inner, out=nxt, residual=cur, res_mode=ops.RES_SAME, plan=plan)

@@ -61,7 +61,7 @@ def parse():
     ap.add_argument("--ref-batch", type=int, default=8)
     ap.add_argument("--dump-ops", default=None, help="write every recorded op's kind/flops/bytes/ms of one step to this CSV")
     ap.add_argument("--unet-only", action="store_true", help="headline = the UNet-only variant (no classifier cond_fn)")
-    ap.add_argument("--workload", default="admg64", choices=["admg64", "lsun256"],
+    ap.add_argument("--workload", default="admg64", choices=["admg64", "lsun256", "sdv1"],
                     help="admg64 = BASELINE configs[1] (default, the metric's config); lsun256 = configs[3]")
     return ap.parse_args()
 
@@ -528,9 +528,176 @@ def run_lsun(args):
         dist.destroy_process_group()
 
 
+# ------------------------------------------------------------------------------------------
+# secondary workload: BASELINE configs[4], Stable Diffusion v1 UNet on 64x64x4 latents, CFG 7.5
+# ------------------------------------------------------------------------------------------
+SD_CAND = [981, 861, 741, 641, 501, 421, 301, 201, 121, 21]  # a searched-style 10-step subsequence of the 1000 DDPM steps
+SD_GFLOP_PER_FWD = 803.27  # per image per UNet forward (x2 per step under CFG)
+
+
+def sd_cpu_rate(n_steps_timed=1):
+    """The oracle port of the reference's CFG DDIM step on the host cores: batch 1 (2 UNet forwards per step)."""
+    import torch
+
+    from oracle import sd_unet_ref as R
+
+    torch.set_num_threads(os.cpu_count() or 1)
+    cfg = R.sd_v1_config()
+    sd = R.make_weights(cfg, seed=0)
+    g = torch.Generator().manual_seed(0)
+    x, c, uc = torch.randn(1, 4, 64, 64, generator=g), torch.randn(1, 77, 768, generator=g), torch.randn(1, 77, 768, generator=g)
+    t0 = time.time()
+    R.ddim_sample(lambda xx, tt, cc: R.unet_forward(sd, cfg, xx, tt, cc), x, c, uc, 7.5, SD_CAND[:n_steps_timed], R.sd_alphas_cumprod())
+    dt = time.time() - t0
+    return 1.0 / (dt / n_steps_timed * len(SD_CAND)), dt
+
+
+def run_sdv1(args):
+    """latent images/s of the SD-v1 UNet (859.5 M params) under the searched 10-step DDIM with CFG 7.5, batch 32 per
+    GPU (scripts/search_ea.py:504-538 without the text encoder / VAE, which are outside the searched path)."""
+    import torch
+    import torch.distributed as dist
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        if rank == 0:
+            rate, dt = sd_cpu_rate(1)
+            print(json.dumps({"impl": "reference", "metric": "SD-v1 latent images/s, 10-step searched DDIM, CFG 7.5", "value": rate,
+                              "unit": "images/s", "n_gpus": world, "steps": 1, "warmup": 0, "ms_per_step": dt * 1e3,
+                              "higher_is_better": True, "dtype": "f32", "data": "synthetic",
+                              "config": {"workload": "SD-v1 UNet, CFG 7.5, 10 searched steps; sample: 1 of the 10 steps at batch 1"},
+                              "cpu_baseline": {"value": rate, "unit": "images/s", "cores": os.cpu_count(), "kind": "port",
+                                               "sample": "one CFG DDIM step (2 UNet forwards) at batch 1, extrapolated to 10 steps"},
+                              "e2e": {"value": rate, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}), flush=True)
+        return
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    from autodiffusion_b200.sd_ddim import CandidatePlan, LatentDiffusionUNet
+    from autodiffusion_b200.sd_unet import UNetModel
+
+    unet = UNetModel(image_size=32, in_channels=4, out_channels=4, model_channels=320, attention_resolutions=[4, 2, 1],
+                     num_res_blocks=2, channel_mult=[1, 2, 4, 4], num_heads=8, use_spatial_transformer=True, transformer_depth=1,
+                     context_dim=768, use_checkpoint=True, legacy=False)
+    unet.load_state_dict(bench_weights({k: tuple(v.shape) for k, v in unet.state_dict().items()}))
+    unet.to(dev).eval()
+    ld = LatentDiffusionUNet(unet)
+    B = args.batch if args.batch != 256 else 32
+    K = len(SD_CAND)
+    t0 = time.time()
+    plan = CandidatePlan(unet, ld.alphas_cumprod, SD_CAND, B, (4, 64, 64), 7.5, True)
+    torch.cuda.synchronize()
+    build_s = time.time() - t0
+    g = torch.Generator(device=dev).manual_seed(7 + rank)
+    x_T = torch.randn((B, 4, 64, 64), device=dev, generator=g)
+    cond = torch.randn((B, 77, 768), device=dev, generator=g)
+    uncond = torch.randn((1, 77, 768), device=dev, generator=g).repeat(B, 1, 1).contiguous()
+    hx, hc, hu = x_T.cpu().pin_memory(), cond.cpu().pin_memory(), uncond.cpu().pin_memory()
+    hout = torch.empty((B, 4, 64, 64), dtype=torch.float32).pin_memory()
+
+    def timed(fn, steps, warmup):
+        for _ in range(warmup):
+            fn()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms
+
+    def e2e():
+        plan.run(hx, hc, hu)
+        hout.copy_(plan.x, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+
+    sampler = ClockSampler(local)
+    sampler.start()
+    time.sleep(0.3)
+    w0 = time.time()
+    ms = timed(lambda: plan.run(x_T, cond, uncond), args.steps, args.warmup)
+    w1 = time.time()
+    clocks = sampler.stop(w0, w1)
+    ms_e2e = timed(e2e, args.steps, 1)
+    imgs = B * world * args.steps
+    value = imgs / (ms * 1e-3)
+    plan.plan_fwd.run_profiled()
+    info = plan.plan_fwd.op_info()
+    ms_ops = plan.plan_fwd.run_profiled()
+    agg = {}
+    for (kind, fl, by), t in zip(info, ms_ops):
+        a = agg.setdefault(kind, [0, 0.0, 0.0, 0.0])
+        a[0] += 1
+        a[1] += t
+        a[2] += fl
+        a[3] += by
+    if args.dump_ops and rank == 0:
+        with open(args.dump_ops, "w") as f:
+            f.write("idx,kind,flops,bytes,ms\n")
+            for i, ((kind, fl, by), t) in enumerate(zip(info, ms_ops)):
+                f.write(f"{i},{kind},{fl},{by},{t}\n")
+    fwd_ms = sum(ms_ops)
+    pk = peaks()
+    conv = agg.get("conv_igemm", [0, 0.0, 0.0, 0.0])
+    roof = None
+    if conv[1] > 0:
+        ach = conv[2] / (conv[1] * 1e-3) / 1e12
+        roof = {"kernel": "conv_igemm_kernel (tcgen05 implicit GEMM: every conv / Linear of the SD UNet)", "bound": "tensor",
+                "achieved": ach, "peak": pk["tf_sustained"], "unit": "TFLOP/s", "frac": ach / pk["tf_sustained"], "traffic": None,
+                "peak_source": pk["source"] + " (sustained bf16)", "launches": conv[0] * K * args.steps,
+                "share_of_step": conv[1] / fwd_ms, "flops_per_launch_avg": conv[2] / conv[0], "ms_per_launch_avg": conv[1] / conv[0]}
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        rate, dt = sd_cpu_rate(1)
+        cpu = {"value": rate, "unit": "images/s", "cores": os.cpu_count(), "kind": "port",
+               "sample": f"one CFG DDIM step (2 UNet forwards, 859.5M params) at batch 1 on the host: {dt:.1f} s, extrapolated to 10 steps"}
+    recorded_gflop = sum(fl for _, fl, _ in info) / (2 * B) / 1e9
+    if rank == 0:
+        print(json.dumps({
+            "metric": "Stable Diffusion v1 UNet latent images/s (64x64x4 latents = 512x512), 10-step searched DDIM, CFG 7.5",
+            "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
+            "data": "synthetic",
+            "config": {"workload": "SD-v1 UNet (859.5M params, random-init) on 64x64x4 latents, synthetic 77x768 text context + "
+                                   "unconditional context, CFG 7.5 (batched [uncond | cond] forward), 10 searched DDIM steps; one "
+                                   "step = full sampling of one batch as one CUDA graph (context K/V projected once)",
+                       "batch_per_gpu": B, "ddim_steps": K, "timesteps": SD_CAND,
+                       "l2": "activations per launch exceed the 126 MB L2; no explicit flush"},
+            "ms_per_unet_fwd": ms / args.steps / K, "gflop_per_image": 2 * K * SD_GFLOP_PER_FWD,
+            "tflops_effective": value / world * 2 * K * SD_GFLOP_PER_FWD / 1e3,
+            "flop_accounting": {"survey_gflop_per_image_per_forward": SD_GFLOP_PER_FWD,
+                                "recorded_plan_gflop_per_image_per_forward": recorded_gflop},
+            "e2e": {"value": imgs / (ms_e2e * 1e-3), "unit": "images/s",
+                    "h2d_bytes_per_step": (hx.numel() + hc.numel() + hu.numel()) * 4, "d2h_bytes_per_step": hout.numel() * 4},
+            "gpu_launches": plan.launches * args.steps, "plan_build_s": build_s, "clocks": clocks, "roofline": roof,
+            "cpu_baseline": cpu,
+            "kernel_breakdown_one_forward": {k: {"launches": v[0], "ms": round(v[1], 3), "share": round(v[1] / fwd_ms, 4),
+                                                 "tflops": (v[2] / (v[1] * 1e-3) / 1e12) if v[2] and v[1] else None,
+                                                 "gbs": (v[3] / (v[1] * 1e-3) / 1e9) if v[3] and v[1] else None}
+                                             for k, v in agg.items()},
+        }), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     args = parse()
-    if args.impl == "reference":
+    if args.workload == "sdv1":
+        run_sdv1(args)
+    elif args.impl == "reference":
         run_reference(args)
     elif args.workload == "lsun256":
         run_lsun(args)

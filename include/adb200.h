@@ -281,6 +281,8 @@ typedef struct {
   void* out;
   int b, heads, d_head, d_pad;
   int tq, tk_rows, tk_valid;
+  int v_ones;  /* 1: column d_head of every V row holds 1.0 (put there by the V projection's bias; needs d_pad > d_head):
+                  the kernel then takes the softmax denominator from the PV product instead of summing P itself */
 } adb_attn_sd_desc;
 int adb_attention_sd(adb_plan* plan, const adb_attn_sd_desc* d, adb_stream stream);
 

@@ -137,6 +137,15 @@ def test_attention_sd_self(b, heads, d, t):
     if dp > d:
         assert o[..., d:].abs().max().item() == 0.0  # the padding columns come out exactly zero
     _check(o[..., :d].reshape(b, t, heads * d), ref, 2 ** -6, f"self-attention b{b} h{heads} d{d} t{t}")
+    if dp > d:  # denominators from the tensor core: a column of ones in V's padding (v_ones)
+        qkv4 = qkv.view(b, t, 3, heads, dp).clone()
+        qkv4[:, :, 2, :, d] = 1.0
+        out1 = ops.attention_sd(qkv4.view(b, t, -1), qkv4.view(b, t, -1), b, heads, d, dp, t, t, t, 0, heads * dp, 2 * heads * dp,
+                                v_ones=True)
+        torch.cuda.synchronize()
+        o1 = out1.float().cpu().reshape(b, t, heads, dp)
+        assert o1[..., d:].abs().max().item() == 0.0
+        _check(o1[..., :d].reshape(b, t, heads * d), ref, 2 ** -6, f"self-attention (v_ones) b{b} h{heads} d{d} t{t}")
 
 
 @pytest.mark.parametrize("b,heads,d,tq,tk", [(2, 8, 40, 4096, 77), (2, 8, 80, 1024, 77), (3, 8, 160, 64, 77),
@@ -156,6 +165,13 @@ def test_attention_sd_cross(b, heads, d, tq, tk):
     torch.cuda.synchronize()
     o = out.float().cpu().reshape(b, tq, heads, dp)
     _check(o[..., :d].reshape(b, tq, heads * d), ref, 2 ** -6, f"cross-attention b{b} d{d} tq{tq} tk{tk}")
+    kv4 = kv.view(b, 128, 2, heads, dp).clone()
+    kv4[:, :, 1, :, d] = 1.0
+    out1 = ops.attention_sd(qd, kv4.view(b, 128, -1).to(torch.bfloat16).to(DEV), b, heads, d, dp, tq, 128, tk, 0, 0, heads * dp,
+                            v_ones=True)
+    torch.cuda.synchronize()
+    o1 = out1.float().cpu().reshape(b, tq, heads, dp)
+    _check(o1[..., :d].reshape(b, tq, heads * d), ref, 2 ** -6, f"cross-attention (v_ones) b{b} d{d} tq{tq} tk{tk}")
 
 
 def test_cfg_ddim_step_bit_exact_vs_reference():

@@ -327,6 +327,340 @@ __global__ void __launch_bounds__(AT_THREADS, SdCfg<NC>::MIN_CTAS) attention_sd_
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// Experiment (off by default, ADB_ATTN_SD_V2=1; parity-tested): TWO softmax warp groups per CTA, each owning every other key tile with its own S buffer and
+// its own output accumulator (split-KV inside the CTA). Measured on the kernel above at T = 4096, d = 40: XU pipe
+// 48 % busy, issue slots 55 %, top stalls fixed-latency waits and TMEM round trips - with 2 softmax warps per
+// scheduler the exp pipe starves on latency, not on throughput. Here
+//   * warps 0-3 take tiles 0, 2, 4, ... (S0 / P0, accumulator O0), warps 6-9 tiles 1, 3, 5, ... (S1 / P1, O1): the
+//     groups never exchange anything per tile - each keeps its own running maximum - and the two partial results
+//     are merged once at the end: out = (f0 O0 + f1 O1) / (f0 l0 + f1 l1), f_g = 2^(m_g - max(m0, m1));
+//   * S is read from TMEM twice (maximum pass, exponential pass) in 32-column halves, so a softmax thread holds 32
+//     scores instead of 64: 320 threads x 2 CTAs fit the register file, 4 softmax warps per scheduler.
+// TMEM columns: S0 [0,64) | S1 [64,128) | O0 [128, 128+DP) | O1 [128+DP, 128+2DP). Barrier protocol as above (the
+// per-buffer P_FULL / PV_DONE barriers were already indexed by tile parity = group).
+template <int NC>
+struct Sd2Cfg {
+  static constexpr int STAGES = (NC == 1) ? 4 : 3;
+  static constexpr int Q_BYTES = NC * Q_CHUNK_BYTES;
+  static constexpr int STAGE_BYTES = 2 * NC * KV_CHUNK_BYTES;
+  static constexpr int SMEM_BYTES = Q_BYTES + STAGES * STAGE_BYTES + 1024;
+  static constexpr int TMEM_COLS = (O_COL + 2 * NC * CH <= 256) ? 256 : 512;
+  static constexpr int MIN_CTAS = (NC == 1) ? 2 : 1;
+};
+constexpr int AT2_THREADS = 320;
+
+template <int NC, bool ONES>
+__global__ void __launch_bounds__(AT2_THREADS, Sd2Cfg<NC>::MIN_CTAS) attention_sd2_kernel(const __grid_constant__ AttnSdParams p) {
+  using C = Sd2Cfg<NC>;
+  constexpr int STAGES = C::STAGES;
+  constexpr int B_Q = 0;
+  constexpr int B_KV_FULL = 1;
+  constexpr int B_KV_EMPTY = B_KV_FULL + STAGES;
+  constexpr int B_S_FULL = B_KV_EMPTY + STAGES;
+  constexpr int B_P_FULL = B_S_FULL + 2;
+  constexpr int B_PV_DONE = B_P_FULL + 2;
+  constexpr int B_MERGE = B_PV_DONE + 2;
+  constexpr int NUM_BARS = B_MERGE + 1;
+  constexpr int DP = NC * CH;
+
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t bars[NUM_BARS];
+  __shared__ uint32_t tmem_slot_s;
+  __shared__ float merge_m[BM], merge_l[BM];  // group 1's running maximum / denominator per row
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t q_smem = smem_base;
+  auto k_smem = [&](int st) { return smem_base + C::Q_BYTES + st * C::STAGE_BYTES; };
+  auto v_smem = [&](int st) { return k_smem(st) + NC * KV_CHUNK_BYTES; };
+  const uint32_t bar0 = smem_u32(bars);
+  auto bar = [&](int i) { return bar0 + 8u * i; };
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int bh = blockIdx.y;
+  const int b = bh / p.heads;
+  const int h = bh - b * p.heads;
+  const int q0 = blockIdx.x * BM;
+  const int qrow_base = b * p.tq;
+  const int krow_base = b * p.tk_rows;
+  const int qc = p.q_col0 + h * DP;
+  const int kc = p.k_col0 + h * DP;
+  const int vc = p.v_col0 + h * DP;
+  const int nkt = (p.tk_valid + KT - 1) / KT;
+
+  if (warp == 4 && lane == 0) {
+    tma_prefetch_desc(&p.tmQ);
+    tma_prefetch_desc(&p.tmKV);
+    for (int i = 0; i < NUM_BARS; ++i)
+      mbar_init(bar(i), (i == B_P_FULL || i == B_P_FULL + 1 || i == B_MERGE) ? 4 : 1);
+    fence_mbar_init();
+  }
+  if (warp == 5) {
+    tmem_alloc(smem_u32(&tmem_slot_s), C::TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(&tmem_slot_s);
+
+  if (warp == 4) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      mbar_arrive_expect_tx(bar(B_Q), C::Q_BYTES);
+#pragma unroll
+      for (int c = 0; c < NC; ++c) tma_load_2d(q_smem + c * Q_CHUNK_BYTES, &p.tmQ, bar(B_Q), qc + c * CH, qrow_base + q0);
+      for (int j = 0; j < nkt; ++j) {
+        const int st = j % STAGES;
+        const uint32_t use = (uint32_t)(j / STAGES);
+        mbar_wait(bar(B_KV_EMPTY + st), (use & 1u) ^ 1u);
+        mbar_arrive_expect_tx(bar(B_KV_FULL + st), C::STAGE_BYTES);
+#pragma unroll
+        for (int c = 0; c < NC; ++c) {
+          tma_load_2d(k_smem(st) + c * KV_CHUNK_BYTES, &p.tmKV, bar(B_KV_FULL + st), kc + c * CH, krow_base + j * KT);
+          tma_load_2d(v_smem(st) + c * KV_CHUNK_BYTES, &p.tmKV, bar(B_KV_FULL + st), vc + c * CH, krow_base + j * KT);
+        }
+      }
+    }
+  } else if (warp == 5) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      constexpr uint32_t idesc_s = umma_idesc_bf16(BM, KT, 0, 0);
+      constexpr uint32_t idesc_o = umma_idesc_bf16(BM, CH, 0, 1);
+      const uint32_t idesc_o_last = umma_idesc_bf16(BM, p.n_last, 0, 1);
+      auto issue_s = [&](int j) {
+        const int st = j % STAGES;
+        mbar_wait(bar(B_KV_FULL + st), (uint32_t)(j / STAGES) & 1u);
+        tc_fence_after();
+        for (int kk = 0; kk < p.ksteps; ++kk) {
+          const int c = kk >> 2, w = kk & 3;
+          const uint64_t a_desc = umma_desc_kmajor_sw128(q_smem + c * Q_CHUNK_BYTES) + 2u * w;
+          const uint64_t b_desc = umma_desc_kmajor_sw128(k_smem(st) + c * KV_CHUNK_BYTES) + 2u * w;
+          umma_bf16_ss(tmem_base + (j & 1) * KT, a_desc, b_desc, idesc_s, kk != 0);
+        }
+        umma_commit(bar(B_S_FULL + (j & 1)));
+      };
+      mbar_wait(bar(B_Q), 0);
+      issue_s(0);
+      for (int j = 0; j < nkt; ++j) {
+        if (j + 1 < nkt) issue_s(j + 1);  // S buffer (j+1)&1 last held P_{j-1}, consumed by PV_{j-1} issued one iteration ago
+        const int st = j % STAGES;
+        mbar_wait(bar(B_P_FULL + (j & 1)), (uint32_t)(j >> 1) & 1u);
+        tc_fence_after();
+        const uint32_t o_base = tmem_base + O_COL + (j & 1) * DP;  // the group's own accumulator
+#pragma unroll
+        for (int c = 0; c < NC; ++c) {
+          const uint32_t idesc = (c == NC - 1) ? idesc_o_last : idesc_o;
+#pragma unroll
+          for (int kk = 0; kk < KT / 16; ++kk) {
+            const uint64_t b_desc = umma_desc_mnmajor_sw128(v_smem(st) + c * KV_CHUNK_BYTES + kk * 2048, 1024);
+            umma_bf16_ts(o_base + c * CH, tmem_base + (j & 1) * KT + 8 * kk, b_desc, idesc, ((j >> 1) | kk) != 0);
+          }
+        }
+        umma_commit(bar(B_KV_EMPTY + st));
+        umma_commit(bar(B_PV_DONE + (j & 1)));
+      }
+    }
+  } else {
+    // ===================== softmax groups: warps 0-3 (even tiles), warps 6-9 (odd tiles) =====================
+    const int grp = warp >= 6 ? 1 : 0;
+    const int quarter = warp & 3;  // TMEM lane quarter this warp may access
+    const int row = quarter * 32 + lane;
+    const uint32_t lane_addr = tmem_base + ((uint32_t)(quarter * 32) << 16);
+    const uint32_t s_addr = lane_addr + grp * KT;
+    const uint32_t o_addr = lane_addr + O_COL + grp * DP;
+    const float sc = p.sc;
+    const int ocols = (NC - 1) * CH + p.n_last;
+    float m_run = -INFINITY;
+    float l_run = 0.f;
+    int j_last = -1;
+    for (int j = grp; j < nkt; j += 2) {
+      j_last = j;
+      mbar_wait(bar(B_S_FULL + grp), (uint32_t)(j >> 1) & 1u);
+      tc_fence_after();
+      const int kvalid = p.tk_valid - j * KT;  // warp-uniform
+      // ---- pass 1: row maximum, 32 columns at a time ----
+      float mx;
+      {
+        uint32_t sr[32];
+        float mxs[4];
+        tmem_ld_32x32b_x32(s_addr, sr);
+        tmem_wait_ld();
+        if (kvalid < 32) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            if (i >= kvalid) sr[i] = 0xff800000u;
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) mxs[i] = fmax3(__uint_as_float(sr[i]), __uint_as_float(sr[4 + i]), __uint_as_float(sr[8 + i]));
+#pragma unroll
+        for (int i = 0; i < 4; ++i) mxs[i] = fmax3(mxs[i], __uint_as_float(sr[12 + i]), __uint_as_float(sr[16 + i]));
+#pragma unroll
+        for (int i = 0; i < 4; ++i) mxs[i] = fmax3(mxs[i], __uint_as_float(sr[20 + i]), __uint_as_float(sr[24 + i]));
+#pragma unroll
+        for (int i = 0; i < 4; ++i) mxs[i] = fmaxf(mxs[i], __uint_as_float(sr[28 + i]));
+        tmem_ld_32x32b_x32(s_addr + 32, sr);
+        tmem_wait_ld();
+        if (kvalid < KT) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            if (32 + i >= kvalid) sr[i] = 0xff800000u;
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) mxs[i] = fmax3(mxs[i], __uint_as_float(sr[i]), __uint_as_float(sr[4 + i]));
+#pragma unroll
+        for (int i = 0; i < 4; ++i) mxs[i] = fmax3(mxs[i], __uint_as_float(sr[8 + i]), __uint_as_float(sr[12 + i]));
+#pragma unroll
+        for (int i = 0; i < 4; ++i) mxs[i] = fmax3(mxs[i], __uint_as_float(sr[16 + i]), __uint_as_float(sr[20 + i]));
+#pragma unroll
+        for (int i = 0; i < 4; ++i) mxs[i] = fmax3(mxs[i], __uint_as_float(sr[24 + i]), __uint_as_float(sr[28 + i]));
+        mx = fmaxf(fmaxf(mxs[0], mxs[1]), fmaxf(mxs[2], mxs[3]));
+      }
+      const float m_tile = mx * sc;
+      const bool jump = m_tile > m_run + 8.0f;
+      float alpha = 1.0f;
+      float m_new = m_run;
+      if (__any_sync(0xffffffffu, jump)) {
+        m_new = fmaxf(m_run, m_tile);
+        alpha = ex2_approx_sd(m_run - m_new);
+        if (j >= 2) {
+          // this group's previous product PV_{j-2}: the latest commit on its barrier (PV_j needs the P written below)
+          mbar_wait(bar(B_PV_DONE + grp), (uint32_t)((j - 2) >> 1) & 1u);
+          tc_fence_after();
+#pragma unroll 1
+          for (int c = 0; c < DP; c += 32) {
+            if (c >= ocols) break;
+            uint32_t v[32];
+            tmem_ld_32x32b_x32(o_addr + c, v);
+            tmem_wait_ld();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) * alpha);
+            tmem_st_32x32b_x32(o_addr + c, v);
+          }
+        }
+      }
+      // ---- pass 2: probabilities, 32 keys at a time; bf16 P for keys [32 hf, +32) goes to columns [16 hf, +16) of the
+      // S buffer - below column 32, so the second half of S is still intact when it is read ----
+      float ps = 0.f;
+#pragma unroll
+      for (int hf = 0; hf < 2; ++hf) {
+        uint32_t sr[32];
+        tmem_ld_32x32b_x32(s_addr + 32 * hf, sr);
+        tmem_wait_ld();
+        if (kvalid < KT) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            if (32 * hf + i >= kvalid) sr[i] = 0xff800000u;
+        }
+        uint32_t pk[16];
+        float pa = 0.f, pb = 0.f;
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          const float p0 = ex2_approx_sd(fmaf(__uint_as_float(sr[2 * i]), sc, -m_new));
+          const float p1 = ex2_approx_sd(fmaf(__uint_as_float(sr[2 * i + 1]), sc, -m_new));
+          if (!ONES) {
+            pa += p0;
+            pb += p1;
+          }
+          pk[i] = pack_bf16x2(p0, p1);
+        }
+        tmem_st_32x32b_x16(s_addr + 16 * hf, pk);
+        ps += pa + pb;
+      }
+      if (!ONES) l_run = l_run * alpha + ps;
+      m_run = m_new;
+      tmem_wait_st();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar(B_P_FULL + grp));
+    }
+    if (j_last >= 0) {
+      mbar_wait(bar(B_PV_DONE + grp), (uint32_t)(j_last >> 1) & 1u);  // this group's accumulator is final
+      tc_fence_after();
+    }
+    auto read_l = [&](uint32_t oa) -> float {  // ONES: the denominator the tensor core accumulated in O[:, d_head]
+      uint32_t lv[16];
+      tmem_ld_32x32b_x16(oa + (p.d_head & ~15), lv);
+      tmem_wait_ld();
+      float l = __uint_as_float(lv[0]);
+#pragma unroll
+      for (int i = 1; i < 16; ++i)
+        if (i == (p.d_head & 15)) l = __uint_as_float(lv[i]);
+      return l;
+    };
+    if (grp == 1) {
+      // publish (m1, l1) and leave; group 0 merges. With a single key tile there is nothing here: m1 = -inf.
+      if (ONES && j_last >= 0) l_run = read_l(o_addr);
+      merge_m[row] = m_run;
+      merge_l[row] = l_run;
+      __threadfence_block();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar(B_MERGE));
+    } else {
+      if (ONES) l_run = read_l(o_addr);
+      mbar_wait(bar(B_MERGE), 0);
+      const float m1 = merge_m[row];
+      const float l1 = merge_l[row];
+      const bool has1 = nkt >= 2;  // uniform: O1 was written at all
+      const float m = fmaxf(m_run, m1);
+      const float f0 = ex2_approx_sd(m_run - m);
+      const float f1 = has1 ? ex2_approx_sd(m1 - m) : 0.f;
+      const float inv = 1.0f / (f0 * l_run + (has1 ? f1 * l1 : 0.f));
+      const float w0 = f0 * inv, w1 = f1 * inv;
+      const bool ok = (q0 + row) < p.tq;
+      __nv_bfloat16* orow = p.out + ((size_t)(qrow_base + q0 + row)) * ((size_t)p.heads * DP) + h * DP;
+#pragma unroll 1
+      for (int c = 0; c < DP; c += 16) {  // 16 columns at a time: the merge must fit the 96-register budget
+        uint32_t v[16], u[16];
+        if (c < ocols) {
+          tmem_ld_32x32b_x16(o_addr + c, v);
+          if (has1) tmem_ld_32x32b_x16(o_addr + DP + c, u);
+          tmem_wait_ld();
+        }
+        uint32_t ow[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          float a0 = 0.f, a1 = 0.f;
+          if (c + 2 * i < p.d_head) {
+            a0 = __uint_as_float(v[2 * i]) * w0;
+            if (has1) a0 = fmaf(__uint_as_float(u[2 * i]), w1, a0);
+          }
+          if (c + 2 * i + 1 < p.d_head) {
+            a1 = __uint_as_float(v[2 * i + 1]) * w0;
+            if (has1) a1 = fmaf(__uint_as_float(u[2 * i + 1]), w1, a1);
+          }
+          ow[i] = pack_bf16x2(a0, a1);
+        }
+        if (ok) {
+          *reinterpret_cast<uint4*>(orow + c) = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+          *reinterpret_cast<uint4*>(orow + c + 8) = make_uint4(ow[4], ow[5], ow[6], ow[7]);
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 5) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, C::TMEM_COLS);
+  }
+}
+
+template <int NC, bool ONES>
+int launch_attn_sd2(const AttnSdParams& ap, int b, cudaStream_t stream) {
+  using C = Sd2Cfg<NC>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    ADB_CUDA(cudaFuncSetAttribute(attention_sd2_kernel<NC, ONES>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+    attr_set = true;
+  }
+  dim3 grid((ap.tq + BM - 1) / BM, b * ap.heads);
+  attention_sd2_kernel<NC, ONES><<<grid, AT2_THREADS, C::SMEM_BYTES, stream>>>(ap);
+  ADB_CUDA(cudaGetLastError());
+  return 1;
+}
+
 template <int NC, bool ONES, bool POLY>
 int launch_attn_sd(const AttnSdParams& ap, int b, cudaStream_t stream) {
   using C = SdCfg<NC>;
@@ -397,6 +731,26 @@ int attention_sd_submit(adb_plan* plan, const adb_attn_sd_desc* d, cudaStream_t 
     poly_on = (e && e[0] == '1') ? 1 : 0;
   }
   const int poly = (ones && poly_on && d->tk_valid >= 1024) ? 1 : 0;
+  // ADB_ATTN_SD_V2=1 selects the two-group kernel. Measured (batch 64, T = 4096, d = 40): 3.52 ms vs 3.37-3.59 ms for the
+  // single-group kernel - both sit at 64 % of the XU (MUFU.EX2) pipe's peak with the SMs fully active and L2 at 20 %;
+  // doubling the softmax warps per scheduler did not move it, so the single-group kernel stays the default.
+  static int gen2 = -1;
+  if (gen2 < 0) {
+    const char* e = getenv("ADB_ATTN_SD_V2");
+    gen2 = (e && e[0] == '1') ? 1 : 0;
+  }
+  if (gen2 && !poly) {
+    return submit(plan, stream, "attention_sd", flops, 0.0, [ap, b, nc, ones](cudaStream_t s) -> int {
+      switch (nc * 2 + ones) {
+        case 2: return launch_attn_sd2<1, false>(ap, b, s);
+        case 3: return launch_attn_sd2<1, true>(ap, b, s);
+        case 4: return launch_attn_sd2<2, false>(ap, b, s);
+        case 5: return launch_attn_sd2<2, true>(ap, b, s);
+        case 6: return launch_attn_sd2<3, false>(ap, b, s);
+        default: return launch_attn_sd2<3, true>(ap, b, s);
+      }
+    });
+  }
   return submit(plan, stream, "attention_sd", flops, 0.0, [ap, b, nc, ones, poly](cudaStream_t s) -> int {
     switch (nc * 4 + ones * 2 + poly) {
       case 4: return launch_attn_sd<1, false, false>(ap, b, s);

@@ -772,6 +772,16 @@ int launch(const ConvKParams& kp, cudaStream_t stream) {
 int conv_block_n(int cout) {
   if (cout % 192 == 0) return 192;
   if (cout % 256 == 0) return 256;
+  // 320-channel layers (Stable Diffusion): two 160-wide CTA-pair tiles cover them exactly; the 192-wide tile would
+  // compute 384 columns (17 % wasted MMA work). ADB_CONV_NO160=1 restores the padded tiling (A/B testing).
+  if (cout % 160 == 0 && cout % 128 != 0) {
+    static int no160 = -1;
+    if (no160 < 0) {
+      const char* e = getenv("ADB_CONV_NO160");
+      no160 = (e && e[0] == '1') ? 1 : 0;
+    }
+    if (!no160) return 160;
+  }
   if (cout % 128 == 0) return 128;
   if (cout <= 16) return 16;
   if (cout <= 64) return 64;
@@ -792,7 +802,7 @@ int conv_ncta(int block_n) {
     const char* e = getenv("ADB_CONV_1CTA");
     force1 = (e && e[0] == '1') ? 1 : 0;
   }
-  if (block_n == 256) return 2;
+  if (block_n == 256 || block_n == 160) return 2;
   return (block_n == 192 && !force1) ? 2 : 1;
 }
 
@@ -924,6 +934,7 @@ int conv_igemm_submit(adb_plan* plan, const adb_conv_desc* d, cudaStream_t strea
     switch (block_n) {
       case 256: return launch<256, 2>(kp, s);
       case 192: return ncta == 2 ? launch<192, 2>(kp, s) : launch<192, 1>(kp, s);
+      case 160: return launch<160, 2>(kp, s);
       case 128: return launch<128, 1>(kp, s);
       case 64: return launch<64, 1>(kp, s);
       default: return launch<16, 1>(kp, s);

@@ -176,7 +176,7 @@ class CandidateEvaluator:
                  batch_size: int = 100, num_samples: int = 1000, image_size: int = 64, class_cond: bool = True,
                  clip_denoised: bool = True, cond_fn: Optional[Callable] = None, seed: int = 0,
                  rank: Optional[int] = None, world_size: Optional[int] = None, group=None, max_cached_plans: int = 8,
-                 fid_method: str = "sqrtm", fid_threads: Optional[int] = None, shard_fid: bool = True):
+                 fid_method: str = "eigh", fid_threads: Optional[int] = None, shard_fid: bool = True):
         self.model = model
         self.base_diffusion = base_diffusion
         self.feature_fn = feature_fn
@@ -197,7 +197,12 @@ class CandidateEvaluator:
         self._fid_pool: Optional[ThreadPoolExecutor] = None
         self._host_bufs: list = []
         assert fid_method in ("sqrtm", "eigh")
-        self.fid_method = fid_method  # "sqrtm": the reference's arithmetic; "eigh": frechet_distance_eigh
+        # "eigh" (default): frechet_distance_eigh - the same statistic through a symmetric eigenproblem, equal to the
+        # reference's sqrtm arithmetic to rounding (tests/test_evaluator_cpu.py; 4+ decimals on the d = 2048 population
+        # runs under profiles/) and ~30x cheaper on the host. "sqrtm": scipy.linalg.sqrtm exactly as the reference
+        # (evaluator_v1.py:114-157); its Python-level Schur loops hold the GIL and were measured to stretch the
+        # sampling thread's plan building 8x when run beside it.
+        self.fid_method = fid_method
         self._ref_sqrt = None
         # BLAS threads for the host-side FID. torchrun exports OMP_NUM_THREADS=1, which would make the 2048x2048
         # sqrtm take ~10 s; the worker lifts the limit for its own calls (threadpoolctl) to this many threads.
@@ -250,7 +255,16 @@ class CandidateEvaluator:
             vals = t.cpu().tolist()
         return vals
 
-    def submit_cand_fid(self, cand=None, args=None) -> Future:
+    def evaluate_population(self, cands, args=None) -> list:
+        """FID of every candidate in `cands`, on every rank, with the POPULATION sharded over ranks: candidate i is
+        sampled (all of its batches), reduced and scored by rank i % world alone - no per-candidate collective, plan
+        building and the host-side sqrtm parallelise with the sampling - and the values are exchanged by one
+        all-reduce of len(cands) doubles at the end. Images are those of the batch-sharded path (seeds depend on
+        (seed, candidate, batch index) only). Every rank must pass the same list."""
+        futures = [self.submit_cand_fid(c, args, _whole_on=i % self.world_size) for i, c in enumerate(cands)]
+        return self.resolve(futures)
+
+    def submit_cand_fid(self, cand=None, args=None, _whole_on: Optional[int] = None) -> Future:
         """Same work as `get_cand_fid`, but only the device part (sampling, moments, all-reduce, D2H of the
         33.6 MB moment buffer) happens before this returns; mu / sigma / sqrtm run on a host worker thread.
         The search driver keeps sampling the next candidate meanwhile (`fid_time` was serial in the
@@ -259,6 +273,9 @@ class CandidateEvaluator:
             for k in ("batch_size", "num_samples", "image_size", "class_cond", "clip_denoised"):
                 if hasattr(args, k):
                     setattr(self, k, getattr(args, k))
+        if _whole_on is not None and _whole_on != self.rank:  # another rank evaluates this candidate entirely
+            self.last_times = dict(reset_time=0.0, sample_time=0.0, fid_time=0.0)
+            return _RemoteFid(_whole_on)
         t0 = time.time()
         plan = self._plan_for(cand, self.batch_size)
         reset_time = time.time() - t0
@@ -266,7 +283,8 @@ class CandidateEvaluator:
         cand_key = str(cand)
         num_batches = (self.num_samples + self.batch_size - 1) // self.batch_size
         acc = None
-        for b in shard_batches(num_batches, self.rank, self.world_size):
+        my_batches = range(num_batches) if _whole_on is not None else shard_batches(num_batches, self.rank, self.world_size)
+        for b in my_batches:
             images, _ = self.sample_batch(plan, cand_key, b)
             keep = min(self.batch_size, self.num_samples - b * self.batch_size)  # arr[:num_samples], :432-433
             feats = self.feature_fn(images[:keep])
@@ -282,10 +300,11 @@ class CandidateEvaluator:
                 self._acc = MomentAccumulator(dim, self.model._device())
             acc = self._acc
             acc.reset()
-        acc.all_reduce(self.group)
+        if _whole_on is None:
+            acc.all_reduce(self.group)
         seq = self._seq
         self._seq += 1
-        if self.shard_fid and self.world_size > 1 and seq % self.world_size != self.rank:
+        if _whole_on is None and self.shard_fid and self.world_size > 1 and seq % self.world_size != self.rank:
             th.cuda.current_stream().synchronize() if acc.buf.is_cuda else None
             self.last_times = dict(reset_time=reset_time, sample_time=time.time() - t0, fid_time=0.0)
             return _RemoteFid(seq % self.world_size)

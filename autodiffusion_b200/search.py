@@ -58,7 +58,7 @@ class EvolutionSearcher:
     def __init__(self, args, model, base_diffusion, time_step, classifier=None, index_step=None, *,
                  feature_fn: Optional[Callable] = None, ref_stats: Optional[FIDStatistics] = None,
                  evaluator: Optional[CandidateEvaluator] = None, log: Callable[[str], None] = print,
-                 defer_fid: bool = True):
+                 defer_fid: bool = True, shard_population: Optional[bool] = None):
         """`args` carries the reference's flags (:722-752): max_epochs, select_num, population_num, m_prob,
         crossover_num, mutation_num, max_prun, min_prun, batch_size, num_samples, image_size, class_cond,
         clip_denoised, classifier_scale, use_ddim, use_ddim_init_x, time_step.
@@ -92,7 +92,10 @@ class EvolutionSearcher:
         self.last_best_cand = None
         self.log = log
         self.defer_fid = defer_fid
+        # more than one rank: whole candidates (not batches of one candidate) are dealt to ranks, SURVEY §8(e)
+        self.shard_population = shard_population
         self._pending: Dict[str, Future] = {}
+        self._queued: Dict[str, object] = {}
         if not getattr(args, "use_ddim", True):
             raise NotImplementedError("the evaluator path covers DDIM sampling (use_ddim=True), as every search script sets")
         if evaluator is None:
@@ -107,6 +110,8 @@ class EvolutionSearcher:
                 image_size=args.image_size, class_cond=getattr(args, "class_cond", True),
                 clip_denoised=getattr(args, "clip_denoised", True), cond_fn=cond_fn, seed=getattr(args, "seed", 0))
         self.evaluator = evaluator
+        if self.shard_population is None:
+            self.shard_population = getattr(evaluator, "world_size", 1) > 1
 
     # ---- genome <-> flat index list (kept for parity with :206-217; used by predictor-based variants) ----
     def cand2gen(self, cand):
@@ -129,7 +134,9 @@ class EvolutionSearcher:
             self.log("cand: {} has visited!".format(cand))
             return False
         parsed = ast.literal_eval(cand)
-        if self.defer_fid and callable(getattr(self.evaluator, "submit_cand_fid", None)):
+        if self.defer_fid and self.shard_population and callable(getattr(self.evaluator, "evaluate_population", None)):
+            self._queued[cand] = parsed  # sampled at join(): the generation's candidates are dealt to the ranks
+        elif self.defer_fid and callable(getattr(self.evaluator, "submit_cand_fid", None)):
             self._pending[cand] = self.evaluator.submit_cand_fid(cand=parsed, args=self.args)
         else:
             info["fid"] = self.evaluator.get_cand_fid(cand=parsed, args=self.args)
@@ -142,6 +149,12 @@ class EvolutionSearcher:
 
     def join(self):
         """Resolve every deferred FID (in submission order) and emit its log line."""
+        if self._queued:
+            fids = self.evaluator.evaluate_population(list(self._queued.values()), self.args)
+            for cand, fid in zip(list(self._queued), fids):
+                self.vis_dict[cand]["fid"] = fid
+                self.log("cand: {}, fid: {}".format(cand, fid))
+            self._queued.clear()
         resolve = getattr(self.evaluator, "resolve", None)
         fids = resolve(list(self._pending.values())) if callable(resolve) else [f.result() for f in self._pending.values()]
         for (cand, fut), fid in zip(list(self._pending.items()), fids):

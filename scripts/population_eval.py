@@ -69,6 +69,10 @@ def main():
     ap.add_argument("--feature_dim", type=int, default=2048)
     ap.add_argument("--seed", type=int, default=0)
     ap.add_argument("--small", action="store_true", help="64-channel 1-res-block UNet (functional check)")
+    ap.add_argument("--shard", default="candidates", choices=["candidates", "batches"],
+                    help="candidates: each rank evaluates whole candidates (no per-candidate collective); batches: every "
+                         "candidate's batches are split over ranks and its moments all-reduced")
+    ap.add_argument("--fid_method", default="eigh", choices=["sqrtm", "eigh"])
     ap.add_argument("--guided", action="store_true", help="classifier guidance (native depth-4 noisy classifier, scale 1.0)")
     args = ap.parse_args()
 
@@ -125,7 +129,7 @@ def main():
 
     ev = CandidateEvaluator(model, diffusion, feature_fn, ref_stats, batch_size=args.batch_size,
                             num_samples=args.num_samples, seed=args.seed, max_cached_plans=args.candidates + 1,
-                            cond_fn=cond_fn)
+                            cond_fn=cond_fn, fid_method=args.fid_method)
     rng = random.Random(args.seed)
     population = [draw_candidate(rng, args.time_step, model.layer_num, args.max_prun, args.mask_pool)
                   for _ in range(args.candidates)]
@@ -138,10 +142,10 @@ def main():
     t0 = time.time()
     t_sample, t_fid, t_plan = 0.0, 0.0, 0.0
     pending, times = [], []
-    for cand in population:  # the host-side FID of candidate i overlaps the sampling of candidate i+1
-        pending.append(ev.submit_cand_fid(cand))
+    for i, cand in enumerate(population):  # the host-side FID of candidate i overlaps the sampling of the next one
+        pending.append(ev.submit_cand_fid(cand, _whole_on=(i % world) if args.shard == "candidates" else None))
         times.append(ev.last_times)
-    fids = ev.resolve(pending)  # each rank finishes the host-side FID of every world-th candidate
+    fids = ev.resolve(pending)  # one all-reduce of the FID values
     for tm in times:
         t_plan += tm["reset_time"]
         t_sample += tm["sample_time"]
@@ -164,7 +168,7 @@ def main():
             "metric": "population evaluation, candidates/s", "value": n / wall, "unit": "candidates/s",
             "images_per_s": n * args.num_samples / wall, "n_gpus": world, "candidates": n,
             "num_samples": args.num_samples, "batch_size": args.batch_size, "ddim_steps": args.time_step,
-            "feature_dim": d, "wall_s": wall, "guided": bool(args.guided),
+            "feature_dim": d, "wall_s": wall, "guided": bool(args.guided), "shard": args.shard, "fid_method": args.fid_method,
             "split_s": {"plan_build": round(t_plan, 3), "sampling_plus_allreduce": round(t_sample, 3),
                         "host_sqrtm_fid_overlapped": round(t_fid, 3)},
             "fid_first3": [round(x, 4) for x in fids[:3]],

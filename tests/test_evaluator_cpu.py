@@ -105,6 +105,8 @@ def test_fid_statistics_matches_reference_fixture():
         a = FIDStatistics(*fid_ref.compute_statistics(g[f"{name}/f1"]))
         b = FIDStatistics(*fid_ref.compute_statistics(g[f"{name}/f2"]))
         assert abs(a.frechet_distance(b) - float(g[f"{name}/fid"])) <= 1e-6 * float(g[f"{name}/fid"])
+        # the evaluator's default (symmetric-eigenproblem form) against the same reference value
+        assert abs(a.frechet_distance_eigh(b) - float(g[f"{name}/fid"])) <= 1e-6 * float(g[f"{name}/fid"])
 
 
 def test_eigh_form_of_the_frechet_distance_matches_sqrtm():

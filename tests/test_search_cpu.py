@@ -94,6 +94,42 @@ def test_deferred_fids_change_nothing_but_when_the_fid_lines_appear():
     assert len(lines) == g["n_log"]
 
 
+class PopulationStub(StubEvaluator):
+    """An evaluator on more than one rank: whole candidates are dealt to ranks at join() (evaluate_population)."""
+    world_size = 2
+
+    def __init__(self):
+        super().__init__(True)
+        self.generations = []
+
+    def evaluate_population(self, cands, args=None):
+        self.generations.append(len(cands))
+        self.calls += [str(c) for c in cands]
+        return [stub_fid(c) for c in cands]
+
+    def submit_cand_fid(self, cand=None, args=None):
+        raise AssertionError("with population sharding nothing is sampled before join()")
+
+
+def test_population_sharding_visits_the_same_individuals():
+    """More than one rank: the search queues a generation's candidates and evaluates them as one sharded population;
+    the individuals visited, the top-k and the log are those of the serial reference run."""
+    g = json.load(open(os.path.join(GOLDEN, "search_trace.json")))["random_init"]
+    cfg = g["config"]
+    lines = []
+    ev = PopulationStub()
+    s = build(cfg, ev, lines.append)
+    assert s.shard_population
+    random.seed(cfg["seed"])
+    np.random.seed(cfg["seed"])
+    top = s.search()
+    assert list(s.vis_dict.keys()) == g["visited"] and top == g["top"]
+    assert ev.calls == g["visited"] and len(ev.generations) >= 2 and max(ev.generations) > 1
+    fid_lines = [l for l in lines if l.startswith("cand: ") and ", fid: " in l]
+    assert [l.split(", fid: ")[0][len("cand: "):] for l in fid_lines] == g["visited"]
+    assert len(lines) == g["n_log"]
+
+
 def test_save_and_resume(tmp_path):
     g = json.load(open(os.path.join(GOLDEN, "search_trace.json")))["random_init"]
     cfg = dict(g["config"])

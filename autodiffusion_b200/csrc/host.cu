@@ -126,6 +126,9 @@ int geglu_submit(adb_plan*, const void*, void*, int, int, cudaStream_t);
 int cfg_ddim_step_submit(adb_plan*, const float*, const float*, float*, float*, int, int, int, float, const float*,
                          cudaStream_t);
 int pad_context_submit(adb_plan*, const float*, void*, int, int, int, int, cudaStream_t);
+int cfg_combine_submit(adb_plan*, const float*, float*, size_t, int, float, cudaStream_t);
+int plms_update_submit(adb_plan*, const float*, const float*, const float*, const float*, const float*, int, const float*,
+                       float*, float*, size_t, cudaStream_t);
 
 }  // namespace adb
 
@@ -335,6 +338,15 @@ int adb_geglu(adb_plan* plan, const void* x, void* out, int rows, int inner, adb
 int adb_cfg_ddim_step(adb_plan* plan, const float* x, const float* eps, float* x_prev, float* pred_x0, int n,
                       int chw, int cfg, float scale, const float coef[4], adb_stream stream) {
   return cfg_ddim_step_submit(plan, x, eps, x_prev, pred_x0, n, chw, cfg, scale, coef, static_cast<cudaStream_t>(stream));
+}
+
+int adb_cfg_combine(adb_plan* plan, const float* eps, float* e_out, size_t total, int cfg, float scale, adb_stream stream) {
+  return cfg_combine_submit(plan, eps, e_out, total, cfg, scale, static_cast<cudaStream_t>(stream));
+}
+
+int adb_plms_update(adb_plan* plan, const float* x, const float* e_t, const float* o1, const float* o2, const float* o3,
+                    int mode, const float coef[4], float* x_prev, float* pred_x0, size_t total, adb_stream stream) {
+  return plms_update_submit(plan, x, e_t, o1, o2, o3, mode, coef, x_prev, pred_x0, total, static_cast<cudaStream_t>(stream));
 }
 
 int adb_pad_context(adb_plan* plan, const float* ctx, void* out, int n, int t, int c, int t_pad, adb_stream stream) {

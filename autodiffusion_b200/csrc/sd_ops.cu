@@ -124,6 +124,43 @@ __global__ void __launch_bounds__(256) cfg_ddim_step_kernel(const float* __restr
   }
 }
 
+// e_t = e_u + scale * (e_c - e_u) (plms.py:202-207 / ddim.py:187-190), kept as its own tensor for the multistep history
+__global__ void __launch_bounds__(256) cfg_combine_kernel(const float* __restrict__ eps, float* __restrict__ e_out,
+                                                          size_t total, int cfg, float scale) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    float e = eps[i];
+    if (cfg) e = __fadd_rn(e, __fmul_rn(scale, __fsub_rn(eps[total + i], e)));
+    e_out[i] = e;
+  }
+}
+
+// p_sample_plms after the model call (plms.py:241-257): e' from the eps history, then the eta = 0 DDIM update with e'.
+// mode 0: e' = e_t; 1: (e_t + o1) / 2 (o1 = e_t_next, pseudo improved Euler); 2: (3 e_t - o1) / 2;
+// 3: (23 e_t - 16 o1 + 5 o2) / 12; 4: (55 e_t - 59 o1 + 37 o2 - 9 o3) / 24 - each product, sum and division rounded
+// separately, left to right, as the reference's tensor expression evaluates.
+__global__ void __launch_bounds__(256) plms_update_kernel(const float* __restrict__ x, const float* __restrict__ e_t,
+                                                          const float* __restrict__ o1, const float* __restrict__ o2,
+                                                          const float* __restrict__ o3, int mode, CfgCoef cf,
+                                                          float* __restrict__ x_prev, float* __restrict__ pred_x0,
+                                                          size_t total) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    float e = e_t[i];
+    if (mode == 1) {
+      e = __fdiv_rn(__fadd_rn(e, o1[i]), 2.0f);
+    } else if (mode == 2) {
+      e = __fdiv_rn(__fsub_rn(__fmul_rn(3.0f, e), o1[i]), 2.0f);
+    } else if (mode == 3) {
+      e = __fdiv_rn(__fadd_rn(__fsub_rn(__fmul_rn(23.0f, e), __fmul_rn(16.0f, o1[i])), __fmul_rn(5.0f, o2[i])), 12.0f);
+    } else if (mode == 4) {
+      const float a = __fsub_rn(__fmul_rn(55.0f, e), __fmul_rn(59.0f, o1[i]));
+      e = __fdiv_rn(__fsub_rn(__fadd_rn(a, __fmul_rn(37.0f, o2[i])), __fmul_rn(9.0f, o3[i])), 24.0f);
+    }
+    const float x0 = __fdiv_rn(__fsub_rn(x[i], __fmul_rn(cf.v[0], e)), cf.v[1]);
+    x_prev[i] = __fadd_rn(__fmul_rn(cf.v[2], x0), __fmul_rn(cf.v[3], e));
+    if (pred_x0 != nullptr) pred_x0[i] = x0;
+  }
+}
+
 __global__ void __launch_bounds__(256) pad_context_kernel(const float* __restrict__ ctx, __nv_bfloat16* __restrict__ out,
                                                           int n, int t, int c, int t_pad) {
   const size_t total = (size_t)n * t_pad * c;
@@ -185,6 +222,29 @@ int cfg_ddim_step_submit(adb_plan* plan, const float* x, const float* eps, float
   const double bytes = 4.0 * (double)total * (cfg ? 4.0 : 3.0);
   return submit(plan, stream, "cfg_ddim_step", 0.0, bytes, [=](cudaStream_t s) -> int {
     cfg_ddim_step_kernel<<<grid_for(total, 256), 256, 0, s>>>(x, eps, x_prev, pred_x0, total, cfg, scale, cf);
+    ADB_CUDA(cudaGetLastError());
+    return 1;
+  });
+}
+
+int cfg_combine_submit(adb_plan* plan, const float* eps, float* e_out, size_t total, int cfg, float scale,
+                       cudaStream_t stream) {
+  ADB_REQUIRE(eps && e_out && total > 0, "cfg_combine: bad arguments");
+  return submit(plan, stream, "cfg_combine", 0.0, 4.0 * (double)total * (cfg ? 3.0 : 2.0), [=](cudaStream_t s) -> int {
+    cfg_combine_kernel<<<grid_for(total, 256), 256, 0, s>>>(eps, e_out, total, cfg, scale);
+    ADB_CUDA(cudaGetLastError());
+    return 1;
+  });
+}
+
+int plms_update_submit(adb_plan* plan, const float* x, const float* e_t, const float* o1, const float* o2, const float* o3,
+                       int mode, const float coef[4], float* x_prev, float* pred_x0, size_t total, cudaStream_t stream) {
+  ADB_REQUIRE(x && e_t && x_prev && coef && total > 0 && mode >= 0 && mode <= 4, "plms_update: bad arguments");
+  ADB_REQUIRE((mode < 1 || o1) && (mode < 3 || o2) && (mode < 4 || o3), "plms_update: mode %d needs more eps history", mode);
+  CfgCoef cf;
+  for (int i = 0; i < 4; ++i) cf.v[i] = coef[i];
+  return submit(plan, stream, "plms_update", 0.0, 4.0 * (double)total * (3.0 + (mode > 1 ? mode - 1 : mode)), [=](cudaStream_t s) -> int {
+    plms_update_kernel<<<grid_for(total, 256), 256, 0, s>>>(x, e_t, o1, o2, o3, mode, cf, x_prev, pred_x0, total);
     ADB_CUDA(cudaGetLastError());
     return 1;
   });

@@ -36,7 +36,7 @@ __all__ = [
     "attention_backward", "gn_backward", "pool_prepare", "pool_attention", "pool_attention_backward", "pool_merge",
     "logsoftmax_grad", "pack_conv_weight_dgrad", "pack_linear_weight_split", "linear_tc",
     "pack_stem_weight", "stem_conv_tc",
-    "attention_sd", "layernorm", "geglu", "cfg_ddim_step", "pad_context",
+    "attention_sd", "layernorm", "geglu", "cfg_ddim_step", "pad_context", "cfg_combine", "plms_update",
 ]
 
 
@@ -718,3 +718,34 @@ def pad_context(ctx: torch.Tensor, t_pad: int, out: Optional[torch.Tensor] = Non
     if plan is not None:
         plan.keep(ctx, out)
     return out
+
+
+def cfg_combine(eps: torch.Tensor, scale: float = 1.0, cfg: bool = False, out: Optional[torch.Tensor] = None,
+                plan: Optional[Plan] = None) -> torch.Tensor:
+    """e_t = e_u + scale * (e_c - e_u) from eps = [uncond | cond] (cfg) or a copy of eps: PLMS keeps it as history."""
+    total = eps.numel() // (2 if cfg else 1)
+    if out is None:
+        out = torch.empty((eps.shape[0] // (2 if cfg else 1),) + tuple(eps.shape[1:]), dtype=torch.float32, device=eps.device)
+    assert out.numel() == total
+    _lib.check(_lib.lib().adb_cfg_combine(_ph(plan), _dev(eps, "eps", torch.float32), _dev(out, "out", torch.float32), total,
+                                          int(bool(cfg)), float(scale), _stream()), "adb_cfg_combine")
+    if plan is not None:
+        plan.keep(eps, out)
+    return out
+
+
+def plms_update(x: torch.Tensor, e_t: torch.Tensor, old: Sequence[torch.Tensor], mode: int, coef: Sequence[float],
+                x_prev: Optional[torch.Tensor] = None, pred_x0: Optional[torch.Tensor] = None,
+                plan: Optional[Plan] = None) -> torch.Tensor:
+    """p_sample_plms after the model call (include/adb200.h: adb_plms_update). old = (newest, ..., oldest) eps tensors;
+    for mode 1 old[0] is e_t_next."""
+    if x_prev is None:
+        x_prev = torch.empty_like(x)
+    o = [(_dev(t, "old", torch.float32) if t is not None else None) for t in (list(old) + [None] * 3)[:3]]
+    cf = (C.c_float * 4)(*[float(v) for v in coef])
+    _lib.check(_lib.lib().adb_plms_update(_ph(plan), _dev(x, "x", torch.float32), _dev(e_t, "e_t", torch.float32), o[0], o[1], o[2],
+                                          int(mode), cf, _dev(x_prev, "x_prev", torch.float32),
+                                          _opt(pred_x0, "pred_x0", torch.float32), x.numel(), _stream()), "adb_plms_update")
+    if plan is not None:
+        plan.keep(x, e_t, *[t for t in old if t is not None], x_prev, pred_x0)
+    return x_prev

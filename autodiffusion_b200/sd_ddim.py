@@ -82,11 +82,13 @@ class CandidatePlan:
     CFG + DDIM update written back into both halves of the UNet's input buffer."""
 
     def __init__(self, unet: UNetModel, alphas_cumprod: th.Tensor, sampled_timestep: Sequence[int], batch: int, shape,
-                 scale: float, cfg: bool, ctx_tokens: int = 77, use_graph: Optional[bool] = None):
+                 scale: float, cfg: bool, ctx_tokens: int = 77, use_graph: Optional[bool] = None, method: str = "ddim"):
         dev = unet._device()
         if dev.type != "cuda":
             raise RuntimeError("CandidatePlan needs the model on a CUDA device (no CPU path)")
         C, H, W = shape
+        assert method in ("ddim", "plms")
+        self.method = method
         self.unet, self.B, self.cfg, self.scale = unet, batch, bool(cfg), float(scale)
         self.steps = sorted(int(t) for t in sampled_timestep)  # ddim.py:93-94
         self.alphas, self.alphas_prev, self.s1m = ddim_tables(alphas_cumprod, self.steps)
@@ -96,6 +98,10 @@ class CandidatePlan:
         self.ctx = th.zeros((n, ctx_tokens, unet.context_dim), dtype=th.float32, device=dev)  # [uncond | cond]
         self.eps = th.empty((n, unet.out_channels, H, W), dtype=th.float32, device=dev)
         self.x = self.x2[:batch]
+        if method == "plms":  # eps history ring (p_sample_plms keeps the last three), e_t_next and x_t of the first step
+            self.e_ring = [th.empty((batch, C, H, W), dtype=th.float32, device=dev) for _ in range(4)]
+            self.e_next = th.empty((batch, C, H, W), dtype=th.float32, device=dev)
+            self.x_keep = th.empty((batch, C, H, W), dtype=th.float32, device=dev)
         self.plan_ctx = ops.Plan()
         cpad = ops.pad_context(self.ctx, CTX_ROWS, plan=self.plan_ctx)
         kvs = unet.record_context(self.plan_ctx, cpad)
@@ -105,7 +111,7 @@ class CandidatePlan:
         with th.no_grad():
             self.launches = self.plan_ctx.run()
             per_fwd = self.plan_fwd.run()
-        self.launches += len(self.steps) * (per_fwd + 1)
+        self.launches += len(self.steps) * (per_fwd + (1 if method == "ddim" else 2)) + (per_fwd + 2 if method == "plms" else 0)
         self.launches_per_forward = per_fwd
         if use_graph is None:
             use_graph = os.environ.get("ADB_NO_GRAPH", "0") != "1"
@@ -117,7 +123,36 @@ class CandidatePlan:
                 self._chain()
             self.graph = g
 
+    def _dup(self):
+        if self.cfg:
+            self.x2[self.B:].copy_(self.x)
+
+    def _chain_plms(self):
+        """plms.py:152-187 + p_sample_plms (:190-257)."""
+        self.plan_ctx.run()
+        time_range = list(reversed(self.steps))
+        for i, step in enumerate(time_range):
+            index = len(self.steps) - i - 1
+            self.t_in.fill_(step)
+            self.plan_fwd.run()
+            e_t = ops.cfg_combine(self.eps, scale=self.scale, cfg=self.cfg, out=self.e_ring[i % 4])
+            if i == 0:  # pseudo improved Euler: a provisional x_prev, the model again at t_next, then the real update from x_t
+                self.x_keep.copy_(self.x)
+                ops.plms_update(self.x, e_t, [], 0, self.coefs[index], x_prev=self.x)
+                self._dup()
+                self.t_in.fill_(time_range[min(i + 1, len(time_range) - 1)])
+                self.plan_fwd.run()
+                ops.cfg_combine(self.eps, scale=self.scale, cfg=self.cfg, out=self.e_next)
+                ops.plms_update(self.x_keep, e_t, [self.e_next], 1, self.coefs[index], x_prev=self.x)
+            else:
+                n_old = min(i, 3)
+                olds = [self.e_ring[(i - k) % 4] for k in range(1, n_old + 1)]  # newest first
+                ops.plms_update(self.x, e_t, olds, 1 + n_old, self.coefs[index], x_prev=self.x)
+            self._dup()
+
     def _chain(self):
+        if self.method == "plms":
+            return self._chain_plms()
         self.plan_ctx.run()
         for i, step in enumerate(reversed(self.steps)):
             index = len(self.steps) - i - 1
@@ -147,6 +182,8 @@ class CandidatePlan:
 
 class DDIMSampler(object):
     """ddim.py:13-217 restricted to what the search calls: eta = 0, no mask / x0 / score corrector / quantisation."""
+
+    method = "ddim"
 
     def __init__(self, model, schedule="linear", **kwargs):
         self.model = model
@@ -189,31 +226,48 @@ class DDIMSampler(object):
         intermediates = {"x_inter": [img], "pred_x0": [img]}
         if isinstance(unet, UNetModel) and not isinstance(conditioning, dict) and callback is None and img_callback is None:
             steps = [int(t) for t in self.ddim_timesteps]
-            key = (tuple(steps), batch_size, C, H, W, float(unconditional_guidance_scale), cfg, conditioning.shape[1])
+            key = (self.method, tuple(steps), batch_size, C, H, W, float(unconditional_guidance_scale), cfg, conditioning.shape[1])
             plan = self._plans.get(key)
             if plan is None:
                 if len(self._plans) >= 4:
                     self._plans.pop(next(iter(self._plans)))
                 plan = CandidatePlan(unet, self.model.alphas_cumprod, steps, batch_size, (C, H, W),
-                                     unconditional_guidance_scale, cfg, ctx_tokens=conditioning.shape[1])
+                                     unconditional_guidance_scale, cfg, ctx_tokens=conditioning.shape[1], method=self.method)
                 self._plans[key] = plan
             out = plan.run(img, conditioning, unconditional_conditioning).clone()
             return out, intermediates
         # generic apply_model: the reference's loop (ddim.py:143-172) with the fused update
         steps = np.asarray(self.ddim_timesteps)
         total = steps.shape[0]
-        for i, step in enumerate(np.flip(steps)):
+        time_range = [int(t) for t in np.flip(steps)]
+
+        def model_eps(x, ts):
+            if cfg:
+                return self.model.apply_model(th.cat([x] * 2), th.cat([ts] * 2),
+                                              th.cat([unconditional_conditioning, conditioning])).float().contiguous()
+            return self.model.apply_model(x, ts, conditioning).float().contiguous()
+
+        old_eps: List[th.Tensor] = []
+        for i, step in enumerate(time_range):
             index = total - i - 1
             ts = th.full((batch_size,), int(step), device=dev, dtype=th.long)
-            if cfg:
-                eps = self.model.apply_model(th.cat([img] * 2), th.cat([ts] * 2),
-                                             th.cat([unconditional_conditioning, conditioning]))
-            else:
-                eps = self.model.apply_model(img, ts, conditioning)
+            coef = ddim_coefficients(self.ddim_alphas, self.ddim_alphas_prev, self.ddim_sqrt_one_minus_alphas, index)
             pred = th.empty_like(img)
-            img = ops.cfg_ddim_step(img.contiguous(), eps.float().contiguous(),
-                                    ddim_coefficients(self.ddim_alphas, self.ddim_alphas_prev, self.ddim_sqrt_one_minus_alphas, index),
-                                    scale=unconditional_guidance_scale, cfg=cfg, pred_x0=pred)
+            img = img.contiguous()
+            if self.method == "ddim":
+                img = ops.cfg_ddim_step(img, model_eps(img, ts), coef, scale=unconditional_guidance_scale, cfg=cfg, pred_x0=pred)
+            else:  # plms.py:190-257
+                e_t = ops.cfg_combine(model_eps(img, ts), scale=unconditional_guidance_scale, cfg=cfg)
+                if not old_eps:
+                    ts_next = th.full((batch_size,), time_range[min(i + 1, total - 1)], device=dev, dtype=th.long)
+                    x_prov = ops.plms_update(img, e_t, [], 0, coef)
+                    e_next = ops.cfg_combine(model_eps(x_prov, ts_next), scale=unconditional_guidance_scale, cfg=cfg)
+                    img = ops.plms_update(img, e_t, [e_next], 1, coef, pred_x0=pred)
+                else:
+                    img = ops.plms_update(img, e_t, old_eps[::-1], 1 + len(old_eps), coef, pred_x0=pred)
+                old_eps.append(e_t)
+                if len(old_eps) >= 4:
+                    old_eps.pop(0)
             if callback:
                 callback(i)
             if img_callback:
@@ -222,3 +276,15 @@ class DDIMSampler(object):
                 intermediates["x_inter"].append(img)
                 intermediates["pred_x0"].append(pred)
         return img, intermediates
+
+
+class PLMSSampler(DDIMSampler):
+    """ldm/models/diffusion/plms.py:13-257 as the search calls it (scripts/search_ea.py with the PLMS sampler,
+    search_plms.sh): same schedule tables as DDIM, pseudo linear multistep eps combinations, eta must be 0."""
+
+    method = "plms"
+
+    def make_schedule(self, ddim_num_steps, ddim_discretize="uniform", ddim_eta=0.0, verbose=True, sampled_timestep=None):
+        if ddim_eta != 0:
+            raise ValueError("ddim_eta must be 0 for PLMS")  # plms.py:25-26
+        return super().make_schedule(ddim_num_steps, ddim_discretize, ddim_eta, verbose, sampled_timestep)

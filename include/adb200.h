@@ -304,6 +304,16 @@ int adb_geglu(adb_plan* plan, const void* x, void* out, int rows, int inner, adb
 int adb_cfg_ddim_step(adb_plan* plan, const float* x, const float* eps, float* x_prev, float* pred_x0, int n,
                       int chw, int cfg, float scale, const float coef[4], adb_stream stream);
 
+/* PLMS (ldm/models/diffusion/plms.py:190-257). adb_cfg_combine: e_out = e_u + scale * (e_c - e_u) over `total`
+ * elements (eps is [2*total] with the unconditional half first when cfg, else [total] copied), the tensor p_sample_plms
+ * returns as e_t and keeps in `old_eps`. adb_plms_update: e' from e_t and up to three older eps tensors -
+ * mode 0: e_t; 1: (e_t + o1) / 2 with o1 = e_t_next; 2: (3 e_t - o1) / 2; 3: (23 e_t - 16 o1 + 5 o2) / 12;
+ * 4: (55 e_t - 59 o1 + 37 o2 - 9 o3) / 24 (o1 = newest) - followed by the eta = 0 update of adb_cfg_ddim_step with e'.
+ * Bit-exact against the reference's fp32 tensor expressions. x_prev may alias x. */
+int adb_cfg_combine(adb_plan* plan, const float* eps, float* e_out, size_t total, int cfg, float scale, adb_stream stream);
+int adb_plms_update(adb_plan* plan, const float* x, const float* e_t, const float* o1, const float* o2, const float* o3,
+                    int mode, const float coef[4], float* x_prev, float* pred_x0, size_t total, adb_stream stream);
+
 /* fp32 [n, t, c] -> bf16 [n, t_pad, c_pad] zero-padded: the text context (77 x 768) into the 128-row buffer the
  * K/V projection GEMMs and adb_attention_sd read. */
 int adb_pad_context(adb_plan* plan, const float* ctx, void* out, int n, int t, int c, int t_pad, adb_stream stream);

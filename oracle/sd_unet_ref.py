@@ -14,6 +14,8 @@ Paths below are relative to /root/reference/examples/Stable Diffusion/ (`SD/`). 
   * make_ddim_sampling_parameters        ldm/modules/diffusionmodules/util.py:63-75
   * DDIMSampler.sample / ddim_sampling / p_sample_ddim with `sampled_timestep`
                                          ldm/models/diffusion/ddim.py:59-119, 121-175, 177-217
+  * PLMSSampler.sample / plms_sampling / p_sample_plms with `sampled_timestep`
+                                         ldm/models/diffusion/plms.py:62-122, 124-188, 190-257
   * the candidate call (CFG 7.5)         scripts/search_ea.py:737-739
 
 Weights are a plain dict keyed exactly like the reference module's `state_dict()`.
@@ -364,4 +366,44 @@ def ddim_sample(apply_model, x_T: torch.Tensor, cond: torch.Tensor, uncond: Opti
             e_u, e_c = apply_model(torch.cat([img] * 2), torch.cat([ts] * 2), torch.cat([uncond, cond])).chunk(2)
             e_t = e_u + scale * (e_c - e_u)
         img, _ = ddim_step(img, e_t, alphas[index], alphas_prev[index], s1m[index])
+    return img
+
+
+@torch.no_grad()
+def plms_sample(apply_model, x_T: torch.Tensor, cond: torch.Tensor, uncond: Optional[torch.Tensor], scale: float,
+                sampled_timestep: Sequence[int], alphas_cumprod: torch.Tensor) -> torch.Tensor:
+    """PLMSSampler.sample(..., sampled_timestep=cand) (plms.py:62-257): same tables as DDIM (make_schedule :24-60);
+    the first step is a pseudo improved Euler step (one extra model call at t_next), later steps use 2nd/3rd/4th order
+    Adams-Bashforth combinations of the last eps values; every combination feeds the eta = 0 update of ddim_step."""
+    steps, alphas, alphas_prev, s1m = ddim_tables(alphas_cumprod, sampled_timestep)
+    time_range = list(reversed(steps))
+    img = x_T
+    b = x_T.shape[0]
+    old_eps: List[torch.Tensor] = []
+
+    def model_out(x, t):
+        if uncond is None or scale == 1.0:
+            return apply_model(x, t, cond)
+        e_u, e_c = apply_model(torch.cat([x] * 2), torch.cat([t] * 2), torch.cat([uncond, cond])).chunk(2)
+        return e_u + scale * (e_c - e_u)
+
+    for i, step in enumerate(time_range):
+        index = len(steps) - i - 1
+        ts = torch.full((b,), step, dtype=torch.long)
+        ts_next = torch.full((b,), time_range[min(i + 1, len(time_range) - 1)], dtype=torch.long)
+        e_t = model_out(img, ts)
+        if len(old_eps) == 0:
+            x_prev, _ = ddim_step(img, e_t, alphas[index], alphas_prev[index], s1m[index])
+            e_t_next = model_out(x_prev, ts_next)
+            e_t_prime = (e_t + e_t_next) / 2
+        elif len(old_eps) == 1:
+            e_t_prime = (3 * e_t - old_eps[-1]) / 2
+        elif len(old_eps) == 2:
+            e_t_prime = (23 * e_t - 16 * old_eps[-1] + 5 * old_eps[-2]) / 12
+        else:
+            e_t_prime = (55 * e_t - 59 * old_eps[-1] + 37 * old_eps[-2] - 9 * old_eps[-3]) / 24
+        img, _ = ddim_step(img, e_t_prime, alphas[index], alphas_prev[index], s1m[index])
+        old_eps.append(e_t)
+        if len(old_eps) >= 4:
+            old_eps.pop(0)
     return img

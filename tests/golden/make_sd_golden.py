@@ -35,12 +35,14 @@ sys.modules.setdefault("omegaconf", oc)
 sys.modules.setdefault("omegaconf.listconfig", ocl)
 
 from ldm.models.diffusion.ddim import DDIMSampler  # noqa: E402
+from ldm.models.diffusion.plms import PLMSSampler  # noqa: E402
 from ldm.modules.diffusionmodules.openaimodel import UNetModel  # noqa: E402
 from ldm.modules.diffusionmodules.util import make_beta_schedule  # noqa: E402
 
 from oracle import sd_unet_ref as R  # noqa: E402
 
 DDIMSampler.register_buffer = lambda self, name, attr: setattr(self, name, attr)
+PLMSSampler.register_buffer = lambda self, name, attr: setattr(self, name, attr)
 
 SMALL = R.SDConfig(model_channels=64, context_dim=128)
 CAND10 = [981, 861, 741, 641, 501, 421, 301, 201, 121, 21]  # a searched-style 10-step subsequence (unsorted input below)
@@ -77,7 +79,55 @@ class Holder:
         return self.unet(x, t, context=c)
 
 
+def plms_golden():
+    """PLMS (the sampler search_plms.sh uses): 6 searched steps so every Adams-Bashforth order occurs, CFG 7.5."""
+    g = torch.Generator().manual_seed(23)
+    sd = R.make_weights(SMALL, seed=0)
+    m = ref_unet(SMALL, sd)
+    holder = Holder(m)
+    cand = [641, 981, 201, 21, 861, 421]
+    x_T = torch.randn(2, 4, 64, 64, generator=g)
+    ctx = torch.randn(2, 77, SMALL.context_dim, generator=g)
+    uc = torch.randn(1, 77, SMALL.context_dim, generator=g).repeat(2, 1, 1)
+    sampler = PLMSSampler(holder)
+    samples, _ = sampler.sample(S=len(cand), conditioning=ctx, batch_size=2, shape=[4, 64, 64], verbose=False,
+                                unconditional_guidance_scale=7.5, unconditional_conditioning=uc, eta=0.0, x_T=x_T,
+                                sampled_timestep=np.array(cand))
+    mine = R.plms_sample(lambda xx, tt, cc: R.unet_forward(sd, SMALL, xx, tt, cc), x_T, ctx, uc, 7.5, cand, R.sd_alphas_cumprod())
+    d = (samples - mine).abs().max().item()
+    print("small CFG-PLMS: max|ref - oracle| =", d, "model calls at", holder.calls)
+    assert d <= 1e-4 * samples.abs().max().item()
+    # the multistep combinations on recorded eps tensors: the fused update's bit-exactness fixture
+    es = [torch.randn(2, 4, 64, 64, generator=g) for _ in range(4)]
+
+    class Fixed:
+        num_timesteps = 1000
+        betas, alphas_cumprod, alphas_cumprod_prev, device = holder.betas, holder.alphas_cumprod, holder.alphas_cumprod_prev, holder.device
+
+        def __init__(self):
+            self.k = 0
+
+        def apply_model(self, xx, tt, cc):
+            self.k += 1
+            return es[0] if self.k == 1 else es[1]  # e_t, then (first step only) e_t_next
+
+    out = {}
+    for n_old in range(4):
+        fx = Fixed()
+        s2 = PLMSSampler(fx)
+        s2.make_schedule(ddim_num_steps=len(cand), ddim_eta=0.0, verbose=False, sampled_timestep=sorted(cand))
+        old = [es[3 - k] for k in range(n_old)][::-1]  # old_eps list, newest last: [.., es[3]]; here es[3], es[2], es[1]... newest = es[3]
+        xp, x0, e_t = s2.p_sample_plms(x_T, ctx, torch.full((2,), 421), index=2, unconditional_guidance_scale=1.0,
+                                       unconditional_conditioning=None, old_eps=list(old), t_next=torch.full((2,), 201))
+        assert torch.equal(e_t, es[0])
+        out[f"plms_x_prev_{n_old}"] = xp.numpy()
+    np.savez_compressed(os.path.join(HERE, "sd_small_plms.npz"), cand=np.array(cand), x_T=x_T.numpy(), ctx=ctx.numpy(), uc=uc.numpy(),
+                        samples=samples.numpy(), calls=np.array(holder.calls), es=torch.stack(es).numpy(), **out)
+
+
 def main():
+    if len(sys.argv) > 1 and sys.argv[1] == "plms":
+        return plms_golden()
     torch.manual_seed(0)
     g = torch.Generator().manual_seed(11)
     # ---- small config: forward + CFG DDIM ----
@@ -151,6 +201,7 @@ def main():
     d_full = (of - minef).abs().max().item()
     print(f"full forward ({nparam / 1e6:.1f} M params): max|ref - oracle| = {d_full}, out std {of.std().item():.4f}")
     assert d_full <= 1e-5 * of.abs().max().item()
+    plms_golden()
     np.savez_compressed(os.path.join(HERE, "sd_full.npz"), x=xf.numpy(), t=tf_.numpy(), ctx=cf.numpy(), out=of.numpy(),
                         nparam=np.array(nparam))
 

@@ -202,3 +202,27 @@ def test_pad_context():
     assert out.shape == (3, 128, 768)
     assert torch.equal(out[:, :77].cpu(), c.to(torch.bfloat16))
     assert out[:, 77:].abs().max().item() == 0.0
+
+
+def test_plms_update_bit_exact_vs_reference():
+    """The fused PLMS eps combination + update against x_prev recorded from the reference's p_sample_plms with 0..3
+    older eps tensors (sd_small_plms.npz): pseudo improved Euler and 2nd / 3rd / 4th order Adams-Bashforth."""
+    ops = _ops()
+    from autodiffusion_b200.sd_ddim import ddim_coefficients
+
+    g = golden("sd_small_plms.npz")
+    steps, a, ap, s1m = R.ddim_tables(R.sd_alphas_cumprod(), g["cand"].tolist())
+    coef = ddim_coefficients(a, ap, s1m, 2)
+    x = torch.tensor(g["x_T"]).to(DEV)
+    es = [torch.tensor(e).to(DEV) for e in g["es"]]
+    e_t = ops.cfg_combine(es[0])  # no guidance: a copy
+    assert torch.equal(e_t, es[0])
+    cases = {0: (1, [es[1]]), 1: (2, [es[3]]), 2: (3, [es[3], es[2]]), 3: (4, [es[3], es[2], es[1]])}
+    for n_old, (mode, olds) in cases.items():
+        out = ops.plms_update(x, e_t, olds, mode, coef)
+        torch.cuda.synchronize()
+        assert np.array_equal(out.cpu().numpy(), g[f"plms_x_prev_{n_old}"]), n_old
+    # CFG combine: the same expression as inside the DDIM step kernel
+    eu, ec = es[1], es[2]
+    comb = ops.cfg_combine(torch.cat([eu, ec]), scale=7.5, cfg=True)
+    assert torch.equal(comb.cpu(), (eu.cpu() + 7.5 * (ec.cpu() - eu.cpu())))

@@ -54,3 +54,19 @@ def test_sd_cfg_ddim_sampling_matches_reference():
                         torch.tensor(g["uc"]), 7.5, g["cand"].tolist(), R.sd_alphas_cumprod())
     ref = torch.tensor(g["samples"])
     assert (out - ref).abs().max().item() <= 1e-4 * ref.abs().max().item()
+
+
+def test_sd_plms_sampling_matches_reference():
+    g = golden("sd_small_plms.npz")
+    sd = R.make_weights(SMALL, seed=0)
+    calls = []
+
+    def model(x, t, c):
+        calls.append(int(t[0]))
+        return R.unet_forward(sd, SMALL, x, t, c)
+
+    out = R.plms_sample(model, torch.tensor(g["x_T"]), torch.tensor(g["ctx"]), torch.tensor(g["uc"]), 7.5, g["cand"].tolist(),
+                        R.sd_alphas_cumprod())
+    ref = torch.tensor(g["samples"])
+    assert (out - ref).abs().max().item() <= 1e-4 * ref.abs().max().item()
+    assert calls == g["calls"].tolist()  # 6 steps + the pseudo-improved-Euler extra call at the second timestep

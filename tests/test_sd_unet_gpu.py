@@ -66,6 +66,44 @@ def test_sd_small_cfg_ddim_matches_reference():
     assert [int(t) for t in sampler.ddim_timesteps] == sorted(cand.tolist())  # searched steps: exact
 
 
+def test_sd_small_cfg_plms_matches_reference():
+    """PLMSSampler (search_plms.sh) with 6 searched steps - every multistep order occurs - and CFG 7.5, vs the reference
+    run; the graph path and the generic apply_model loop give identical latents."""
+    from autodiffusion_b200.sd_ddim import LatentDiffusionUNet, PLMSSampler
+
+    g = golden("sd_small_plms.npz")
+    m, _ = _build(SMALL)
+    ld = LatentDiffusionUNet(m)
+    args = dict(S=len(g["cand"]), conditioning=torch.tensor(g["ctx"]).to(DEV), batch_size=2, shape=[4, 64, 64], verbose=False,
+                unconditional_guidance_scale=7.5, unconditional_conditioning=torch.tensor(g["uc"]).to(DEV), eta=0.0,
+                x_T=torch.tensor(g["x_T"]).to(DEV), sampled_timestep=g["cand"])
+    samples, _ = PLMSSampler(ld).sample(**args)
+    ref = torch.tensor(g["samples"])
+    out = samples.cpu()
+    peak = (ref.max() - ref.min()).item()
+    psnr = 10 * np.log10(peak * peak / ((out.double() - ref.double()) ** 2).mean().item())
+    print(f"SD small 6-step CFG-7.5 PLMS vs reference: PSNR {psnr:.2f} dB (peak {peak:.3g})")
+    assert psnr >= 30.0
+
+    class Foreign:
+        num_timesteps, betas, alphas_cumprod, alphas_cumprod_prev, device = (ld.num_timesteps, ld.betas, ld.alphas_cumprod,
+                                                                             ld.alphas_cumprod_prev, ld.device)
+
+        def __init__(self):
+            self.calls = []
+
+        def apply_model(self, x, t, c):
+            self.calls.append(int(t[0]))
+            return ld.apply_model(x, t, c)
+
+    f = Foreign()
+    b, _ = PLMSSampler(f).sample(**args)
+    assert f.calls == g["calls"].tolist()  # the model is called at the reference's timesteps, incl. the extra t_next call
+    assert torch.equal(samples, b)
+    with pytest.raises(ValueError):
+        PLMSSampler(ld).sample(**dict(args, eta=0.5))
+
+
 def test_sd_generic_apply_model_loop_matches_plan():
     """A foreign apply_model (here: a wrapper hiding our UNet) takes the generic loop; same numbers as the graph."""
     from autodiffusion_b200.sd_ddim import DDIMSampler, LatentDiffusionUNet

@@ -209,6 +209,9 @@ SYMBOLS = {
     "adb_geglu": (_I, [_P, _P, _P, _I, _I, _P]),
     "adb_cfg_ddim_step": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, C.c_float, C.POINTER(C.c_float), _P]),
     "adb_pad_context": (_I, [_P, _P, _P, _I, _I, _I, _I, _P]),
+    "adb_timestep_embedding_f32": (_I, [_P, _P, _P, _P, _I, _I, _P]),
+    "adb_dpm_x0": (_I, [_P, _P, _P, _P, C.c_size_t, _I, C.c_float, C.c_float, C.c_float, _P]),
+    "adb_dpm_update": (_I, [_P, _P, _P, _P, _P, C.c_size_t, _I, C.c_float, C.c_float, C.c_float, C.c_float, _P]),
     "adb_cfg_combine": (_I, [_P, _P, _P, C.c_size_t, _I, C.c_float, _P]),
     "adb_plms_update": (_I, [_P, _P, _P, _P, _P, _P, _I, C.POINTER(C.c_float), _P, _P, C.c_size_t, _P]),
 }

@@ -144,7 +144,8 @@ __global__ void __launch_bounds__(256) stem_conv64_kernel(const float* __restric
 // timestep_embedding (guided_diffusion/nn.py:103-121), fp32 as written there:
 // args = t * freqs; out = [cos(args) | sin(args)]
 // ------------------------------------------------------------------------------------
-__global__ void timestep_embedding_kernel(const int64_t* __restrict__ t, const float* __restrict__ freqs,
+template <typename T>
+__global__ void timestep_embedding_kernel(const T* __restrict__ t, const float* __restrict__ freqs,
                                           float* __restrict__ out, int b, int dim) {
   const int half = dim / 2;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -340,7 +341,19 @@ int timestep_embedding_submit(adb_plan* plan, const int64_t* t, const float* fre
   ADB_REQUIRE(t && freqs && out && b > 0 && dim >= 2, "timestep_embedding: bad arguments");
   return submit(plan, stream, "timestep_embedding", 0.0, 0.0, [=](cudaStream_t s) -> int {
     const int total = b * (dim / 2);
-    timestep_embedding_kernel<<<(total + 127) / 128, 128, 0, s>>>(t, freqs, out, b, dim);
+    timestep_embedding_kernel<int64_t><<<(total + 127) / 128, 128, 0, s>>>(t, freqs, out, b, dim);
+    ADB_CUDA(cudaGetLastError());
+    return 1;
+  });
+}
+
+// fractional model timesteps (DPM-Solver feeds (t - 1/N) * 1000, dpm_solver.py:278-286)
+int timestep_embedding_f32_submit(adb_plan* plan, const float* t, const float* freqs, float* out, int b, int dim,
+                                  cudaStream_t stream) {
+  ADB_REQUIRE(t && freqs && out && b > 0 && dim >= 2, "timestep_embedding_f32: bad arguments");
+  return submit(plan, stream, "timestep_embedding", 0.0, 0.0, [=](cudaStream_t s) -> int {
+    const int total = b * (dim / 2);
+    timestep_embedding_kernel<float><<<(total + 127) / 128, 128, 0, s>>>(t, freqs, out, b, dim);
     ADB_CUDA(cudaGetLastError());
     return 1;
   });

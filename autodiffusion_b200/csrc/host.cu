@@ -127,6 +127,10 @@ int cfg_ddim_step_submit(adb_plan*, const float*, const float*, float*, float*, 
                          cudaStream_t);
 int pad_context_submit(adb_plan*, const float*, void*, int, int, int, int, cudaStream_t);
 int cfg_combine_submit(adb_plan*, const float*, float*, size_t, int, float, cudaStream_t);
+int timestep_embedding_f32_submit(adb_plan*, const float*, const float*, float*, int, int, cudaStream_t);
+int dpm_x0_submit(adb_plan*, const float*, const float*, float*, size_t, int, float, float, float, cudaStream_t);
+int dpm_update_submit(adb_plan*, const float*, const float*, const float*, float*, size_t, int, float, float, float, float,
+                      cudaStream_t);
 int plms_update_submit(adb_plan*, const float*, const float*, const float*, const float*, const float*, int, const float*,
                        float*, float*, size_t, cudaStream_t);
 
@@ -347,6 +351,21 @@ int adb_cfg_combine(adb_plan* plan, const float* eps, float* e_out, size_t total
 int adb_plms_update(adb_plan* plan, const float* x, const float* e_t, const float* o1, const float* o2, const float* o3,
                     int mode, const float coef[4], float* x_prev, float* pred_x0, size_t total, adb_stream stream) {
   return plms_update_submit(plan, x, e_t, o1, o2, o3, mode, coef, x_prev, pred_x0, total, static_cast<cudaStream_t>(stream));
+}
+
+int adb_timestep_embedding_f32(adb_plan* plan, const float* t, const float* freqs, float* out, int b, int dim,
+                               adb_stream stream) {
+  return timestep_embedding_f32_submit(plan, t, freqs, out, b, dim, static_cast<cudaStream_t>(stream));
+}
+
+int adb_dpm_x0(adb_plan* plan, const float* x, const float* eps, float* x0, size_t total, int cfg, float scale,
+               float sigma, float alpha, adb_stream stream) {
+  return dpm_x0_submit(plan, x, eps, x0, total, cfg, scale, sigma, alpha, static_cast<cudaStream_t>(stream));
+}
+
+int adb_dpm_update(adb_plan* plan, const float* x, const float* m0, const float* m1, float* x_out, size_t total,
+                   int order, float c0, float c1, float c2, float inv_r0, adb_stream stream) {
+  return dpm_update_submit(plan, x, m0, m1, x_out, total, order, c0, c1, c2, inv_r0, static_cast<cudaStream_t>(stream));
 }
 
 int adb_pad_context(adb_plan* plan, const float* ctx, void* out, int n, int t, int c, int t_pad, adb_stream stream) {

@@ -161,6 +161,34 @@ __global__ void __launch_bounds__(256) plms_update_kernel(const float* __restric
   }
 }
 
+// DPM-Solver++ data prediction (dpm_solver.py:336-343, 386-391): noise = e_u + scale (e_c - e_u),
+// x0 = (x - sigma_t * noise) / alpha_t, each op rounded separately.
+__global__ void __launch_bounds__(256) dpm_x0_kernel(const float* __restrict__ x, const float* __restrict__ eps,
+                                                     float* __restrict__ x0, size_t total, int cfg, float scale, float sigma,
+                                                     float alpha) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    float e = eps[i];
+    if (cfg) e = __fadd_rn(e, __fmul_rn(scale, __fsub_rn(eps[total + i], e)));
+    x0[i] = __fdiv_rn(__fsub_rn(x[i], __fmul_rn(sigma, e)), alpha);
+  }
+}
+
+// multistep updates (dpm_solver.py:519-533, 770-790, data-prediction branch, 'dpm_solver' type):
+// order 1: x_t = c0 x - c1 m0;  order 2: x_t = (c0 x - c1 m0) - c2 (inv_r0 (m0 - m1)), with
+// c0 = sigma_t / sigma_s, c1 = alpha_t * expm1(-h) or alpha_t * (exp(-h) - 1), c2 = 0.5 * c1 - computed by the host
+// in fp32 as the reference computes them.
+__global__ void __launch_bounds__(256) dpm_update_kernel(const float* __restrict__ x, const float* __restrict__ m0,
+                                                         const float* __restrict__ m1, float* __restrict__ x_out, size_t total,
+                                                         int order, float c0, float c1, float c2, float inv_r0) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const float a = __fmul_rn(c0, x[i]);
+    const float mm = m0[i];
+    float r = __fsub_rn(a, __fmul_rn(c1, mm));
+    if (order == 2) r = __fsub_rn(r, __fmul_rn(c2, __fmul_rn(inv_r0, __fsub_rn(mm, m1[i]))));
+    x_out[i] = r;
+  }
+}
+
 __global__ void __launch_bounds__(256) pad_context_kernel(const float* __restrict__ ctx, __nv_bfloat16* __restrict__ out,
                                                           int n, int t, int c, int t_pad) {
   const size_t total = (size_t)n * t_pad * c;
@@ -245,6 +273,26 @@ int plms_update_submit(adb_plan* plan, const float* x, const float* e_t, const f
   for (int i = 0; i < 4; ++i) cf.v[i] = coef[i];
   return submit(plan, stream, "plms_update", 0.0, 4.0 * (double)total * (3.0 + (mode > 1 ? mode - 1 : mode)), [=](cudaStream_t s) -> int {
     plms_update_kernel<<<grid_for(total, 256), 256, 0, s>>>(x, e_t, o1, o2, o3, mode, cf, x_prev, pred_x0, total);
+    ADB_CUDA(cudaGetLastError());
+    return 1;
+  });
+}
+
+int dpm_x0_submit(adb_plan* plan, const float* x, const float* eps, float* x0, size_t total, int cfg, float scale,
+                  float sigma, float alpha, cudaStream_t stream) {
+  ADB_REQUIRE(x && eps && x0 && total > 0, "dpm_x0: bad arguments");
+  return submit(plan, stream, "dpm_x0", 0.0, 4.0 * (double)total * (cfg ? 4.0 : 3.0), [=](cudaStream_t s) -> int {
+    dpm_x0_kernel<<<grid_for(total, 256), 256, 0, s>>>(x, eps, x0, total, cfg, scale, sigma, alpha);
+    ADB_CUDA(cudaGetLastError());
+    return 1;
+  });
+}
+
+int dpm_update_submit(adb_plan* plan, const float* x, const float* m0, const float* m1, float* x_out, size_t total, int order,
+                      float c0, float c1, float c2, float inv_r0, cudaStream_t stream) {
+  ADB_REQUIRE(x && m0 && x_out && total > 0 && (order == 1 || (order == 2 && m1)), "dpm_update: bad arguments");
+  return submit(plan, stream, "dpm_update", 0.0, 4.0 * (double)total * (order + 2.0), [=](cudaStream_t s) -> int {
+    dpm_update_kernel<<<grid_for(total, 256), 256, 0, s>>>(x, m0, m1, x_out, total, order, c0, c1, c2, inv_r0);
     ADB_CUDA(cudaGetLastError());
     return 1;
   });

@@ -36,7 +36,7 @@ __all__ = [
     "attention_backward", "gn_backward", "pool_prepare", "pool_attention", "pool_attention_backward", "pool_merge",
     "logsoftmax_grad", "pack_conv_weight_dgrad", "pack_linear_weight_split", "linear_tc",
     "pack_stem_weight", "stem_conv_tc",
-    "attention_sd", "layernorm", "geglu", "cfg_ddim_step", "pad_context", "cfg_combine", "plms_update",
+    "attention_sd", "layernorm", "geglu", "cfg_ddim_step", "pad_context", "cfg_combine", "plms_update", "dpm_x0", "dpm_update",
 ]
 
 
@@ -510,11 +510,18 @@ def timestep_embedding(t: torch.Tensor, dim: int, out: Optional[torch.Tensor] = 
     if out is None:
         out = torch.empty((b, dim), dtype=torch.float32, device=t.device)
     freqs = timestep_freqs(dim, t.device)
-    _lib.check(
-        _lib.lib().adb_timestep_embedding(_ph(plan), _dev(t, "t", torch.int64), _dev(freqs, "freqs", torch.float32),
-                                          _dev(out, "out", torch.float32), b, dim, _stream()),
-        "adb_timestep_embedding",
-    )
+    if t.dtype == torch.float32:  # fractional model timesteps (DPM-Solver)
+        _lib.check(
+            _lib.lib().adb_timestep_embedding_f32(_ph(plan), _dev(t, "t", torch.float32), _dev(freqs, "freqs", torch.float32),
+                                                  _dev(out, "out", torch.float32), b, dim, _stream()),
+            "adb_timestep_embedding_f32",
+        )
+    else:
+        _lib.check(
+            _lib.lib().adb_timestep_embedding(_ph(plan), _dev(t, "t", torch.int64), _dev(freqs, "freqs", torch.float32),
+                                              _dev(out, "out", torch.float32), b, dim, _stream()),
+            "adb_timestep_embedding",
+        )
     if plan is not None:
         plan.keep(t, freqs, out)
     return out
@@ -749,3 +756,30 @@ def plms_update(x: torch.Tensor, e_t: torch.Tensor, old: Sequence[torch.Tensor],
     if plan is not None:
         plan.keep(x, e_t, *[t for t in old if t is not None], x_prev, pred_x0)
     return x_prev
+
+
+def dpm_x0(x: torch.Tensor, eps: torch.Tensor, sigma: float, alpha: float, scale: float = 1.0, cfg: bool = False,
+           out: Optional[torch.Tensor] = None, plan: Optional[Plan] = None) -> torch.Tensor:
+    """DPM-Solver++ data prediction with classifier-free guidance: x0 = (x - sigma * noise) / alpha."""
+    if out is None:
+        out = torch.empty_like(x)
+    assert eps.numel() == (2 if cfg else 1) * x.numel()
+    _lib.check(_lib.lib().adb_dpm_x0(_ph(plan), _dev(x, "x", torch.float32), _dev(eps, "eps", torch.float32),
+                                     _dev(out, "out", torch.float32), x.numel(), int(bool(cfg)), float(scale), float(sigma),
+                                     float(alpha), _stream()), "adb_dpm_x0")
+    if plan is not None:
+        plan.keep(x, eps, out)
+    return out
+
+
+def dpm_update(x: torch.Tensor, m0: torch.Tensor, m1: Optional[torch.Tensor], order: int, c0: float, c1: float, c2: float = 0.0,
+               inv_r0: float = 0.0, out: Optional[torch.Tensor] = None, plan: Optional[Plan] = None) -> torch.Tensor:
+    """Multistep DPM-Solver++ update of order 1 or 2 (include/adb200.h: adb_dpm_update). m0 = newest data prediction."""
+    if out is None:
+        out = torch.empty_like(x)
+    _lib.check(_lib.lib().adb_dpm_update(_ph(plan), _dev(x, "x", torch.float32), _dev(m0, "m0", torch.float32),
+                                         _opt(m1, "m1", torch.float32), _dev(out, "out", torch.float32), x.numel(), int(order),
+                                         float(c0), float(c1), float(c2), float(inv_r0), _stream()), "adb_dpm_update")
+    if plan is not None:
+        plan.keep(x, m0, m1, out)
+    return out

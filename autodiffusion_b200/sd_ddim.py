@@ -288,3 +288,192 @@ class PLMSSampler(DDIMSampler):
         if ddim_eta != 0:
             raise ValueError("ddim_eta must be 0 for PLMS")  # plms.py:25-26
         return super().make_schedule(ddim_num_steps, ddim_discretize, ddim_eta, verbose, sampled_timestep)
+
+
+# ------------------------------------------------------------------------------------------
+# DPM-Solver++(2M) with searched time steps (ldm/models/diffusion/dpm_solver/, search_dpm_solver.sh)
+# ------------------------------------------------------------------------------------------
+class DiscreteNoiseSchedule:
+    """NoiseScheduleVP('discrete', alphas_cumprod=...) (dpm_solver.py:97-156): log alpha_t is piecewise linear in t over
+    the knots t_n = n / N, n = 1..N (outermost segments extended); every quantity a fp32 torch op on the host, in the
+    reference's order, so the per-step scalars equal the reference's."""
+
+    def __init__(self, alphas_cumprod: th.Tensor):
+        self.log_alpha = 0.5 * th.log(alphas_cumprod.detach().float().cpu())
+        self.total_N = int(self.log_alpha.shape[0])
+        self.T = 1.0
+        self.t_array = th.linspace(0.0, 1.0, self.total_N + 1)[1:]
+
+    def marginal_log_mean_coeff(self, t: th.Tensor) -> th.Tensor:
+        t = t.contiguous()
+        lo = th.clamp(th.searchsorted(self.t_array, t, right=False) - 1, 0, self.total_N - 2)
+        x0, x1, y0, y1 = self.t_array[lo], self.t_array[lo + 1], self.log_alpha[lo], self.log_alpha[lo + 1]
+        return y0 + (t - x0) * (y1 - y0) / (x1 - x0)
+
+    def marginal_alpha(self, t):
+        return th.exp(self.marginal_log_mean_coeff(t))
+
+    def marginal_std(self, t):
+        return th.sqrt(1.0 - th.exp(2.0 * self.marginal_log_mean_coeff(t)))
+
+    def marginal_lambda(self, t):
+        lm = self.marginal_log_mean_coeff(t)
+        return lm - 0.5 * th.log(1.0 - th.exp(2.0 * lm))
+
+
+def dpm_time_steps(ea_timesteps, total_N: int = 1000) -> th.Tensor:
+    """dpm_solver.py:1079-1091: integer candidates index the reversed uniform 1001-point grid between t_T = 1 and
+    t_0 = 1/N in the order given; candidates already in (0, 1] are sorted descending."""
+    ea = [float(v) for v in ea_timesteps]
+    if max(ea) > 1:
+        full = list(th.linspace(1.0, 1.0 / total_N, 1000 + 1))
+        full.reverse()
+        return th.Tensor([full[int(v)].item() for v in ea])
+    return th.Tensor(sorted(ea, reverse=True))
+
+
+def dpm_schedule(ns: DiscreteNoiseSchedule, ts: th.Tensor):
+    """Everything the 2M solver needs per model evaluation / update as Python floats (fp32 values):
+    model input times, (sigma, alpha) for the data prediction, and the update coefficients
+    (order, c0, c1, c2, inv_r0) for steps 1..S (dpm_solver.py:519-533, 770-790, 1099-1121)."""
+    S = ts.shape[0] - 1
+    assert S >= 2, "the order-2 multistep solver needs at least 2 steps (dpm_solver.py:1077)"
+    t_in = ((ts - 1.0 / ns.total_N) * 1000.0).tolist()  # get_model_input_time (:278-286)
+    sig, alp = ns.marginal_std(ts).tolist(), ns.marginal_alpha(ts).tolist()
+    lam, lm, std = ns.marginal_lambda(ts), ns.marginal_log_mean_coeff(ts), ns.marginal_std(ts)
+    upd = []
+    for step in range(1, S + 1):
+        order = 1 if step == 1 else (min(2, S + 1 - step) if S < 15 else 2)
+        s_, t_ = step - 1, step
+        alpha_t = th.exp(lm[t_])
+        c0 = std[t_] / std[s_]
+        if order == 1:
+            h = lam[t_] - lam[s_]
+            upd.append((1, c0.item(), (alpha_t * th.expm1(-h)).item(), 0.0, 0.0))
+        else:
+            h_0 = lam[s_] - lam[s_ - 1]
+            h = lam[t_] - lam[s_]
+            r0 = h_0 / h
+            c1 = alpha_t * (th.exp(-h) - 1.0)
+            upd.append((2, c0.item(), c1.item(), (0.5 * c1).item(), (1.0 / r0).item()))
+    return t_in, sig, alp, upd
+
+
+class DPMCandidatePlan(CandidatePlan):
+    """A DPM-Solver++(2M) candidate (S + 1 time points, S model evaluations) as one CUDA graph: the UNet runs on
+    fractional timesteps; two data-prediction buffers alternate as (older, newer)."""
+
+    def __init__(self, unet: UNetModel, alphas_cumprod: th.Tensor, ea_timesteps, batch: int, shape, scale: float, cfg: bool,
+                 ctx_tokens: int = 77, use_graph: Optional[bool] = None):
+        dev = unet._device()
+        if dev.type != "cuda":
+            raise RuntimeError("DPMCandidatePlan needs the model on a CUDA device (no CPU path)")
+        C, H, W = shape
+        self.method = "dpm_solver++"
+        self.unet, self.B, self.cfg, self.scale = unet, batch, bool(cfg), float(scale)
+        ns = DiscreteNoiseSchedule(alphas_cumprod)
+        self.ts = dpm_time_steps(ea_timesteps, ns.total_N)
+        self.steps = self.ts.tolist()
+        self.t_model, self.sigmas, self.alphas_t, self.updates = dpm_schedule(ns, self.ts)
+        n = batch * (2 if cfg else 1)
+        self.x2 = th.zeros((n, C, H, W), dtype=th.float32, device=dev)
+        self.t_in = th.zeros((n,), dtype=th.float32, device=dev)
+        self.ctx = th.zeros((n, ctx_tokens, unet.context_dim), dtype=th.float32, device=dev)
+        self.eps = th.empty((n, unet.out_channels, H, W), dtype=th.float32, device=dev)
+        self.x = self.x2[:batch]
+        self.m = [th.empty((batch, C, H, W), dtype=th.float32, device=dev) for _ in range(2)]
+        self.plan_ctx = ops.Plan()
+        cpad = ops.pad_context(self.ctx, CTX_ROWS, plan=self.plan_ctx)
+        kvs = unet.record_context(self.plan_ctx, cpad)
+        self.plan_fwd = ops.Plan()
+        unet.record_forward(self.plan_fwd, self.x2, self.t_in, kvs, self.eps, ctx_tokens=ctx_tokens)
+        S = len(self.updates)
+        with th.no_grad():
+            self.launches = self.plan_ctx.run()
+            per_fwd = self.plan_fwd.run()
+        self.launches += S * (per_fwd + 2)
+        self.launches_per_forward = per_fwd
+        if use_graph is None:
+            use_graph = os.environ.get("ADB_NO_GRAPH", "0") != "1"
+        self.graph = None
+        if use_graph:
+            th.cuda.current_stream().synchronize()
+            g = th.cuda.CUDAGraph()
+            with th.cuda.graph(g):
+                self._chain()
+            self.graph = g
+
+    def _model(self, k: int, dst: th.Tensor):
+        self.t_in.fill_(self.t_model[k])
+        self.plan_fwd.run()
+        ops.dpm_x0(self.x, self.eps, self.sigmas[k], self.alphas_t[k], scale=self.scale, cfg=self.cfg, out=dst)
+
+    def _chain(self):
+        self.plan_ctx.run()
+        S = len(self.updates)
+        old, new = 0, 0
+        self._model(0, self.m[0])
+        for step in range(1, S + 1):
+            order, c0, c1, c2, inv_r0 = self.updates[step - 1]
+            ops.dpm_update(self.x, self.m[new], self.m[old] if order == 2 else None, order, c0, c1, c2, inv_r0, out=self.x)
+            self._dup()
+            if step < S:  # the final model value is never needed (dpm_solver.py:1119-1121)
+                old, new = new, 1 - new
+                self._model(step, self.m[new])
+
+
+class DPMSolverSampler(object):
+    """ldm/models/diffusion/dpm_solver/sampler.py:8-83: DPM-Solver++ (data prediction), multistep, order 2,
+    lower_order_final, classifier-free guidance, `sampled_timestep` = S + 1 searched time points."""
+
+    def __init__(self, model, **kwargs):
+        self.model = model
+        self.alphas_cumprod = model.alphas_cumprod.detach().float()
+        self._plans: Dict[tuple, DPMCandidatePlan] = {}
+
+    @th.no_grad()
+    def sample(self, S, batch_size, shape, conditioning=None, callback=None, normals_sequence=None, img_callback=None,
+               quantize_x0=False, eta=0.0, mask=None, x0=None, temperature=1.0, noise_dropout=0.0, score_corrector=None,
+               corrector_kwargs=None, verbose=True, x_T=None, log_every_t=100, unconditional_guidance_scale=1.0,
+               unconditional_conditioning=None, sampled_timestep=None, **kwargs):
+        if sampled_timestep is None:
+            ns_T, t0 = 1.0, 1.0 / int(self.alphas_cumprod.shape[0])
+            sampled_timestep = th.linspace(ns_T, t0, S + 1).tolist()  # get_time_steps('time_uniform'), dpm_solver.py:431-432
+        assert len(sampled_timestep) - 1 == S  # dpm_solver.py:1097
+        C, H, W = shape
+        dev = self.model.device
+        img = th.randn((batch_size, C, H, W), device=dev) if x_T is None else x_T
+        cfg = not (unconditional_guidance_scale == 1.0 or unconditional_conditioning is None)  # dpm_solver.py:337
+        unet = getattr(self.model, "unet", None)
+        if isinstance(unet, UNetModel) and not isinstance(conditioning, dict):
+            key = (tuple(float(v) for v in sampled_timestep), batch_size, C, H, W, float(unconditional_guidance_scale), cfg,
+                   conditioning.shape[1])
+            plan = self._plans.get(key)
+            if plan is None:
+                if len(self._plans) >= 4:
+                    self._plans.pop(next(iter(self._plans)))
+                plan = DPMCandidatePlan(unet, self.alphas_cumprod, sampled_timestep, batch_size, (C, H, W),
+                                        unconditional_guidance_scale, cfg, ctx_tokens=conditioning.shape[1])
+                self._plans[key] = plan
+            return plan.run(img, conditioning, unconditional_conditioning).clone(), None
+        # generic apply_model: dpm_solver.py:1099-1121 with the fused kernels
+        ns = DiscreteNoiseSchedule(self.alphas_cumprod)
+        ts = dpm_time_steps(sampled_timestep, ns.total_N)
+        t_model, sig, alp, upd = dpm_schedule(ns, ts)
+
+        def model(x, k):
+            t = th.full((batch_size,), t_model[k], device=dev, dtype=th.float32)
+            if cfg:
+                eps = self.model.apply_model(th.cat([x] * 2), th.cat([t] * 2), th.cat([unconditional_conditioning, conditioning]))
+            else:
+                eps = self.model.apply_model(x, t, conditioning)
+            return ops.dpm_x0(x, eps.float().contiguous(), sig[k], alp[k], scale=unconditional_guidance_scale, cfg=cfg)
+
+        x = img.contiguous()
+        m_old = m_new = model(x, 0)
+        for step in range(1, len(upd) + 1):
+            order, c0, c1, c2, inv_r0 = upd[step - 1]
+            x = ops.dpm_update(x, m_new, m_old if order == 2 else None, order, c0, c1, c2, inv_r0)
+            if step < len(upd):
+                m_old, m_new = m_new, model(x, step)
+        return x, None

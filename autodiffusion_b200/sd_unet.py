@@ -546,12 +546,13 @@ class UNetModel(nn.Module):
         self._ready()
         n, _, H, W = x.shape
         tokens = context.shape[1]
-        key = (n, H, W, tokens)
+        t_dtype = th.float32 if timesteps.is_floating_point() else th.int64  # DPM-Solver passes fractional timesteps
+        key = (n, H, W, tokens, t_dtype)
         entry = self._plans.get(key)
         if entry is None:
             dev = self._device()
             x_in = th.zeros((n, self.in_channels, H, W), dtype=th.float32, device=dev)
-            t_in = th.zeros((n,), dtype=th.int64, device=dev)
+            t_in = th.zeros((n,), dtype=t_dtype, device=dev)
             c_in = th.zeros((n, tokens, self.context_dim), dtype=th.float32, device=dev)
             out = th.empty((n, self.out_channels, H, W), dtype=th.float32, device=dev)
             plan = ops.Plan()
@@ -562,7 +563,7 @@ class UNetModel(nn.Module):
             self._plans[key] = entry
         plan, x_in, t_in, c_in, out = entry
         x_in.copy_(x.float())
-        t_in.copy_(timesteps.to(th.int64))
+        t_in.copy_(timesteps.to(t_dtype))
         c_in.copy_(context.float())
         self.gpu_launches += plan.run()
         return out.clone()

@@ -314,6 +314,19 @@ int adb_cfg_combine(adb_plan* plan, const float* eps, float* e_out, size_t total
 int adb_plms_update(adb_plan* plan, const float* x, const float* e_t, const float* o1, const float* o2, const float* o3,
                     int mode, const float coef[4], float* x_prev, float* pred_x0, size_t total, adb_stream stream);
 
+/* DPM-Solver++(2M) (ldm/models/diffusion/dpm_solver/dpm_solver.py). adb_timestep_embedding_f32: the sinusoid of
+ * fractional model timesteps (t_continuous - 1/N) * 1000 (:278-286). adb_dpm_x0: classifier-free combine (:336-343)
+ * + data prediction x0 = (x - sigma_t * noise) / alpha_t (:386-391) over `total` elements (eps is [2*total],
+ * unconditional half first, when cfg). adb_dpm_update: order 1 x_t = c0 x - c1 m0 (:519-533); order 2
+ * x_t = c0 x - c1 m0 - c2 * (inv_r0 * (m0 - m1)) (:770-790); the scalars are the reference's fp32 schedule
+ * expressions evaluated on the host. x_out may alias x. */
+int adb_timestep_embedding_f32(adb_plan* plan, const float* t, const float* freqs, float* out, int b, int dim,
+                               adb_stream stream);
+int adb_dpm_x0(adb_plan* plan, const float* x, const float* eps, float* x0, size_t total, int cfg, float scale,
+               float sigma, float alpha, adb_stream stream);
+int adb_dpm_update(adb_plan* plan, const float* x, const float* m0, const float* m1, float* x_out, size_t total,
+                   int order, float c0, float c1, float c2, float inv_r0, adb_stream stream);
+
 /* fp32 [n, t, c] -> bf16 [n, t_pad, c_pad] zero-padded: the text context (77 x 768) into the 128-row buffer the
  * K/V projection GEMMs and adb_attention_sd read. */
 int adb_pad_context(adb_plan* plan, const float* ctx, void* out, int n, int t, int c, int t_pad, adb_stream stream);

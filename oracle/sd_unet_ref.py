@@ -16,6 +16,11 @@ Paths below are relative to /root/reference/examples/Stable Diffusion/ (`SD/`). 
                                          ldm/models/diffusion/ddim.py:59-119, 121-175, 177-217
   * PLMSSampler.sample / plms_sampling / p_sample_plms with `sampled_timestep`
                                          ldm/models/diffusion/plms.py:62-122, 124-188, 190-257
+  * DPMSolverSampler.sample -> DPM_Solver(predict_x0=True).sample(method="multistep", order=2, lower_order_final=True,
+    ea_timesteps=cand) with NoiseScheduleVP("discrete") and the classifier-free model_wrapper
+                                         ldm/models/diffusion/dpm_solver/sampler.py:20-83,
+                                         ldm/models/diffusion/dpm_solver/dpm_solver.py:97-156, 278-343, 386-399,
+                                         504-533, 755-790, 1072-1121, 1149-1188
   * the candidate call (CFG 7.5)         scripts/search_ea.py:737-739
 
 Weights are a plain dict keyed exactly like the reference module's `state_dict()`.
@@ -407,3 +412,106 @@ def plms_sample(apply_model, x_T: torch.Tensor, cond: torch.Tensor, uncond: Opti
         if len(old_eps) >= 4:
             old_eps.pop(0)
     return img
+
+
+# --------------------------------------------------------------------------------------
+# DPM-Solver++(2M) with searched time steps (the sampler search_dpm_solver.sh uses)
+# --------------------------------------------------------------------------------------
+def _interp(x: torch.Tensor, xp: torch.Tensor, yp: torch.Tensor) -> torch.Tensor:
+    """interpolate_fn (dpm_solver.py:1149-1188) for one channel: piecewise-linear through (xp, yp) with xp ascending,
+    the outermost segments extended beyond the ends; same arithmetic `y0 + (x - x0) * (y1 - y0) / (x1 - x0)`."""
+    K = xp.shape[0]
+    idx = torch.searchsorted(xp, x.contiguous(), right=False)  # number of knots < x
+    lo = torch.clamp(idx - 1, 0, K - 2)
+    x0, x1, y0, y1 = xp[lo], xp[lo + 1], yp[lo], yp[lo + 1]
+    return y0 + (x - x0) * (y1 - y0) / (x1 - x0)
+
+
+class DiscreteVP:
+    """NoiseScheduleVP('discrete', alphas_cumprod=acp) (dpm_solver.py:97-156): log alpha_t by interpolation over
+    t_n = n / N, n = 1..N."""
+
+    def __init__(self, alphas_cumprod: torch.Tensor):
+        self.log_alpha = 0.5 * torch.log(alphas_cumprod.float())
+        self.N = self.log_alpha.shape[0]
+        self.t_array = torch.linspace(0.0, 1.0, self.N + 1)[1:]
+
+    def log_mean(self, t):
+        return _interp(t, self.t_array, self.log_alpha)
+
+    def alpha(self, t):
+        return torch.exp(self.log_mean(t))
+
+    def std(self, t):
+        return torch.sqrt(1.0 - torch.exp(2.0 * self.log_mean(t)))
+
+    def lam(self, t):
+        lm = self.log_mean(t)
+        return lm - 0.5 * torch.log(1.0 - torch.exp(2.0 * lm))
+
+
+def dpm_timesteps(ea_timesteps: Sequence[float], N: int = 1000) -> torch.Tensor:
+    """dpm_solver.py:1079-1091: integer candidates index the reversed 1001-point uniform grid between t_T = 1 and
+    t_0 = 1/N IN THE ORDER GIVEN; candidates already in (0, 1] are sorted descending."""
+    if max(ea_timesteps) > 1:
+        full = list(torch.linspace(1.0, 1.0 / N, 1000 + 1))
+        full.reverse()
+        return torch.Tensor([full[int(ea)].item() for ea in ea_timesteps])
+    return torch.Tensor(sorted(ea_timesteps, reverse=True))
+
+
+@torch.no_grad()
+def dpm_solver_sample(apply_model, x_T: torch.Tensor, cond: torch.Tensor, uncond: Optional[torch.Tensor], scale: float,
+                      ea_timesteps: Sequence[float], alphas_cumprod: torch.Tensor, record=None) -> torch.Tensor:
+    """DPMSolverSampler.sample(S=len(cand) - 1, ..., sampled_timestep=cand): data-prediction multistep solver of order 2
+    with a first-order start and (fewer than 15 steps) a first-order final step."""
+    ns = DiscreteVP(alphas_cumprod)
+    ts = dpm_timesteps(ea_timesteps, ns.N)
+    steps = ts.shape[0] - 1
+    b = x_T.shape[0]
+
+    def e4(v):
+        return v[:, None, None, None]
+
+    def model_fn(x, t):  # model_wrapper "classifier-free" (:336-343) + data_prediction_fn (:386-391)
+        t_in = (t - 1.0 / ns.N) * 1000.0  # get_model_input_time (:278-286): fractional model timesteps
+        if scale == 1.0 or uncond is None:
+            noise = apply_model(x, t_in, cond)
+        else:
+            n_u, n_c = apply_model(torch.cat([x] * 2), torch.cat([t_in] * 2), torch.cat([uncond, cond])).chunk(2)
+            noise = n_u + scale * (n_c - n_u)
+        if record is not None:
+            record.append(float(t_in[0]))
+        return (x - e4(ns.std(t)) * noise) / e4(ns.alpha(t))
+
+    def first_update(x, s, t, m_s):  # dpm_solver_first_update, predict_x0 branch (:519-533)
+        h = ns.lam(t) - ns.lam(s)
+        alpha_t = torch.exp(ns.log_mean(t))
+        return e4(ns.std(t) / ns.std(s)) * x - e4(alpha_t * torch.expm1(-h)) * m_s
+
+    def second_update(x, m1, m0, t1, t0, t):  # multistep_dpm_solver_second_update (:770-790), 'dpm_solver' type
+        l1, l0, lt = ns.lam(t1), ns.lam(t0), ns.lam(t)
+        alpha_t = torch.exp(ns.log_mean(t))
+        h_0, h = l0 - l1, lt - l0
+        r0 = h_0 / h
+        D1_0 = e4(1.0 / r0) * (m0 - m1)
+        return (e4(ns.std(t) / ns.std(t0)) * x - e4(alpha_t * (torch.exp(-h) - 1.0)) * m0
+                - 0.5 * e4(alpha_t * (torch.exp(-h) - 1.0)) * D1_0)
+
+    x = x_T
+    vec = lambda k: ts[k].expand(b)
+    models, times = [model_fn(x, vec(0))], [vec(0)]
+    x = first_update(x, times[-1], vec(1), models[-1])
+    models.append(model_fn(x, vec(1)))
+    times.append(vec(1))
+    for step in range(2, steps + 1):
+        order = min(2, steps + 1 - step) if steps < 15 else 2
+        if order == 1:
+            x = first_update(x, times[-1], vec(step), models[-1])
+        else:
+            x = second_update(x, models[0], models[1], times[0], times[1], vec(step))
+        models[0], times[0] = models[1], times[1]
+        times[1] = vec(step)
+        if step < steps:
+            models[1] = model_fn(x, vec(step))
+    return x

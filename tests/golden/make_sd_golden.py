@@ -125,9 +125,65 @@ def plms_golden():
                         samples=samples.numpy(), calls=np.array(holder.calls), es=torch.stack(es).numpy(), **out)
 
 
+def dpm_golden():
+    """DPM-Solver++(2M) with searched steps (search_dpm_solver.sh): 6 model evaluations (7 time points), CFG 7.5.
+    Extra shim: the solver moves its time-step tensor with a hard-coded `.to('cuda')` (dpm_solver.py:1088,1091);
+    during this run `Tensor.to('cuda')` is a no-op so the unmodified code runs on the CPU."""
+    from ldm.models.diffusion.dpm_solver import DPMSolverSampler
+    from ldm.models.diffusion.dpm_solver.dpm_solver import DPM_Solver, NoiseScheduleVP, model_wrapper
+
+    DPMSolverSampler.register_buffer = lambda self, name, attr: setattr(self, name, attr)
+    orig_to = torch.Tensor.to
+
+    def to_cpu(self, *a, **k):
+        a = tuple("cpu" if (isinstance(v, str) and v == "cuda") else v for v in a)
+        return orig_to(self, *a, **k)
+
+    g = torch.Generator().manual_seed(29)
+    sd = R.make_weights(SMALL, seed=0)
+    m = ref_unet(SMALL, sd)
+
+    class FloatHolder(Holder):
+        def apply_model(self, x, t, c):
+            self.calls.append(float(t[0]))
+            return self.unet(x, t, context=c)
+
+    holder = FloatHolder(m)
+    cand = [981, 861, 641, 421, 201, 61, 0]  # descending, as the SD search keeps them (time_step + 1 entries)
+    x_T = torch.randn(2, 4, 64, 64, generator=g)
+    ctx = torch.randn(2, 77, SMALL.context_dim, generator=g)
+    uc = torch.randn(1, 77, SMALL.context_dim, generator=g).repeat(2, 1, 1)
+    torch.Tensor.to = to_cpu
+    try:
+        sampler = DPMSolverSampler(holder)
+        samples, _ = sampler.sample(S=len(cand) - 1, conditioning=ctx, batch_size=2, shape=[4, 64, 64], verbose=False,
+                                    unconditional_guidance_scale=7.5, unconditional_conditioning=uc, eta=0.0, x_T=x_T,
+                                    sampled_timestep=cand)
+        # schedule scalars of the reference at the candidate's time points
+        ns = NoiseScheduleVP("discrete", alphas_cumprod=holder.alphas_cumprod)
+        tt = R.dpm_timesteps(cand)
+        ref_lam, ref_alpha, ref_std = ns.marginal_lambda(tt), ns.marginal_alpha(tt), ns.marginal_std(tt)
+    finally:
+        torch.Tensor.to = orig_to
+    rec = []
+    mine = R.dpm_solver_sample(lambda xx, t, cc: R.unet_forward(sd, SMALL, xx, t, cc), x_T, ctx, uc, 7.5, cand,
+                               R.sd_alphas_cumprod(), record=rec)
+    d = (samples - mine).abs().max().item()
+    print("small CFG DPM-Solver++(2M): max|ref - oracle| =", d, "model times", holder.calls)
+    assert d <= 1e-4 * samples.abs().max().item()
+    vp = R.DiscreteVP(R.sd_alphas_cumprod())
+    assert torch.equal(vp.lam(tt), ref_lam) and torch.equal(vp.alpha(tt), ref_alpha) and torch.equal(vp.std(tt), ref_std)
+    assert np.allclose(rec, holder.calls, rtol=0, atol=0)
+    np.savez_compressed(os.path.join(HERE, "sd_small_dpm.npz"), cand=np.array(cand), x_T=x_T.numpy(), ctx=ctx.numpy(), uc=uc.numpy(),
+                        samples=samples.numpy(), calls=np.array(holder.calls), times=tt.numpy(), lam=ref_lam.numpy(),
+                        alpha=ref_alpha.numpy(), std=ref_std.numpy())
+
+
 def main():
     if len(sys.argv) > 1 and sys.argv[1] == "plms":
         return plms_golden()
+    if len(sys.argv) > 1 and sys.argv[1] == "dpm":
+        return dpm_golden()
     torch.manual_seed(0)
     g = torch.Generator().manual_seed(11)
     # ---- small config: forward + CFG DDIM ----
@@ -202,6 +258,7 @@ def main():
     print(f"full forward ({nparam / 1e6:.1f} M params): max|ref - oracle| = {d_full}, out std {of.std().item():.4f}")
     assert d_full <= 1e-5 * of.abs().max().item()
     plms_golden()
+    dpm_golden()
     np.savez_compressed(os.path.join(HERE, "sd_full.npz"), x=xf.numpy(), t=tf_.numpy(), ctx=cf.numpy(), out=of.numpy(),
                         nparam=np.array(nparam))
 

@@ -66,3 +66,21 @@ def test_schedule_tables_and_coefficients_bit_exact():
         c = ddim_coefficients(a, ap, s1m, i)
         want = (s1m[i].item(), a[i].sqrt().item(), ap[i].sqrt().item(), (1.0 - ap[i]).sqrt().item())
         assert c == want  # the fp32 values torch computes in p_sample_ddim
+
+
+def test_dpm_solver_schedule_scalars_bit_exact():
+    """Host side of DPM-Solver++(2M): time points, fractional model timesteps and the noise-schedule values at them
+    equal what the unmodified reference computed (sd_small_dpm.npz), bit for bit."""
+    from autodiffusion_b200.sd_ddim import DiscreteNoiseSchedule, dpm_schedule, dpm_time_steps
+
+    g = golden("sd_small_dpm.npz")
+    ns = DiscreteNoiseSchedule(R.sd_alphas_cumprod())
+    ts = dpm_time_steps(g["cand"].tolist())
+    assert np.array_equal(ts.numpy(), g["times"])
+    assert np.array_equal(ns.marginal_lambda(ts).numpy(), g["lam"])
+    assert np.array_equal(ns.marginal_alpha(ts).numpy(), g["alpha"])
+    assert np.array_equal(ns.marginal_std(ts).numpy(), g["std"])
+    t_in, sig, alp, upd = dpm_schedule(ns, ts)
+    assert np.array_equal(np.float32(t_in[:-1]), g["calls"])
+    assert [u[0] for u in upd] == [1, 2, 2, 2, 2, 1]  # first-order start, lower_order_final at < 15 steps
+    assert dpm_time_steps([0.9, 0.1, 0.5]).tolist() == sorted(np.float32([0.9, 0.1, 0.5]).tolist(), reverse=True)

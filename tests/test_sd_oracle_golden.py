@@ -70,3 +70,14 @@ def test_sd_plms_sampling_matches_reference():
     ref = torch.tensor(g["samples"])
     assert (out - ref).abs().max().item() <= 1e-4 * ref.abs().max().item()
     assert calls == g["calls"].tolist()  # 6 steps + the pseudo-improved-Euler extra call at the second timestep
+
+
+def test_sd_dpm_solver_sampling_matches_reference():
+    g = golden("sd_small_dpm.npz")
+    sd = R.make_weights(SMALL, seed=0)
+    rec = []
+    out = R.dpm_solver_sample(lambda x, t, c: R.unet_forward(sd, SMALL, x, t, c), torch.tensor(g["x_T"]), torch.tensor(g["ctx"]),
+                              torch.tensor(g["uc"]), 7.5, g["cand"].tolist(), R.sd_alphas_cumprod(), record=rec)
+    ref = torch.tensor(g["samples"])
+    assert (out - ref).abs().max().item() <= 1e-4 * ref.abs().max().item()
+    assert np.array_equal(np.float32(rec), g["calls"])

@@ -104,6 +104,43 @@ def test_sd_small_cfg_plms_matches_reference():
         PLMSSampler(ld).sample(**dict(args, eta=0.5))
 
 
+def test_sd_small_cfg_dpm_solver_matches_reference():
+    """DPMSolverSampler (search_dpm_solver.sh): DPM-Solver++(2M), 7 searched time points = 6 model evaluations at fractional
+    timesteps, CFG 7.5, vs the reference run; graph path == generic apply_model loop."""
+    from autodiffusion_b200.sd_ddim import DPMSolverSampler, LatentDiffusionUNet
+
+    g = golden("sd_small_dpm.npz")
+    m, _ = _build(SMALL)
+    ld = LatentDiffusionUNet(m)
+    cand = g["cand"].tolist()
+    args = dict(S=len(cand) - 1, conditioning=torch.tensor(g["ctx"]).to(DEV), batch_size=2, shape=[4, 64, 64], verbose=False,
+                unconditional_guidance_scale=7.5, unconditional_conditioning=torch.tensor(g["uc"]).to(DEV), eta=0.0,
+                x_T=torch.tensor(g["x_T"]).to(DEV), sampled_timestep=cand)
+    samples, _ = DPMSolverSampler(ld).sample(**args)
+    ref = torch.tensor(g["samples"])
+    out = samples.cpu()
+    peak = (ref.max() - ref.min()).item()
+    psnr = 10 * np.log10(peak * peak / ((out.double() - ref.double()) ** 2).mean().item())
+    print(f"SD small 6-evaluation CFG-7.5 DPM-Solver++(2M) vs reference: PSNR {psnr:.2f} dB (peak {peak:.3g})")
+    assert psnr >= 30.0
+
+    class Foreign:
+        num_timesteps, betas, alphas_cumprod, alphas_cumprod_prev, device = (ld.num_timesteps, ld.betas, ld.alphas_cumprod,
+                                                                             ld.alphas_cumprod_prev, ld.device)
+
+        def __init__(self):
+            self.calls = []
+
+        def apply_model(self, x, t, c):
+            self.calls.append(float(t[0]))
+            return ld.apply_model(x, t, c)
+
+    f = Foreign()
+    b, _ = DPMSolverSampler(f).sample(**args)
+    assert np.array_equal(np.float32(f.calls), g["calls"])  # the reference's fractional model timesteps, bit for bit
+    assert torch.equal(samples, b)
+
+
 def test_sd_generic_apply_model_loop_matches_plan():
     """A foreign apply_model (here: a wrapper hiding our UNet) takes the generic loop; same numbers as the graph."""
     from autodiffusion_b200.sd_ddim import DDIMSampler, LatentDiffusionUNet

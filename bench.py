@@ -670,6 +670,11 @@ def run_sdv1(args):
     fwd_per_image = (K + (1 if args.sd_sampler == "plms" else 0)) * 2  # PLMS: one extra evaluation in its first step
     torch.cuda.synchronize()
     build_s = time.time() - t0
+    t0 = time.time()  # a second candidate of the same geometry: only its own chain is captured
+    other = CandidatePlan(unet, ld.alphas_cumprod, [t - 10 for t in SD_CAND], B, (4, 64, 64), 7.5, True)
+    torch.cuda.synchronize()
+    build_next_s = time.time() - t0
+    del other
     g = torch.Generator(device=dev).manual_seed(7 + rank)
     x_T = torch.randn((B, 4, 64, 64), device=dev, generator=g)
     cond = torch.randn((B, 77, 768), device=dev, generator=g)
@@ -762,7 +767,7 @@ def run_sdv1(args):
                                 "recorded_plan_gflop_per_image_per_forward": recorded_gflop},
             "e2e": {"value": imgs / (ms_e2e * 1e-3), "unit": "images/s",
                     "h2d_bytes_per_step": (hx.numel() + hc.numel() + hu.numel()) * 4, "d2h_bytes_per_step": hout.numel() * 4},
-            "gpu_launches": plan.launches * args.steps, "plan_build_s": build_s, "clocks": clocks, "roofline": roof,
+            "gpu_launches": plan.launches * args.steps, "plan_build_s": build_s, "next_candidate_plan_build_s": build_next_s, "clocks": clocks, "roofline": roof,
             "cpu_baseline": cpu,
             "kernel_breakdown_one_forward": {k: {"launches": v[0], "ms": round(v[1], 3), "share": round(v[1] / fwd_ms, 4),
                                                  "tflops": (v[2] / (v[1] * 1e-3) / 1e12) if v[2] and v[1] else None,

@@ -141,6 +141,33 @@ def test_sd_small_cfg_dpm_solver_matches_reference():
     assert torch.equal(samples, b)
 
 
+def test_sd_no_guidance_odd_batch_and_shared_forward():
+    """scale = 1 (no CFG: one conditional forward per step), batch 3, a short context; candidates of one geometry share
+    the recorded forward, so alternating between them must reproduce each one's latents exactly."""
+    from autodiffusion_b200.sd_ddim import DDIMSampler, LatentDiffusionUNet
+
+    m, sd = _build(SMALL)
+    sampler = DDIMSampler(LatentDiffusionUNet(m))
+    gen = torch.Generator().manual_seed(41)
+    x_T = torch.randn(3, 4, 64, 64, generator=gen)
+    ctx = torch.randn(3, 5, SMALL.context_dim, generator=gen)
+    cand_a, cand_b = [801, 401, 1], [951, 301]
+
+    def run(cand):
+        out, _ = sampler.sample(S=len(cand), conditioning=ctx.to(DEV), batch_size=3, shape=[4, 64, 64], verbose=False,
+                                unconditional_guidance_scale=1.0, unconditional_conditioning=None, eta=0.0, x_T=x_T.to(DEV),
+                                sampled_timestep=cand)
+        return out.cpu()
+
+    a1, b1, a2 = run(cand_a), run(cand_b), run(cand_a)
+    assert torch.equal(a1, a2) and not torch.equal(a1[:, :, :8, :8], b1[:, :, :8, :8])
+    ref = R.ddim_sample(lambda x, t, c: R.unet_forward(sd, SMALL, x, t, c), x_T, ctx, None, 1.0, cand_a, R.sd_alphas_cumprod())
+    peak = (ref.max() - ref.min()).item()
+    psnr = 10 * np.log10(peak * peak / ((a1.double() - ref.double()) ** 2).mean().item())
+    print(f"SD small 3-step DDIM without guidance, batch 3, 5 context tokens vs oracle: PSNR {psnr:.2f} dB")
+    assert psnr >= 30.0
+
+
 def test_sd_generic_apply_model_loop_matches_plan():
     """A foreign apply_model (here: a wrapper hiding our UNet) takes the generic loop; same numbers as the graph."""
     from autodiffusion_b200.sd_ddim import DDIMSampler, LatentDiffusionUNet

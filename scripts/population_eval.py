@@ -69,6 +69,9 @@ def main():
     ap.add_argument("--feature_dim", type=int, default=2048)
     ap.add_argument("--seed", type=int, default=0)
     ap.add_argument("--small", action="store_true", help="64-channel 1-res-block UNet (functional check)")
+    ap.add_argument("--features", default="projection", choices=["projection", "inception"],
+                    help="projection: fixed random projection to --feature_dim; inception: Inception-V3 pool_3 on the device "
+                         "(autodiffusion_b200.inception, random-init offline), 2048-d")
     ap.add_argument("--shard", default="candidates", choices=["candidates", "batches"],
                     help="candidates: each rank evaluates whole candidates (no per-candidate collective); batches: every "
                          "candidate's batches are split over ranks and its moments all-reduced")
@@ -117,11 +120,17 @@ def main():
         clf.to(dev).eval()
         cond_fn = ClassifierGuidance(clf, 1.0)
 
-    d = args.feature_dim
+    d = args.feature_dim if args.features == "projection" else 2048
     proj = (th.randn(3 * 64 * 64, d, generator=th.Generator().manual_seed(7)) * (3.0 / (3 * 64 * 64) ** 0.5)).to(dev)
 
     def feature_fn(u8):  # stand-in for Inception pool_3: uint8 NHWC -> fp32 [n, d], O(1) entries
         return (u8.reshape(u8.shape[0], -1).float() / 255.0 - 0.5) @ proj
+
+    if args.features == "inception":
+        from autodiffusion_b200.inception import InceptionPool3
+
+        inception = InceptionPool3().to(dev)
+        feature_fn = inception  # noqa: F811  uint8 NHWC -> fp32 [n, 2048] on the device
 
     rs = np.random.RandomState(11)
     a = rs.randn(d, d) / d ** 0.5
@@ -168,7 +177,7 @@ def main():
             "metric": "population evaluation, candidates/s", "value": n / wall, "unit": "candidates/s",
             "images_per_s": n * args.num_samples / wall, "n_gpus": world, "candidates": n,
             "num_samples": args.num_samples, "batch_size": args.batch_size, "ddim_steps": args.time_step,
-            "feature_dim": d, "wall_s": wall, "guided": bool(args.guided), "shard": args.shard, "fid_method": args.fid_method,
+            "feature_dim": d, "wall_s": wall, "guided": bool(args.guided), "shard": args.shard, "fid_method": args.fid_method, "features": args.features,
             "split_s": {"plan_build": round(t_plan, 3), "sampling_plus_allreduce": round(t_sample, 3),
                         "host_sqrtm_fid_overlapped": round(t_fid, 3)},
             "fid_first3": [round(x, 4) for x in fids[:3]],

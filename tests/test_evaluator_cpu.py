@@ -157,3 +157,18 @@ def test_remote_fid_placeholder_refuses_a_direct_result():
 
     with pytest.raises(RuntimeError):
         _RemoteFid(1).result()
+
+
+def test_inception_pool3_feature_extractor_contract():
+    """uint8 NHWC in, fp32 [B, 2048] out, deterministic for a seed, rejects anything that is not uint8 NHWC RGB."""
+    from autodiffusion_b200.inception import InceptionPool3
+
+    m = InceptionPool3(seed=0)
+    u8 = torch.randint(0, 256, (2, 64, 64, 3), dtype=torch.uint8, generator=torch.Generator().manual_seed(0))
+    f = m(u8)
+    assert f.shape == (2, 2048) and f.dtype == torch.float32 and torch.isfinite(f).all()
+    assert torch.equal(f, InceptionPool3(seed=0)(u8)) and not torch.equal(f, InceptionPool3(seed=1)(u8))
+    with pytest.raises(ValueError):
+        m(u8.float())
+    with pytest.raises(ValueError):
+        m(u8.permute(0, 3, 1, 2))

@@ -16,7 +16,8 @@ from pathlib import Path
 _PKG = Path(__file__).resolve().parent
 CSRC = _PKG / "csrc"
 LIB_DIR = _PKG / "lib"
-LIB_PATH = LIB_DIR / "libadb200.so"
+# ADB_LIB_PATH: load another build of the library (A/B timing of kernel variants); the default is the in-tree build
+LIB_PATH = Path(os.environ["ADB_LIB_PATH"]) if os.environ.get("ADB_LIB_PATH") else LIB_DIR / "libadb200.so"
 HEADER = _PKG.parent / "include" / "adb200.h"
 
 SOURCES = ["host.cu", "conv_igemm.cu", "attention.cu", "attention2.cu", "groupnorm.cu", "elementwise.cu", "moments.cu",

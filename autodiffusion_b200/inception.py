@@ -24,7 +24,7 @@ import torch.nn.functional as F
 
 
 class InceptionPool3(nn.Module):
-    def __init__(self, weights: Optional[str] = None, seed: int = 0, half: bool = True):
+    def __init__(self, weights: Optional[str] = None, seed: int = 0, half: Optional[bool] = None):
         super().__init__()
         import torchvision
 
@@ -38,7 +38,8 @@ class InceptionPool3(nn.Module):
             if any(not k.startswith("fc.") and not k.startswith("AuxLogits.") for k in list(missing) + list(unexpected)):
                 raise ValueError(f"Inception weights do not fit torchvision's inception_v3: missing {missing}, unexpected {unexpected}")
         self.net = net.eval()
-        self.half = half
+        # fp16 autocast only with trained weights: a randomly initialised Inception's activations overflow fp16
+        self.half = (weights is not None) if half is None else half
         self.dim = 2048
 
     @th.no_grad()
@@ -54,4 +55,7 @@ class InceptionPool3(nn.Module):
                 f = self.net(x)
         else:
             f = self.net(x)
-        return f.float().reshape(u8.shape[0], -1)
+        f = f.float().reshape(u8.shape[0], -1)
+        if not bool(th.isfinite(f).all()):
+            raise FloatingPointError("InceptionPool3 produced non-finite features (fp16 overflow? construct with half=False)")
+        return f

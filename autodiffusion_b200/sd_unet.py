@@ -133,6 +133,7 @@ class UNetModel(nn.Module):
                     ds //= 2
                 out.append(layers)
         self._arch = (inp, middle, out)
+        self._skip_chans = list(chans)  # channels of hs[i], the input blocks' outputs
         self._final_ch = ch
         self._levels = len(self.channel_mult) - 1
         self._make_parameters()
@@ -391,16 +392,41 @@ class UNetModel(nn.Module):
         produced: Dict[int, th.Tensor] = {}
         ctx.on_alloc = lambda t: produced.pop(t.data_ptr(), None)
 
-        def new_stats(t: th.Tensor):
+        # th.cat([h, hs.pop()], 1) feeds the first GroupNorm of every output block: both producers also accumulate their
+        # sums in the CONCAT's group layout (conv_igemm stats2: group width (c_h + c_skip) / 32, channel offset 0 / c_h),
+        # so that GroupNorm becomes apply-only too. The architecture is static: consumer k of input block i is output
+        # block k = last - i; the running h of output block k comes from block k - 1 (the middle block for k = 0).
+        inp, middle, outb = self._arch
+        n_out = len(outb)
+        cat_cpg = [(outb[k][0].cin) // 32 for k in range(n_out)]
+        c_h = [outb[k][0].cin - self._skip_chans[n_out - 1 - k] for k in range(n_out)]
+        cat_arena = th.empty((n_out, B, 32, 2), dtype=th.float64, device=dev)
+        plan.keep(cat_arena)
+        ops.memset0(cat_arena, plan=plan)
+        cat_have: Dict[int, Dict[int, int]] = {k: {} for k in range(n_out)}  # consumer -> {half: data_ptr}
+
+        def new_stats(t: th.Tensor, cat: Optional[Tuple[int, int]] = None):
+            """cat = (consumer output block, half): also accumulate into that block's concat statistics."""
             if t.shape[3] % 32 != 0 or (t.shape[1] * t.shape[2]) % 32 != 0:
                 return {}
             st = arena[slot[0]]
             slot[0] += 1
             produced[t.data_ptr()] = st
-            return {"stats_out": st}
+            kw = {"stats_out": st}
+            if cat is not None and 96 // cat_cpg[cat[0]] + 2 <= 40:
+                k, half = cat
+                kw["stats2"] = (cat_arena[k], cat_cpg[k], 0 if half == 0 else c_h[k])
+                cat_have[k][half] = t.data_ptr()
+            return kw
+
+        cur_out = [-1]  # index of the output block being recorded (for the concat GroupNorm lookup)
 
         def gn(srcs, gamma, beta, out_t, eps, silu):
             st = produced.get(srcs[0].data_ptr()) if len(srcs) == 1 else None
+            if len(srcs) == 2 and cur_out[0] >= 0:
+                have = cat_have[cur_out[0]]
+                if have.get(0) == srcs[0].data_ptr() and have.get(1) == srcs[1].data_ptr():
+                    st = cat_arena[cur_out[0]]
             ops.groupnorm(srcs[0], gamma, beta, src1=srcs[1] if len(srcs) > 1 else None, out=out_t, eps=eps, silu=silu,
                           stats=st if st is not None else scratch, stats_ready=st is not None, plan=plan)
 
@@ -409,7 +435,7 @@ class UNetModel(nn.Module):
         emb = ops.linear(e1, P["time_embed.2.w"], P["time_embed.2.b"], silu_in=True, plan=plan)
         emb_all = ops.linear_tc(emb, P["emb_w"], P["emb_b"], P["emb_total"], silu_in=True, plan=plan)  # [B, sum cout]
 
-        def run_res(b: _Blk, srcs: List[th.Tensor]) -> th.Tensor:
+        def run_res(b: _Blk, srcs: List[th.Tensor], cat=None) -> th.Tensor:
             q = P[b.name]
             n, h, w = srcs[0].shape[:3]
             g1 = ctx.alloc((n, h, w, b.cin))
@@ -424,15 +450,15 @@ class UNetModel(nn.Module):
             o = ctx.alloc((n, h, w, b.cout))
             if q["ws_raw"] is not None:
                 w2 = self._w2_for(b, tuple(s.shape[3] for s in srcs))
-                ops.conv_igemm([(g2, 9)] + [(s, 1) for s in srcs], w2, q["b2"], b.cout, out=o, plan=plan, **new_stats(o))
+                ops.conv_igemm([(g2, 9)] + [(s, 1) for s in srcs], w2, q["b2"], b.cout, out=o, plan=plan, **new_stats(o, cat))
             else:
                 assert len(srcs) == 1
                 ops.conv_igemm([(g2, 9)], self._w2_for(b, ()), q["b2"], b.cout, out=o, residual=srcs[0],
-                               res_mode=ops.RES_SAME, plan=plan, **new_stats(o))
+                               res_mode=ops.RES_SAME, plan=plan, **new_stats(o, cat))
             ctx.release(g2)
             return o
 
-        def run_st(b: _Blk, x: th.Tensor) -> th.Tensor:
+        def run_st(b: _Blk, x: th.Tensor, cat=None) -> th.Tensor:
             q = P[b.name]
             n, h, w, c = x.shape
             t = h * w
@@ -490,45 +516,48 @@ class UNetModel(nn.Module):
                 cur = nxt
             o = ctx.alloc((n, h, w, c))
             ops.conv_igemm([(cur, 1)], q["w_out"], q["b_out"], c, out=o, residual=x, res_mode=ops.RES_SAME, plan=plan,
-                           **new_stats(o))
+                           **new_stats(o, cat))
             ctx.release(cur)
             return o
 
-        def run_block(layers: Sequence[_Blk], srcs: List[th.Tensor]) -> th.Tensor:
-            """Consumes one reference to each tensor in srcs; returns a tensor the caller owns."""
-            for b in layers:
+        def run_block(layers: Sequence[_Blk], srcs: List[th.Tensor], cat=None) -> th.Tensor:
+            """Consumes one reference to each tensor in srcs; returns a tensor the caller owns. `cat`: the block's final
+            tensor is one half of a later concat (consumer output block, half)."""
+            for li, b in enumerate(layers):
+                lcat = cat if li == len(layers) - 1 else None
                 if b.kind == "res":
-                    o = run_res(b, srcs)
+                    o = run_res(b, srcs, lcat)
                 elif b.kind == "st":
-                    o = run_st(b, srcs[0])
+                    o = run_st(b, srcs[0], lcat)
                 elif b.kind == "down":
                     x = srcs[0]
                     o = ctx.alloc((x.shape[0], x.shape[1] // 2, x.shape[2] // 2, b.cout))
-                    ops.conv_igemm([(x, 9, 2)], P[b.name]["w"], P[b.name]["b"], b.cout, out=o, plan=plan, **new_stats(o))
+                    ops.conv_igemm([(x, 9, 2)], P[b.name]["w"], P[b.name]["b"], b.cout, out=o, plan=plan, **new_stats(o, lcat))
                 else:  # up: F.interpolate(nearest, 2x) then conv3x3 (openaimodel.py:109-118)
                     x = srcs[0]
                     u = ctx.alloc((x.shape[0], x.shape[1] * 2, x.shape[2] * 2, b.cin))
                     ops.resample2x(x, ops.RESAMPLE_NEAREST2, out=u, plan=plan)
                     o = ctx.alloc((x.shape[0], x.shape[1] * 2, x.shape[2] * 2, b.cout))
-                    ops.conv_igemm([(u, 9)], P[b.name]["w"], P[b.name]["b"], b.cout, out=o, plan=plan, **new_stats(o))
+                    ops.conv_igemm([(u, 9)], P[b.name]["w"], P[b.name]["b"], b.cout, out=o, plan=plan, **new_stats(o, lcat))
                     ctx.release(u)
                 for s in srcs:
                     ctx.release(s)
                 srcs = [o]
             return srcs[0]
 
-        inp, middle, outb = self._arch
         h = ctx.alloc((B, H, W, mc))
-        ops.stem_conv(x_in, P["stem_w"], P["stem_b"], out=h, plan=plan)
+        ops.stem_conv(x_in, P["stem_w"], P["stem_b"], out=h, plan=plan)  # hs[0]: no epilogue sums (last concat keeps its stats pass)
         hs = [h]
         ctx.retain(h)
-        for layers in inp[1:]:
-            h = run_block(layers, [h])
+        for i, layers in enumerate(inp[1:], start=1):
+            h = run_block(layers, [h], cat=(n_out - 1 - i, 1))
             hs.append(h)
             ctx.retain(h)
-        h = run_block(middle, [h])
-        for layers in outb:
-            h = run_block(layers, [h, hs.pop()])  # th.cat([h, hs.pop()], dim=1), openaimodel.py:735
+        h = run_block(middle, [h], cat=(0, 0))
+        for k, layers in enumerate(outb):
+            cur_out[0] = k
+            h = run_block(layers, [h, hs.pop()], cat=(k + 1, 0) if k + 1 < n_out else None)  # th.cat([h, hs.pop()], 1), openaimodel.py:735
+        cur_out[0] = -1
         g = ctx.alloc(tuple(h.shape))
         gn([h], P["out_g"], P["out_be"], g, 1e-5, True)
         ctx.release(h)

@@ -30,7 +30,13 @@ class InceptionPool3(nn.Module):
 
         with th.random.fork_rng(devices=[]):
             th.manual_seed(seed)
-            net = torchvision.models.inception_v3(weights=None, aux_logits=False, transform_input=False, init_weights=True)
+            net = torchvision.models.inception_v3(weights=None, aux_logits=False, transform_input=False, init_weights=False)
+            if weights is None:
+                # fan-in scaled (He) draws keep the 94 conv layers' activations O(1); torchvision's own init (std 0.1
+                # everywhere) makes an untrained network's features ~1e12
+                for m in net.modules():
+                    if isinstance(m, nn.Conv2d):
+                        nn.init.kaiming_normal_(m.weight, nonlinearity="relu")
         net.fc = nn.Identity()
         if weights is not None:
             sd = th.load(weights, map_location="cpu")

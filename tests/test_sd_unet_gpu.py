@@ -213,3 +213,43 @@ def test_sd_full_forward_batch_vs_oracle():
     out = m(x.to(DEV), t.to(DEV), context=c.to(DEV)).cpu()
     rel, mx = _report(out, ref, "SD-v1 UNet forward batch 3 vs oracle")
     assert rel <= 0.02 and mx <= 0.12
+
+
+@pytest.mark.parametrize("sampler,cand,scale", [
+    ("ddim", [501], 7.5),                      # a single searched step
+    ("plms", [777], 1.0),                      # one step: Euler stage evaluates the model twice at the same t
+    ("plms", [901, 301], 7.5),                 # Euler + one 2nd-order step
+    ("plms", [901, 601, 301], 1.0),            # up to the 3rd-order combination
+    ("dpm", [999, 500, 0], 7.5),               # S = 2: first-order start, first-order final
+    ("dpm", list(range(990, -1, -66)), 1.0),   # S = 15: no lower_order_final (steps >= 15), second order to the end
+    ("dpm", [0.95, 0.5, 0.25, 0.02], 1.0),     # continuous candidates in (0, 1], given unsorted below
+])
+def test_sd_sampler_edge_cases_vs_oracle(sampler, cand, scale):
+    """Short / long / continuous schedules through the three samplers at batch 1, against the CPU oracle's run of the
+    reference algorithm: PSNR >= 30 dB on the final latents (peak = the oracle latents' range)."""
+    from autodiffusion_b200.sd_ddim import DDIMSampler, DPMSolverSampler, LatentDiffusionUNet, PLMSSampler
+
+    m, sd = _build(SMALL)
+    ld = LatentDiffusionUNet(m)
+    gen = torch.Generator().manual_seed(len(cand) * 7 + int(scale))
+    x_T = torch.randn(1, 4, 64, 64, generator=gen)
+    ctx = torch.randn(1, 77, SMALL.context_dim, generator=gen)
+    uc = torch.randn(1, 77, SMALL.context_dim, generator=gen) if scale != 1.0 else None
+    if sampler == "dpm" and max(cand) <= 1:
+        cand = [cand[2], cand[0], cand[3], cand[1]]
+    model = lambda x, t, c: R.unet_forward(sd, SMALL, x, t, c)
+    acp = R.sd_alphas_cumprod()
+    if sampler == "ddim":
+        ref, S, cls = R.ddim_sample(model, x_T, ctx, uc, scale, cand, acp), len(cand), DDIMSampler
+    elif sampler == "plms":
+        ref, S, cls = R.plms_sample(model, x_T, ctx, uc, scale, cand, acp), len(cand), PLMSSampler
+    else:
+        ref, S, cls = R.dpm_solver_sample(model, x_T, ctx, uc, scale, cand, acp), len(cand) - 1, DPMSolverSampler
+    out, _ = cls(ld).sample(S=S, conditioning=ctx.to(DEV), batch_size=1, shape=[4, 64, 64], verbose=False,
+                            unconditional_guidance_scale=scale, unconditional_conditioning=None if uc is None else uc.to(DEV),
+                            eta=0.0, x_T=x_T.to(DEV), sampled_timestep=cand)
+    out = out.cpu()
+    peak = (ref.max() - ref.min()).item()
+    psnr = 10 * np.log10(peak * peak / max(((out.double() - ref.double()) ** 2).mean().item(), 1e-30))
+    print(f"{sampler} cand={cand if len(cand) < 6 else str(cand[:3]) + '...'} scale={scale}: PSNR {psnr:.2f} dB")
+    assert torch.isfinite(out).all() and psnr >= 30.0

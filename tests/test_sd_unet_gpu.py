@@ -253,3 +253,48 @@ def test_sd_sampler_edge_cases_vs_oracle(sampler, cand, scale):
     psnr = 10 * np.log10(peak * peak / max(((out.double() - ref.double()) ** 2).mean().item(), 1e-30))
     print(f"{sampler} cand={cand if len(cand) < 6 else str(cand[:3]) + '...'} scale={scale}: PSNR {psnr:.2f} dB")
     assert torch.isfinite(out).all() and psnr >= 30.0
+
+
+def test_sd_candidate_evaluator_fid_matches_numpy_on_the_same_latents():
+    """sd_evaluator.SDCandidateEvaluator (the drop-in for search_ea.py's get_cand_fid around the fused sampler): the FID
+    from the device-side moments equals the reference's numpy statistic on the very features it saw; a population call
+    returns the same values; the last batch is truncated to num_samples."""
+    from autodiffusion_b200.evaluator import FIDStatistics
+    from autodiffusion_b200.sd_ddim import DDIMSampler, LatentDiffusionUNet
+    from autodiffusion_b200.sd_evaluator import SDCandidateEvaluator
+    from oracle import fid_ref
+
+    m, _ = _build(SMALL)
+    sampler = DDIMSampler(LatentDiffusionUNet(m))
+    d = 4
+    proj = torch.randn(4 * 64 * 64, d, generator=torch.Generator().manual_seed(3)).to(DEV) / 128.0
+    seen = []
+
+    def feature_fn(z):
+        f = z.reshape(z.shape[0], -1) @ proj
+        seen.append(f.cpu())
+        return f
+
+    def contexts(b, n):
+        g = torch.Generator(device=DEV)
+        g.manual_seed(50 + b)
+        return torch.randn((n, 77, SMALL.context_dim), generator=g, device=DEV), torch.zeros((n, 77, SMALL.context_dim), device=DEV)
+
+    rs = np.random.RandomState(0)
+    ref_f = rs.randn(64, d) * 2 + 1
+    ref_stats = FIDStatistics(*fid_ref.compute_statistics(ref_f))
+    ev = SDCandidateEvaluator(sampler, contexts, feature_fn, ref_stats, batch_size=4, num_samples=6, seed=1)
+    cands = [[801, 401, 1], [951, 301, 11]]
+    fids = []
+    for c in cands:
+        seen.clear()
+        fid = ev.get_cand_fid(c)
+        allf = torch.cat(seen).double().numpy()
+        assert allf.shape == (6, d)
+        want = fid_ref.frechet_distance(*fid_ref.compute_statistics(allf), ref_stats.mu, ref_stats.sigma)
+        print(f"SD get_cand_fid({c}) = {fid:.6f}, numpy on the same latents = {want:.6f}")
+        assert abs(fid - want) <= 1e-5 * max(1.0, abs(want))
+        fids.append(fid)
+    again = ev.evaluate(cands)  # same seeds per (candidate, batch): reproducible
+    assert np.allclose(again, fids, rtol=1e-4)
+    assert abs(fids[0] - fids[1]) > 1e-6

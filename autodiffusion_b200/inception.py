@@ -10,9 +10,11 @@ Inception-V3 run by PyTorch/cuDNN (the network's cost is ~0.2 % of a candidate's
 No Inception weights exist offline (`classify_image_graph_def.pb` / `pt_inception-2015-12-05` are downloads), so by
 default the network is randomly initialised from a fixed seed: FID values are then only comparable between runs of
 this code, exactly like the random-projection stand-in used by the tests. Pass `weights=` (a torchvision-layout
-state_dict file) for real features. torchvision's Inception differs from the TF-FID graph in three pooling details
-(pytorch-fid's FIDInceptionA/C/E), so claiming FID parity with the reference's numbers needs that module instead -
-any callable `uint8 NHWC -> [B, d]` is accepted as `feature_fn`.
+state_dict file, e.g. pytorch-fid's `pt_inception-2015-12-05`) for real features. With `fid_variant=True` (default) the
+graph is the FID Inception both references use - the 2015 TF graph of `evaluator_v1.py`, which pytorch-fid's InceptionV3
+(search_ea.py:45,171-182) reproduces on top of torchvision by changing three pooling details: the 3x3 average pools of the
+Mixed_5x / Mixed_6x / Mixed_7b blocks exclude the zero padding from the divisor, and Mixed_7c's pool branch is a MAX pool.
+Any callable `uint8 NHWC -> [B, d]` is accepted as `feature_fn` by the evaluators.
 """
 from __future__ import annotations
 
@@ -23,8 +25,52 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 
+def _fid_forward_a(self, x):  # InceptionA with count_include_pad=False
+    b1 = self.branch1x1(x)
+    b5 = self.branch5x5_2(self.branch5x5_1(x))
+    b3 = self.branch3x3dbl_3(self.branch3x3dbl_2(self.branch3x3dbl_1(x)))
+    bp = self.branch_pool(F.avg_pool2d(x, kernel_size=3, stride=1, padding=1, count_include_pad=False))
+    return [b1, b5, b3, bp]
+
+
+def _fid_forward_c(self, x):  # InceptionC with count_include_pad=False
+    b1 = self.branch1x1(x)
+    b7 = self.branch7x7_3(self.branch7x7_2(self.branch7x7_1(x)))
+    bd = self.branch7x7dbl_5(self.branch7x7dbl_4(self.branch7x7dbl_3(self.branch7x7dbl_2(self.branch7x7dbl_1(x)))))
+    bp = self.branch_pool(F.avg_pool2d(x, kernel_size=3, stride=1, padding=1, count_include_pad=False))
+    return [b1, b7, bd, bp]
+
+
+def _fid_forward_e(pool):
+    def fwd(self, x):  # InceptionE; pool = padding-excluding average (Mixed_7b) or max (Mixed_7c)
+        b1 = self.branch1x1(x)
+        b3 = self.branch3x3_1(x)
+        b3 = th.cat([self.branch3x3_2a(b3), self.branch3x3_2b(b3)], 1)
+        bd = self.branch3x3dbl_2(self.branch3x3dbl_1(x))
+        bd = th.cat([self.branch3x3dbl_3a(bd), self.branch3x3dbl_3b(bd)], 1)
+        bp = self.branch_pool(pool(x))
+        return [b1, b3, bd, bp]
+
+    return fwd
+
+
+def _apply_fid_variant(net):
+    import types
+
+    for name in ("Mixed_5b", "Mixed_5c", "Mixed_5d"):
+        m = getattr(net, name)
+        m._forward = types.MethodType(_fid_forward_a, m)
+    for name in ("Mixed_6b", "Mixed_6c", "Mixed_6d", "Mixed_6e"):
+        m = getattr(net, name)
+        m._forward = types.MethodType(_fid_forward_c, m)
+    avg = lambda x: F.avg_pool2d(x, kernel_size=3, stride=1, padding=1, count_include_pad=False)
+    mx = lambda x: F.max_pool2d(x, kernel_size=3, stride=1, padding=1)
+    net.Mixed_7b._forward = types.MethodType(_fid_forward_e(avg), net.Mixed_7b)
+    net.Mixed_7c._forward = types.MethodType(_fid_forward_e(mx), net.Mixed_7c)
+
+
 class InceptionPool3(nn.Module):
-    def __init__(self, weights: Optional[str] = None, seed: int = 0, half: Optional[bool] = None):
+    def __init__(self, weights: Optional[str] = None, seed: int = 0, half: Optional[bool] = None, fid_variant: bool = True):
         super().__init__()
         import torchvision
 
@@ -38,6 +84,8 @@ class InceptionPool3(nn.Module):
                     if isinstance(m, nn.Conv2d):
                         nn.init.kaiming_normal_(m.weight, nonlinearity="relu")
         net.fc = nn.Identity()
+        if fid_variant:
+            _apply_fid_variant(net)
         if weights is not None:
             sd = th.load(weights, map_location="cpu")
             missing, unexpected = net.load_state_dict(sd, strict=False)

@@ -172,3 +172,20 @@ def test_inception_pool3_feature_extractor_contract():
         m(u8.float())
     with pytest.raises(ValueError):
         m(u8.permute(0, 3, 1, 2))
+
+
+def test_inception_fid_variant_pooling():
+    """The three pooling details that turn torchvision's Inception into the FID graph (pytorch-fid's FIDInceptionA/C/E):
+    padding-excluding 3x3 average pools (a constant input stays constant up to the border) and a max pool in Mixed_7c."""
+    from autodiffusion_b200.inception import InceptionPool3
+
+    fid, tv = InceptionPool3(seed=0).net, InceptionPool3(seed=0, fid_variant=False).net
+    with torch.no_grad():
+        x = torch.ones(1, 192, 9, 9)
+        pf, pt = fid.Mixed_5b._forward(x)[3], tv.Mixed_5b._forward(x)[3]
+        assert (pf - pf[:, :, 4:5, 4:5]).abs().max() < 1e-5           # constant everywhere, border included
+        assert (pt[:, :, 0, 0] - pt[:, :, 4, 4]).abs().max() > 1e-3   # torchvision divides the border sums by 9 as well
+        assert torch.allclose(pf[:, :, 4, 4], pt[:, :, 4, 4], atol=1e-5)
+        x7 = torch.randn(1, 2048, 5, 5, generator=torch.Generator().manual_seed(1))
+        want = fid.Mixed_7c.branch_pool(torch.nn.functional.max_pool2d(x7, 3, 1, 1))
+        assert torch.allclose(fid.Mixed_7c._forward(x7)[3], want) and not torch.allclose(tv.Mixed_7c._forward(x7)[3], want)

@@ -589,6 +589,9 @@ class UNetModel(nn.Module):
             kvs = self.record_context(plan, cpad)
             self.record_forward(plan, x_in, t_in, kvs, out, ctx_tokens=tokens)
             entry = (plan, x_in, t_in, c_in, out)
+            generic = [k for k in self._plans if not (isinstance(k[0], str))]
+            if len(generic) >= 4:  # a handful of (batch, geometry) plans is all the callers use; drop the oldest
+                self._plans.pop(generic[0])
             self._plans[key] = entry
         plan, x_in, t_in, c_in, out = entry
         x_in.copy_(x.float())

@@ -86,11 +86,11 @@ def plms_golden():
     m = ref_unet(SMALL, sd)
     holder = Holder(m)
     cand = [641, 981, 201, 21, 861, 421]
-    x_T = torch.randn(2, 4, 64, 64, generator=g)
-    ctx = torch.randn(2, 77, SMALL.context_dim, generator=g)
-    uc = torch.randn(1, 77, SMALL.context_dim, generator=g).repeat(2, 1, 1)
+    x_T = torch.randn(1, 4, 64, 64, generator=g)  # batch 1: the CPU replay of this fixture runs in every test session
+    ctx = torch.randn(1, 77, SMALL.context_dim, generator=g)
+    uc = torch.randn(1, 77, SMALL.context_dim, generator=g)
     sampler = PLMSSampler(holder)
-    samples, _ = sampler.sample(S=len(cand), conditioning=ctx, batch_size=2, shape=[4, 64, 64], verbose=False,
+    samples, _ = sampler.sample(S=len(cand), conditioning=ctx, batch_size=1, shape=[4, 64, 64], verbose=False,
                                 unconditional_guidance_scale=7.5, unconditional_conditioning=uc, eta=0.0, x_T=x_T,
                                 sampled_timestep=np.array(cand))
     mine = R.plms_sample(lambda xx, tt, cc: R.unet_forward(sd, SMALL, xx, tt, cc), x_T, ctx, uc, 7.5, cand, R.sd_alphas_cumprod())
@@ -98,7 +98,7 @@ def plms_golden():
     print("small CFG-PLMS: max|ref - oracle| =", d, "model calls at", holder.calls)
     assert d <= 1e-4 * samples.abs().max().item()
     # the multistep combinations on recorded eps tensors: the fused update's bit-exactness fixture
-    es = [torch.randn(2, 4, 64, 64, generator=g) for _ in range(4)]
+    es = [torch.randn(1, 4, 64, 64, generator=g) for _ in range(4)]
 
     class Fixed:
         num_timesteps = 1000
@@ -117,8 +117,8 @@ def plms_golden():
         s2 = PLMSSampler(fx)
         s2.make_schedule(ddim_num_steps=len(cand), ddim_eta=0.0, verbose=False, sampled_timestep=sorted(cand))
         old = [es[3 - k] for k in range(n_old)][::-1]  # old_eps list, newest last: [.., es[3]]; here es[3], es[2], es[1]... newest = es[3]
-        xp, x0, e_t = s2.p_sample_plms(x_T, ctx, torch.full((2,), 421), index=2, unconditional_guidance_scale=1.0,
-                                       unconditional_conditioning=None, old_eps=list(old), t_next=torch.full((2,), 201))
+        xp, x0, e_t = s2.p_sample_plms(x_T, ctx, torch.full((1,), 421), index=2, unconditional_guidance_scale=1.0,
+                                       unconditional_conditioning=None, old_eps=list(old), t_next=torch.full((1,), 201))
         assert torch.equal(e_t, es[0])
         out[f"plms_x_prev_{n_old}"] = xp.numpy()
     np.savez_compressed(os.path.join(HERE, "sd_small_plms.npz"), cand=np.array(cand), x_T=x_T.numpy(), ctx=ctx.numpy(), uc=uc.numpy(),
@@ -150,13 +150,13 @@ def dpm_golden():
 
     holder = FloatHolder(m)
     cand = [981, 861, 641, 421, 201, 61, 0]  # descending, as the SD search keeps them (time_step + 1 entries)
-    x_T = torch.randn(2, 4, 64, 64, generator=g)
-    ctx = torch.randn(2, 77, SMALL.context_dim, generator=g)
-    uc = torch.randn(1, 77, SMALL.context_dim, generator=g).repeat(2, 1, 1)
+    x_T = torch.randn(1, 4, 64, 64, generator=g)
+    ctx = torch.randn(1, 77, SMALL.context_dim, generator=g)
+    uc = torch.randn(1, 77, SMALL.context_dim, generator=g)
     torch.Tensor.to = to_cpu
     try:
         sampler = DPMSolverSampler(holder)
-        samples, _ = sampler.sample(S=len(cand) - 1, conditioning=ctx, batch_size=2, shape=[4, 64, 64], verbose=False,
+        samples, _ = sampler.sample(S=len(cand) - 1, conditioning=ctx, batch_size=1, shape=[4, 64, 64], verbose=False,
                                     unconditional_guidance_scale=7.5, unconditional_conditioning=uc, eta=0.0, x_T=x_T,
                                     sampled_timestep=cand)
         # schedule scalars of the reference at the candidate's time points

@@ -74,8 +74,8 @@ def test_sd_small_cfg_plms_matches_reference():
     g = golden("sd_small_plms.npz")
     m, _ = _build(SMALL)
     ld = LatentDiffusionUNet(m)
-    args = dict(S=len(g["cand"]), conditioning=torch.tensor(g["ctx"]).to(DEV), batch_size=2, shape=[4, 64, 64], verbose=False,
-                unconditional_guidance_scale=7.5, unconditional_conditioning=torch.tensor(g["uc"]).to(DEV), eta=0.0,
+    args = dict(S=len(g["cand"]), conditioning=torch.tensor(g["ctx"]).to(DEV), batch_size=g["x_T"].shape[0], shape=[4, 64, 64],
+                verbose=False, unconditional_guidance_scale=7.5, unconditional_conditioning=torch.tensor(g["uc"]).to(DEV), eta=0.0,
                 x_T=torch.tensor(g["x_T"]).to(DEV), sampled_timestep=g["cand"])
     samples, _ = PLMSSampler(ld).sample(**args)
     ref = torch.tensor(g["samples"])
@@ -113,8 +113,8 @@ def test_sd_small_cfg_dpm_solver_matches_reference():
     m, _ = _build(SMALL)
     ld = LatentDiffusionUNet(m)
     cand = g["cand"].tolist()
-    args = dict(S=len(cand) - 1, conditioning=torch.tensor(g["ctx"]).to(DEV), batch_size=2, shape=[4, 64, 64], verbose=False,
-                unconditional_guidance_scale=7.5, unconditional_conditioning=torch.tensor(g["uc"]).to(DEV), eta=0.0,
+    args = dict(S=len(cand) - 1, conditioning=torch.tensor(g["ctx"]).to(DEV), batch_size=g["x_T"].shape[0], shape=[4, 64, 64],
+                verbose=False, unconditional_guidance_scale=7.5, unconditional_conditioning=torch.tensor(g["uc"]).to(DEV), eta=0.0,
                 x_T=torch.tensor(g["x_T"]).to(DEV), sampled_timestep=cand)
     samples, _ = DPMSolverSampler(ld).sample(**args)
     ref = torch.tensor(g["samples"])

@@ -23,6 +23,7 @@ Fusions relative to the reference's op list:
 from __future__ import annotations
 
 import os
+from collections import OrderedDict
 from dataclasses import dataclass
 from typing import Dict, List, Optional, Sequence, Tuple
 
@@ -205,17 +206,26 @@ class _UNetPlan:
         self.launches = 0
         model.record_forward(self.plan, self.x_in, self.t_in, self.y_in, self.out, skip)
 
-    def finalize(self, use_graph: bool):
-        # first run outside capture: sets kernel attributes, validates the schedule
-        self.launches = self.plan.run()
-        if use_graph:
-            th.cuda.current_stream().synchronize()
-            g = th.cuda.CUDAGraph()
-            with th.cuda.graph(g):
-                self.plan.run()
-            self.graph = g
+    def finalize(self, use_graph: bool, validate: bool = True):
+        # first run outside capture: sets kernel attributes, validates the schedule. Later plans of the same model and
+        # geometry launch the same kernels at the same shapes, so they may skip it (`validate=False`): a population of
+        # fresh skip sets then costs no device time to plan (launch count = recorded ops until the first real run).
+        self.launches = self.plan.run() if validate else self.plan.num_ops()
+        self._want_graph = use_graph
+
+    def capture(self):
+        """Capture this forward in its own CUDA graph. Deferred to the first stand-alone `replay()`: a plan that is
+        only ever consumed by `sampler.SchedulePlan` (which re-issues `plan.run()` into the schedule's graph) never
+        pays for a graph of its own."""
+        th.cuda.current_stream().synchronize()
+        g = th.cuda.CUDAGraph()
+        with th.cuda.graph(g):
+            self.plan.run()
+        self.graph = g
 
     def replay(self):
+        if self.graph is None and getattr(self, "_want_graph", False) and not th.cuda.is_current_stream_capturing():
+            self.capture()
         if self.graph is not None:
             self.graph.replay()
         else:
@@ -335,7 +345,11 @@ class Dynamic_UNetModel(nn.Module):
         self._generation = 0
         self._packed_generation = -1
         self._packed: Dict[str, object] = {}
-        self._plans: Dict[tuple, _UNetPlan] = {}
+        # recorded forwards, least recently used first. Bounded: once the progressive search widens its prune range
+        # nearly every candidate brings a new skip set, and each plan pins a launch list (+ a CUDA graph if it was
+        # ever replayed stand-alone). The empty-mask plan - most steps of most candidates - is never evicted.
+        self._plans: "OrderedDict[tuple, _UNetPlan]" = OrderedDict()
+        self.max_cached_plans = int(os.environ.get("ADB_MAX_UNET_PLANS", "24"))
         self._io: Dict[tuple, _IO] = {}
         self._pool: Optional[_Pool] = None
         self.gpu_launches = 0  # kernels launched through this model (bench.py reports it)
@@ -480,8 +494,17 @@ class Dynamic_UNetModel(nn.Module):
         ctx = _Ctx(self._pool, plan)
         dev = self._device()
         mc, ted = self.model_channels, self.model_channels * 4
-        stats = th.empty((B, 32, 2), dtype=th.float64, device=dev)  # scratch of the stand-alone stats pass
-        plan.keep(stats, up.x_in, up.t_in, up.y_in, up.out)
+        # Per-forward scratch (statistics arena, embedding vectors) comes from the model's shared pool like the
+        # activations and goes back to it at the end of the forward: a recorded plan pins no device memory of its own,
+        # so the number of cached / live plans does not grow the footprint (plans run one after another on a stream).
+        scratch: List[th.Tensor] = []
+
+        def salloc(shape, dtype):
+            t = ctx.alloc(shape, dtype)
+            scratch.append(t)
+            return t
+
+        plan.keep(up.x_in, up.t_in, up.y_in, up.out)
         # GroupNorm sums accumulated by the PRODUCING conv's epilogue (one slot per conv output that a
         # single-source GroupNorm will read); the whole arena is zeroed by one memset per forward.
         fuse_stats = os.environ.get("ADB_NO_FUSED_STATS", "0") != "1" and (H * W) % 32 == 0
@@ -489,7 +512,8 @@ class Dynamic_UNetModel(nn.Module):
         # symbolic pre-walk, so that producer can also accumulate sums in the concat's group layout
         cat_uses, n_cat = self._plan_concat_stats(H, W, skip, fuse_stats)
         n_slots = 2 * self.layer_num + 4
-        arena = th.empty((n_slots + n_cat, B, 32, 2), dtype=th.float64, device=dev)
+        stats = salloc((B, 32, 2), th.float64)  # scratch of the stand-alone stats pass
+        arena = salloc((n_slots + n_cat, B, 32, 2), th.float64)
         slot = [0]
         prod_idx = [0]
         produced: Dict[int, th.Tensor] = {}  # data_ptr of an activation -> its producer-filled stats
@@ -536,12 +560,15 @@ class Dynamic_UNetModel(nn.Module):
                           stats=st if st is not None else stats, stats_ready=st is not None, plan=plan, **kw)
 
         # timestep / label embedding (dynamic_unet.py:687-691) and every emb_layers product (:259)
-        te = ops.timestep_embedding(up.t_in, mc, plan=plan)
-        e1 = ops.linear(te, P["te0_w"], P["te0_b"], plan=plan)
-        emb = ops.linear(e1, P["te2_w"], P["te2_b"], silu_in=True, table=P.get("label"), idx=up.y_in, plan=plan)
+        te = ops.timestep_embedding(up.t_in, mc, out=salloc((B, mc), th.float32), plan=plan)
+        e1 = ops.linear(te, P["te0_w"], P["te0_b"], out=salloc((B, ted), th.float32), plan=plan)
+        emb = ops.linear(e1, P["te2_w"], P["te2_b"], silu_in=True, table=P.get("label"), idx=up.y_in,
+                         out=salloc((B, ted), th.float32), plan=plan)
         # every emb_layers Linear of the forward as ONE tensor-core product (fp32-grade: split-bf16 operands)
-        ss_all = ops.linear_tc(emb, P["emb_w"], P["emb_b"], P["emb_total"], silu_in=True, plan=plan)
         ss_total = P["emb_total"]
+        ss_all = ops.linear_tc(emb, P["emb_w"], P["emb_b"], ss_total, silu_in=True, plan=plan,
+                               out=salloc((B, ss_total), th.float32),
+                               hi_lo=(salloc((B, 1, 1, ted), th.bfloat16), salloc((B, 1, 1, ted), th.bfloat16)))
 
         def run_res(layer: ResBlock, srcs: List[th.Tensor]) -> th.Tensor:
             pk: _PackedRes = P[id(layer)]
@@ -637,6 +664,8 @@ class Dynamic_UNetModel(nn.Module):
         ops.conv_igemm([(g, 9)], P["out_w"], P["out_b"], self.out_channels, out=up.out,
                        out_mode=ops.OUT_F32_NCHW, plan=plan)
         ctx.release(g)
+        for t in scratch:
+            ctx.release(t)
 
     def _plan_concat_stats(self, H: int, W: int, skip: set, fuse_stats: bool):
         """Symbolic twin of the walk in record_forward: numbers every stats-producing conv output in
@@ -701,6 +730,60 @@ class Dynamic_UNetModel(nn.Module):
             h = block(blk, [h, hs.pop()])
         return uses, n_cat[0]
 
+    # ---- analytic cost model (scheduling of population evaluation: longest candidates first) ----
+    def layer_flops(self, H: Optional[int] = None, W: Optional[int] = None):
+        """-> (base, {layer_id: (run, skipped)}) in FLOP (2 x MAC) per image per forward: what block `layer_id` costs when
+        it runs and what is left of it when it is skipped (its 1x1 skip_connection, dynamic_unet.py:246-249). `base` is the
+        unskippable remainder (stem, out conv, time embedding). Reproduces SURVEY.md table A3' (hook-measured on the
+        reference module) to the digits printed there."""
+        H = H or self.image_size
+        W = W or self.image_size
+        mc, ted = self.model_channels, self.model_channels * 4
+        costs: Dict[int, Tuple[float, float]] = {}
+
+        def res(layer: ResBlock, cin, h, w):
+            cout = layer.out_channels
+            ho, wo = (h * 2, w * 2) if layer.up else ((h // 2, w // 2) if layer.down else (h, w))
+            px = ho * wo
+            skipc = 2.0 * cin * cout * px if isinstance(layer.skip_connection, nn.Conv2d) else 0.0
+            run = 2.0 * 9 * cin * cout * px + 2.0 * 9 * cout * cout * px + skipc + 2.0 * ted * 2 * cout
+            costs[layer.layer_id] = (run, skipc)
+            return cout, ho, wo
+
+        def attn(layer: AttentionBlock, c, h, w):
+            t = h * w
+            costs[layer.layer_id] = (2.0 * c * 3 * c * t + 2.0 * c * c * t + 4.0 * t * t * c, 0.0)
+
+        def block(blk, c, h, w):
+            for layer in blk.children():
+                if isinstance(layer, ResBlock):
+                    c, h, w = res(layer, layer.channels, h, w)
+                else:
+                    attn(layer, c, h, w)
+            return c, h, w
+
+        ch0 = int(self.channel_mult[0] * mc)
+        c, h, w = ch0, H, W
+        for blk in list(self.input_blocks)[1:]:
+            c, h, w = block(blk, c, h, w)
+        c, h, w = block(self.middle_block, c, h, w)
+        for blk in self.output_blocks:
+            c, h, w = block(blk, c, h, w)
+        base = 2.0 * 9 * self.in_channels * ch0 * H * W + 2.0 * 9 * ch0 * self.out_channels * H * W \
+            + 2.0 * mc * ted + 2.0 * ted * ted
+        return base, costs
+
+    def forward_flops(self, skip_layer: Sequence[int] = (), H: Optional[int] = None, W: Optional[int] = None) -> float:
+        """Algorithmic FLOP per image of one forward with `skip_layer` elided (F(cand) is the sum of
+        this over the candidate's steps)."""
+        key = (H or self.image_size, W or self.image_size)
+        cache = self.__dict__.setdefault("_flops_cache", {})
+        if key not in cache:
+            cache[key] = self.layer_flops(*key)
+        base, costs = cache[key]
+        skip = set(int(s) for s in skip_layer)
+        return base + sum(sk if lid in skip else run for lid, (run, sk) in costs.items())
+
     def _w2_skip_only(self, layer: ResBlock, split: Tuple[int, ...]) -> th.Tensor:
         key = (id(layer), "skip", split)
         cache = self._packed["w2_cache"]
@@ -714,7 +797,7 @@ class Dynamic_UNetModel(nn.Module):
         return cache[key]
 
     # ---- public forward ----
-    def get_plan(self, B: int, H: int, W: int, skip_layer: Sequence[int] = ()) -> _UNetPlan:
+    def get_plan(self, B: int, H: int, W: int, skip_layer: Sequence[int] = (), validate: Optional[bool] = None) -> _UNetPlan:
         if self._device().type != "cuda":
             raise RuntimeError("Dynamic_UNetModel runs on a CUDA device only: move it with .to('cuda') "
                                "(autodiffusion_b200 has no CPU path)")
@@ -725,8 +808,20 @@ class Dynamic_UNetModel(nn.Module):
         if up is None:
             with th.no_grad():
                 up = _UNetPlan(self, B, H, W, key[3])
-                up.finalize(use_graph=os.environ.get("ADB_NO_GRAPH", "0") != "1")
+                if validate is None or validate:
+                    validate = True
+                else:  # the caller allows skipping the validation run: only once this geometry ran for real
+                    validate = not any(k[:3] == key[:3] and getattr(v, "_validated", False) for k, v in self._plans.items())
+                up.finalize(use_graph=os.environ.get("ADB_NO_GRAPH", "0") != "1", validate=validate)
+                up._validated = validate
             self._plans[key] = up
+            if len(self._plans) > max(2, self.max_cached_plans):
+                for k in self._plans:  # oldest first
+                    if k[3] != () and k != key:
+                        del self._plans[k]  # a SchedulePlan still holding it keeps it alive; the cache lets go
+                        break
+        else:
+            self._plans.move_to_end(key)
         return up
 
     def forward(self, x, timesteps, y=None, skip_layer=[]):

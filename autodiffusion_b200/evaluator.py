@@ -164,6 +164,45 @@ def shard_batches(num_batches: int, rank: int, world_size: int) -> Sequence[int]
     return list(range(rank, num_batches, world_size))
 
 
+def fid_owner(cand_key: str, world_size: int) -> int:
+    """The rank that finishes the host-side FID of a batch-sharded candidate: a function of the candidate alone, so
+    every rank names the same owner whatever it evaluated before."""
+    return zlib.crc32(cand_key.encode()) % max(1, world_size)
+
+
+def schedule_population(costs: Sequence[float], num_batches: int, world_size: int):
+    """Static schedule of a population over the ranks of one box (longest first).
+
+    `costs[i]` = estimated work of candidate i (any unit; equal for all of its `num_batches` batches).
+    Returns (whole, shared):
+      whole  = {rank: [candidate indices, in the order that rank runs them]} - these candidates are sampled, reduced
+               and scored entirely by one rank: no collective, plan building and the host FID stay rank-local;
+      shared = [(candidate index, {rank: [batch indices]})] - the tail that does not divide by the world size is
+               split at batch granularity; each of these candidates costs one all-reduce of its moment buffer.
+    Whole candidates are placed longest-processing-time-first on the least loaded rank; the `n mod world` cheapest
+    ones form the tail and their batches fill the ranks up in the same greedy way, so 50 candidates on 8 ranks end at
+    25 batches per rank instead of 7-vs-6 whole candidates (89 %). Every rank computes the same schedule."""
+    n = len(costs)
+    world = max(1, int(world_size))
+    order = sorted(range(n), key=lambda i: (-float(costs[i]), i))
+    n_whole = n if world == 1 else (n // world) * world
+    load = [0.0] * world
+    whole = {r: [] for r in range(world)}
+    for i in order[:n_whole]:
+        r = min(range(world), key=lambda k: (load[k], k))
+        whole[r].append(i)
+        load[r] += float(costs[i])
+    shared = []
+    for i in order[n_whole:]:
+        per = {}
+        for b in range(num_batches):
+            r = min(range(world), key=lambda k: (load[k], k))
+            per.setdefault(r, []).append(b)
+            load[r] += float(costs[i]) / max(1, num_batches)
+        shared.append((i, per))
+    return whole, shared
+
+
 class CandidateEvaluator:
     """Owns the model, the base diffusion, the feature extractor and the reference statistics.
 
@@ -176,7 +215,7 @@ class CandidateEvaluator:
                  batch_size: int = 100, num_samples: int = 1000, image_size: int = 64, class_cond: bool = True,
                  clip_denoised: bool = True, cond_fn: Optional[Callable] = None, seed: int = 0,
                  rank: Optional[int] = None, world_size: Optional[int] = None, group=None, max_cached_plans: int = 8,
-                 fid_method: str = "eigh", fid_threads: Optional[int] = None, shard_fid: bool = True):
+                 fid_method: str = "sqrtm", fid_threads: Optional[int] = None, shard_fid: bool = True):
         self.model = model
         self.base_diffusion = base_diffusion
         self.feature_fn = feature_fn
@@ -192,16 +231,17 @@ class CandidateEvaluator:
         self._max_cached = max_cached_plans
         self._acc: Optional[MomentAccumulator] = None
         self.last_times: Dict[str, float] = {}
+        self.last_population: Dict[str, object] = {}
         self.vis_dict: Dict[str, dict] = {}
         # deferred FID: the host-side sqrtm of candidate i runs on this worker while candidate i+1 samples
         self._fid_pool: Optional[ThreadPoolExecutor] = None
         self._host_bufs: list = []
         assert fid_method in ("sqrtm", "eigh")
-        # "eigh" (default): frechet_distance_eigh - the same statistic through a symmetric eigenproblem, equal to the
-        # reference's sqrtm arithmetic to rounding (tests/test_evaluator_cpu.py; 4+ decimals on the d = 2048 population
-        # runs under profiles/) and ~30x cheaper on the host. "sqrtm": scipy.linalg.sqrtm exactly as the reference
-        # (evaluator_v1.py:114-157); its Python-level Schur loops hold the GIL and were measured to stretch the
-        # sampling thread's plan building 8x when run beside it.
+        # "sqrtm" (default): scipy.linalg.sqrtm exactly as the reference (evaluator_v1.py:114-157), including the
+        # eps-regularised retry and the complex-result handling. "eigh": frechet_distance_eigh - the same statistic
+        # through a symmetric eigenproblem (tests/test_evaluator_cpu.py bounds the difference, also for n < d), ~30x
+        # cheaper on the host and free of sqrtm's GIL-holding Python-level Schur loops; an explicit opt-in for
+        # throughput runs (scripts/population_eval.py, scripts/search_candidates.py --fid_method eigh).
         self.fid_method = fid_method
         self._ref_sqrt = None
         # BLAS threads for the host-side FID. torchrun exports OMP_NUM_THREADS=1, which would make the 2048x2048
@@ -211,23 +251,43 @@ class CandidateEvaluator:
         local_world = int(os.environ.get("LOCAL_WORLD_SIZE", "1"))
         self.fid_threads = fid_threads if fid_threads is not None else max(1, (os.cpu_count() or 1) // max(1, local_world))
         # The host-side sqrtm (several seconds at d=2048) is the serial term once sampling is sharded: every rank
-        # holds the all-reduced moments, so candidate number i is finished by rank i % world only and the values
-        # are exchanged in `resolve` (one tiny all-reduce per batch of candidates).
+        # holds the all-reduced moments, so a batch-sharded candidate is finished by rank `fid_owner(candidate)` only
+        # and the values are exchanged in `resolve` (one tiny all-reduce per batch of candidates).
         self.shard_fid = shard_fid
-        self._seq = 0
+        self._build_stream: Optional[th.cuda.Stream] = None
 
     # ---- plan cache keyed by what the launch schedule depends on ----
-    def _plan_for(self, cand, batch: int) -> SchedulePlan:
+    def _plan_for(self, cand, batch: int, overlapped: bool = False) -> SchedulePlan:
+        """`overlapped`: build without waiting for the device (previous candidates may still be sampling): recording,
+        weight packing of skipped-block variants and the graph capture run under a side stream, nothing executes."""
         active, per_step = resolve_candidate(cand, self.base_diffusion)
         key = (tuple(active.timestep_map), tuple(tuple(s) for s in per_step), batch, self.image_size, self.clip_denoised)
         plan = self._plans.get(key)
         if plan is None:
-            if len(self._plans) >= self._max_cached:
+            while len(self._plans) >= max(1, self._max_cached):
                 self._plans.pop(next(iter(self._plans)))
-            plan = SchedulePlan(self.model, active, per_step, batch, image_size=self.image_size,
-                                clip_denoised=self.clip_denoised, cond_fn=self.cond_fn, pack_uint8=True)
+            kw = dict(image_size=self.image_size, clip_denoised=self.clip_denoised, cond_fn=self.cond_fn, pack_uint8=True)
+            dev = self.model._device()
+            if overlapped and dev.type == "cuda":
+                if self._build_stream is None:
+                    self._build_stream = th.cuda.Stream(device=dev)
+                with th.cuda.stream(self._build_stream):  # H2D uploads of freshly packed operands do not queue behind sampling
+                    plan = SchedulePlan(self.model, active, per_step, batch, no_sync=True, **kw)
+                th.cuda.current_stream().wait_stream(self._build_stream)
+            else:
+                plan = SchedulePlan(self.model, active, per_step, batch, **kw)
             self._plans[key] = plan
         return plan
+
+    def candidate_cost(self, cand) -> float:
+        """Estimated work of one image of `cand` in FLOP (F(cand) = sum over its steps of the forward's
+        FLOPs minus what its skip list removes; the guidance pass adds the same amount to every step)."""
+        _, per_step = resolve_candidate(cand, self.base_diffusion)
+        ff = getattr(self.model, "forward_flops", None)
+        if not callable(ff):
+            return float(len(per_step))
+        guidance = 0.37 * ff(()) if self.cond_fn is not None else 0.0  # classifier fwd + input gradient ~ 80.8 / 219.4
+        return float(sum(ff(s, self.image_size, self.image_size) + guidance for s in per_step))
 
     def sample_batch(self, plan: SchedulePlan, cand_key: str, batch_index: int):
         """-> (uint8 NHWC images on the device, labels)."""
@@ -245,83 +305,67 @@ class CandidateEvaluator:
 
     def resolve(self, futures) -> list:
         """FID values of `submit_cand_fid` futures, in order, on every rank. Each rank waits for the candidates it
-        owns; with more than one rank the values are exchanged by one all-reduce of len(futures) doubles (every
-        rank must call this with the futures of the same candidates - they do: all ranks walk the same population)."""
+        owns; with more than one rank the values are exchanged by one all-reduce of 2 x len(futures) doubles (value and
+        the number of ranks that contributed it: exactly one, or the ranks disagree about who owns a candidate). Every
+        rank must call this with the futures of the same candidates - they do: all ranks walk the same population."""
         vals = [0.0 if isinstance(f, _RemoteFid) else float(f.result()) for f in futures]
         if any(isinstance(f, _RemoteFid) for f in futures) or (self.shard_fid and self.world_size > 1 and futures):
+            mine = [0.0 if isinstance(f, _RemoteFid) else 1.0 for f in futures]
             nccl = dist.get_backend(self.group) == "nccl"
-            t = th.tensor(vals, dtype=th.float64, device=self.model._device() if nccl else "cpu")
+            t = th.tensor(vals + mine, dtype=th.float64, device=self.model._device() if nccl else "cpu")
             dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group)
-            vals = t.cpu().tolist()
+            out = t.cpu().tolist()
+            vals, owners = out[:len(futures)], out[len(futures):]
+            bad = [i for i, c in enumerate(owners) if c != 1.0]
+            if bad:
+                raise RuntimeError(f"FID exchange: candidates {bad} were finished by {[owners[i] for i in bad]} ranks instead "
+                                   "of exactly one (ranks disagree on candidate ownership)")
         return vals
 
-    def evaluate_population(self, cands, args=None) -> list:
-        """FID of every candidate in `cands`, on every rank, with the POPULATION sharded over ranks: candidate i is
-        sampled (all of its batches), reduced and scored by rank i % world alone - no per-candidate collective, plan
-        building and the host-side sqrtm parallelise with the sampling - and the values are exchanged by one
-        all-reduce of len(cands) doubles at the end. Images are those of the batch-sharded path (seeds depend on
-        (seed, candidate, batch index) only). Every rank must pass the same list."""
-        futures = [self.submit_cand_fid(c, args, _whole_on=i % self.world_size) for i, c in enumerate(cands)]
-        return self.resolve(futures)
-
-    def submit_cand_fid(self, cand=None, args=None, _whole_on: Optional[int] = None) -> Future:
-        """Same work as `get_cand_fid`, but only the device part (sampling, moments, all-reduce, D2H of the
-        33.6 MB moment buffer) happens before this returns; mu / sigma / sqrtm run on a host worker thread.
-        The search driver keeps sampling the next candidate meanwhile (`fid_time` was serial in the
-        reference, :437-443)."""
+    def _apply_args(self, args):
         if args is not None:
             for k in ("batch_size", "num_samples", "image_size", "class_cond", "clip_denoised"):
                 if hasattr(args, k):
                     setattr(self, k, getattr(args, k))
-        if _whole_on is not None and _whole_on != self.rank:  # another rank evaluates this candidate entirely
-            self.last_times = dict(reset_time=0.0, sample_time=0.0, fid_time=0.0)
-            return _RemoteFid(_whole_on)
-        t0 = time.time()
-        plan = self._plan_for(cand, self.batch_size)
-        reset_time = time.time() - t0
-        t0 = time.time()
-        cand_key = str(cand)
-        num_batches = (self.num_samples + self.batch_size - 1) // self.batch_size
+
+    def _accumulator(self, dim: int) -> MomentAccumulator:
+        if self._acc is None or self._acc.dim != dim:
+            self._acc = MomentAccumulator(dim, self.model._device())
+        return self._acc
+
+    def _sample_into(self, plan: SchedulePlan, cand_key: str, batches) -> MomentAccumulator:
+        """Enqueue sampling + features + moment accumulation of `batches`; nothing here waits for the device."""
         acc = None
-        my_batches = range(num_batches) if _whole_on is not None else shard_batches(num_batches, self.rank, self.world_size)
-        for b in my_batches:
+        for b in batches:
             images, _ = self.sample_batch(plan, cand_key, b)
             keep = min(self.batch_size, self.num_samples - b * self.batch_size)  # arr[:num_samples], :432-433
             feats = self.feature_fn(images[:keep])
             if acc is None:
-                if self._acc is None or self._acc.dim != feats.shape[1]:
-                    self._acc = MomentAccumulator(feats.shape[1], feats.device)
-                acc = self._acc
+                acc = self._accumulator(feats.shape[1])
                 acc.reset()
             acc.add(feats)
         if acc is None:  # this rank had no batch of this candidate
-            dim = self.ref_stats.mu.shape[0]
-            if self._acc is None or self._acc.dim != dim:
-                self._acc = MomentAccumulator(dim, self.model._device())
-            acc = self._acc
+            acc = self._accumulator(self.ref_stats.mu.shape[0])
             acc.reset()
-        if _whole_on is None:
-            acc.all_reduce(self.group)
-        seq = self._seq
-        self._seq += 1
-        if _whole_on is None and self.shard_fid and self.world_size > 1 and seq % self.world_size != self.rank:
-            th.cuda.current_stream().synchronize() if acc.buf.is_cuda else None
-            self.last_times = dict(reset_time=reset_time, sample_time=time.time() - t0, fid_time=0.0)
-            return _RemoteFid(seq % self.world_size)
+        return acc
+
+    def _finish_async(self, acc: MomentAccumulator, times: dict, sync: bool, t0: float) -> Future:
+        """D2H of the moment buffer (pinned, async) and the host-side statistics / Frechet distance on the worker."""
         host = self._host_bufs.pop() if self._host_bufs and self._host_bufs[-1].numel() == acc.buf.numel() \
             else th.empty(acc.buf.numel(), dtype=th.float64).pin_memory()
         host.copy_(acc.buf, non_blocking=True)
         done = th.cuda.Event()
         done.record()
-        th.cuda.current_stream().synchronize()  # sample_time as the reference logs it (:435)
-        sample_time = time.time() - t0
+        if sync:
+            th.cuda.current_stream().synchronize()  # sample_time as the reference logs it (:435)
+            times["sample_time"] = time.time() - t0
         dim = acc.dim
-        times = dict(reset_time=reset_time, sample_time=sample_time, fid_time=0.0)
-        self.last_times = times
 
         def finish() -> float:
-            t1 = time.time()
             done.synchronize()
+            t1 = time.time()
+            if not sync:
+                times["sample_time"] = t1 - t0  # includes queueing behind earlier candidates of a pipelined population
             mu, sigma = MomentAccumulator.statistics_from(host.numpy(), dim)
             self._host_bufs.append(host)
             try:
@@ -345,6 +389,90 @@ class CandidateEvaluator:
         if self._fid_pool is None:
             self._fid_pool = ThreadPoolExecutor(max_workers=1, thread_name_prefix="adb-fid")
         return self._fid_pool.submit(finish)
+
+    def evaluate_population(self, cands, args=None) -> list:
+        """FID of every candidate in `cands`, on every rank, with the POPULATION sharded over ranks (BASELINE
+        configs[2]). `schedule_population` places whole candidates longest-first (no per-candidate collective: plan
+        building, sampling, moments and the host FID of such a candidate stay on one rank) and splits the `n mod world`
+        tail at batch granularity, each tail candidate merged by ONE all-reduce of its [n | sum_x | sum_xx] buffer
+        (NCCL over NVLink). Inside a rank the launch plan of candidate i+1 is recorded and captured while candidate i
+        is still sampling (nothing in the build waits for the device). The FID values are exchanged by one all-reduce
+        at the end. Images are those of the single-rank path (seeds depend on (seed, candidate, batch index) only).
+        Every rank must pass the same list."""
+        self._apply_args(args)
+        cands = list(cands)
+        n = len(cands)
+        num_batches = (self.num_samples + self.batch_size - 1) // self.batch_size
+        costs = [self.candidate_cost(c) for c in cands]
+        whole, shared = schedule_population(costs, num_batches, self.world_size)
+        mine = whole[self.rank]
+        todo = [(i, range(num_batches), False) for i in mine] + [(i, per.get(self.rank, []), True) for i, per in shared]
+        futures: list = [None] * n
+        for r, idxs in whole.items():
+            if r != self.rank:
+                for i in idxs:
+                    futures[i] = _RemoteFid(r)
+        t_start = time.time()
+        build_s, allreduce_ms = 0.0, []
+        t0 = time.time()
+        # a rank without a batch of a shared candidate only joins its all-reduce: no plan needed
+        build = lambda k, **kw: self._plan_for(cands[todo[k][0]], self.batch_size, **kw) if len(todo[k][1]) else None
+        nxt = build(0) if todo else None
+        build_first = time.time() - t0
+        for j, (i, batches, is_shared) in enumerate(todo):
+            plan, cand_key = nxt, str(cands[i])
+            times = dict(reset_time=0.0, sample_time=0.0, fid_time=0.0)
+            t0 = time.time()
+            acc = self._sample_into(plan, cand_key, batches)
+            if is_shared:  # the path's data-plane collective: one all-reduce of the candidate's moments
+                e0, e1 = th.cuda.Event(enable_timing=True), th.cuda.Event(enable_timing=True)
+                e0.record()
+                acc.all_reduce(self.group)
+                e1.record()
+                allreduce_ms.append((e0, e1))
+            owner = fid_owner(cand_key, self.world_size) if is_shared else self.rank
+            if owner == self.rank:
+                futures[i] = self._finish_async(acc, times, sync=False, t0=t0)
+            else:
+                futures[i] = _RemoteFid(owner)
+            if j + 1 < len(todo):  # host-side build of the next candidate overlaps this one's sampling on the device
+                t1 = time.time()
+                nxt = build(j + 1, overlapped=True)
+                build_s += time.time() - t1
+        vals = self.resolve(futures)
+        th.cuda.current_stream().synchronize() if th.cuda.is_available() else None
+        self.last_population = dict(
+            candidates=n, whole_per_rank=[len(whole[r]) for r in range(self.world_size)], shared=len(shared),
+            plan_build_first_s=build_first, plan_build_overlapped_s=build_s, wall_s=time.time() - t_start,
+            allreduce_ms=[a.elapsed_time(b) for a, b in allreduce_ms], est_cost_min_max=(min(costs), max(costs)) if costs else None)
+        return vals
+
+    def submit_cand_fid(self, cand=None, args=None, _whole_on: Optional[int] = None) -> Future:
+        """Same work as `get_cand_fid`, but only the device part (sampling, moments, all-reduce, D2H of the
+        33.6 MB moment buffer) happens before this returns; mu / sigma / sqrtm run on a host worker thread.
+        The search driver keeps sampling the next candidate meanwhile (`fid_time` was serial in the
+        reference, :437-443). `_whole_on=r`: rank r alone samples and scores the candidate (no collective)."""
+        self._apply_args(args)
+        if _whole_on is not None and _whole_on != self.rank:  # another rank evaluates this candidate entirely
+            self.last_times = dict(reset_time=0.0, sample_time=0.0, fid_time=0.0)
+            return _RemoteFid(_whole_on)
+        t0 = time.time()
+        plan = self._plan_for(cand, self.batch_size)
+        times = dict(reset_time=time.time() - t0, sample_time=0.0, fid_time=0.0)
+        self.last_times = times
+        t0 = time.time()
+        cand_key = str(cand)
+        num_batches = (self.num_samples + self.batch_size - 1) // self.batch_size
+        my_batches = range(num_batches) if _whole_on is not None else shard_batches(num_batches, self.rank, self.world_size)
+        acc = self._sample_into(plan, cand_key, my_batches)
+        if _whole_on is None:
+            acc.all_reduce(self.group)
+        owner = fid_owner(cand_key, self.world_size)
+        if _whole_on is None and self.shard_fid and self.world_size > 1 and owner != self.rank:
+            th.cuda.current_stream().synchronize() if acc.buf.is_cuda else None
+            times["sample_time"] = time.time() - t0
+            return _RemoteFid(owner)
+        return self._finish_async(acc, times, sync=True, t0=t0)
 
     def is_legal(self, cand: str, log: Callable[[str], None] = print) -> bool:
         """…progressive.py:355-367: candidates are `str(dict)` keys; same log line format."""

@@ -562,14 +562,18 @@ def pack_linear_weight_split(weight: torch.Tensor, device=None) -> torch.Tensor:
 
 
 def linear_tc(x: torch.Tensor, w_split: torch.Tensor, bias: Optional[torch.Tensor], nout: int, silu_in: bool = False,
-              out: Optional[torch.Tensor] = None, plan: Optional[Plan] = None) -> torch.Tensor:
+              out: Optional[torch.Tensor] = None, plan: Optional[Plan] = None, hi_lo: Optional[tuple] = None) -> torch.Tensor:
     """out[b, :] = act(x[b, :]) W^T + bias on tensor cores at fp32-grade accuracy: act(x) is split into bf16
     hi + lo, the weight was split by `pack_linear_weight_split`, and the three cross products that matter run as
     one implicit GEMM over three K-segments with fp32 accumulation and fp32 output. x fp32 [b, k], k % 8 == 0."""
     b, k = x.shape
     assert w_split.shape[1] == 3 * k and k % 8 == 0
-    hi = torch.empty((b, 1, 1, k), dtype=torch.bfloat16, device=x.device)
-    lo = torch.empty_like(hi)
+    if hi_lo is not None:  # caller-provided scratch for the bf16 hi / lo halves (bf16 [b, 1, 1, k] each)
+        hi, lo = hi_lo
+        assert tuple(hi.shape) == (b, 1, 1, k) and tuple(lo.shape) == (b, 1, 1, k)
+    else:
+        hi = torch.empty((b, 1, 1, k), dtype=torch.bfloat16, device=x.device)
+        lo = torch.empty_like(hi)
     _lib.check(_lib.lib().adb_split_bf16(_ph(plan), _dev(x, "x", torch.float32), _dev(hi, "hi", torch.bfloat16),
                                          _dev(lo, "lo", torch.bfloat16), b * k, int(bool(silu_in)), _stream()),
                "adb_split_bf16")

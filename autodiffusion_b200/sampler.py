@@ -66,7 +66,10 @@ class SchedulePlan:
 
     def __init__(self, model, active_diffusion, per_step_skips: Sequence[Sequence[int]], batch: int,
                  image_size: Optional[int] = None, clip_denoised: bool = True, cond_fn: Optional[Callable] = None,
-                 pack_uint8: bool = True, use_graph: Optional[bool] = None):
+                 pack_uint8: bool = True, use_graph: Optional[bool] = None, no_sync: bool = False):
+        """`no_sync`: build without waiting for (or adding work to) the device - no validation run of freshly recorded
+        forwards, graph capture on the current (side) stream without the device-wide synchronize of `torch.cuda.graph`.
+        Used by `CandidateEvaluator.evaluate_population` to plan candidate i+1 while candidate i samples."""
         if active_diffusion.model_mean_type != ModelMeanType.EPSILON:
             raise NotImplementedError("SchedulePlan covers epsilon-prediction models")
         if active_diffusion.rescale_timesteps:
@@ -92,7 +95,7 @@ class SchedulePlan:
 
         self._order = list(range(self.K))[::-1]  # sampling runs high -> low (gaussian_diffusion.py:690)
         with th.no_grad():
-            self.steps = [model.get_plan(batch, hw, hw, self.per_step_skips[i]) for i in self._order]
+            self.steps = [model.get_plan(batch, hw, hw, self.per_step_skips[i], validate=not no_sync) for i in self._order]
         io = model.io_buffers(batch, hw, hw)
         self.x, self.t_in, self.y, self.model_out = io.x_in, io.t_in, io.y_in, io.out
         self.final = self.x  # x_0 ends up in the shared input buffer
@@ -106,27 +109,44 @@ class SchedulePlan:
                 grads[key] = th.zeros(self.shape, dtype=th.float32, device=dev)
             self.grad = grads[key]
         self.u8 = th.empty((batch, hw, hw, model.in_channels), dtype=th.uint8, device=dev) if pack_uint8 else None
-        self.launches = sum(up.launches for up in self.steps) + self.K + (1 if pack_uint8 else 0)
+        self._count_launches()
         # native classifier guidance: forward + input-gradient recorded once over the shared x / t / y buffers
         self.guidance: Optional[ops.Plan] = None
         if isinstance(cond_fn, ClassifierGuidance):
             if self.y is None:  # unconditional UNet guided by a classifier: labels still drive the guidance
                 self.y = th.zeros((batch,), dtype=th.int64, device=dev)
             self.guidance = cond_fn.shared_plan(self.x, self.t_in, self.y, self.grad)
-            self.launches += self.K * self.guidance.launches_per_run
+            self._count_launches()
         self.graph: Optional[th.cuda.CUDAGraph] = None
         if (cond_fn is None or self.guidance is not None) and use_graph:
-            th.cuda.current_stream().synchronize()
             g = th.cuda.CUDAGraph()
-            with th.cuda.graph(g):
-                self._run_chain()
+            if no_sync:
+                # capture on the caller's side stream: nothing executes and nothing inside allocates, so neither the
+                # device-wide synchronize nor the private memory pool handling of `torch.cuda.graph` is needed
+                if th.cuda.current_stream() == th.cuda.default_stream():
+                    raise RuntimeError("SchedulePlan(no_sync=True) must be built under a non-default torch.cuda.stream")
+                g.capture_begin(capture_error_mode="thread_local")
+                try:
+                    self._run_chain()
+                finally:
+                    g.capture_end()
+            else:
+                th.cuda.current_stream().synchronize()
+                with th.cuda.graph(g):
+                    self._run_chain()
             self.graph = g
+            self._count_launches()  # plans built without a validation run learnt their launch counts during capture
+
+    def _count_launches(self):
+        self.launches = sum(up.launches for up in self.steps) + self.K + (1 if self.u8 is not None else 0)
+        if getattr(self, "guidance", None) is not None:
+            self.launches += self.K * self.guidance.launches_per_run
 
     def _step(self, n: int):
         """UNet forward of the n-th sampled step (cached graph as a child node when capturing)."""
         self.t_in.fill_(self.t_values[n])  # original timestep, as _WrappedModel maps it (respace.py:122-127)
         if th.cuda.is_current_stream_capturing():
-            self.steps[n].plan.run()  # re-issue the recorded launches into the schedule's own graph
+            self.steps[n].launches = self.steps[n].plan.run()  # re-issue the recorded launches into the schedule's own graph
         else:
             self.steps[n].replay()
 

@@ -96,6 +96,7 @@ class EvolutionSearcher:
         self.shard_population = shard_population
         self._pending: Dict[str, Future] = {}
         self._queued: Dict[str, object] = {}
+        self._selection_done = False  # selection / widening of `self.epoch` already applied (see load_state)
         if not getattr(args, "use_ddim", True):
             raise NotImplementedError("the evaluator path covers DDIM sampling (use_ddim=True), as every search script sets")
         if evaluator is None:
@@ -167,7 +168,8 @@ class EvolutionSearcher:
         self.join()
         self.log("select ......")
         t = self.keep_top_k[k]
-        t += candidates
+        have = set(t)  # guard: an uninterrupted run never re-adds an individual (every new one passed is_legal)
+        t += [c for c in candidates if not (c in have or have.add(c))]
         t.sort(key=key, reverse=reverse)
         self.keep_top_k[k] = t[:k]
 
@@ -324,7 +326,7 @@ class EvolutionSearcher:
             pickle.dump(dict(vis_dict=self.vis_dict, keep_top_k=self.keep_top_k, epoch=self.epoch,
                              candidates=self.candidates, skip_layer_range=self.skip_layer_range,
                              last_best_cand=self.last_best_cand, py_random=random.getstate(),
-                             np_random=np.random.get_state()), f)
+                             np_random=np.random.get_state(), selection_done=self._selection_done), f)
 
     def load_state(self, path: str):
         with open(path, "rb") as f:
@@ -332,6 +334,9 @@ class EvolutionSearcher:
         self.vis_dict, self.keep_top_k, self.epoch = st["vis_dict"], st["keep_top_k"], st["epoch"]
         self.candidates, self.skip_layer_range = st["candidates"], st["skip_layer_range"]
         self.last_best_cand = st["last_best_cand"]
+        # written from inside the loop, i.e. AFTER selection / prune-range widening of `epoch`: `search()` must not
+        # repeat them for that epoch (it would re-add the generation to the top-k lists and widen the range twice)
+        self._selection_done = bool(st.get("selection_done", False))
         random.setstate(st["py_random"])
         np.random.set_state(st["np_random"])
 
@@ -354,24 +359,26 @@ class EvolutionSearcher:
                 self.candidates += self.mutate_init_x(x0=init_cand, m_prob=0.1,
                                                       mutation_num=self.population_num - self.population_num // 2 - 1)
         while self.epoch < self.max_epochs:
-            self.log("epoch = {}".format(self.epoch))
-            fid_of = lambda x: self.vis_dict[x]["fid"]
-            self.update_top_k(self.candidates, k=self.select_num, key=fid_of)
-            self.update_top_k(self.candidates, k=50, key=fid_of)
-            self.log("epoch = {} : top {} result".format(self.epoch, len(self.keep_top_k[50])))
-            for i, cand in enumerate(self.keep_top_k[50]):
-                self.log("No.{} {} fid = {}".format(i + 1, cand, self.vis_dict[cand]["fid"]))
-            # progressive widening of the prune range (:684-693)
-            if self.skip_layer_range[1] == 0 and (self.last_best_cand == self.keep_top_k[50][0] or self.epoch > 4):
-                self.skip_layer_range[1] = self.max_prun / 5
-            elif 0 < self.skip_layer_range[1] < self.max_prun:
-                self.skip_layer_range[1] += self.max_prun / 5
-            if self.skip_layer_range[0] == 0 and self.epoch > 5:
-                self.skip_layer_range[0] = self.min_prun
-            self.last_best_cand = self.keep_top_k[50][0]
-            self.log("skip_layer_range_left = {} , skip_layer_range_right {}".format(*self.skip_layer_range))
-            if state_path:
-                self.save_state(state_path)
+            if not self._selection_done:  # a state loaded from `state_path` resumes right after this block
+                self.log("epoch = {}".format(self.epoch))
+                fid_of = lambda x: self.vis_dict[x]["fid"]
+                self.update_top_k(self.candidates, k=self.select_num, key=fid_of)
+                self.update_top_k(self.candidates, k=50, key=fid_of)
+                self.log("epoch = {} : top {} result".format(self.epoch, len(self.keep_top_k[50])))
+                for i, cand in enumerate(self.keep_top_k[50]):
+                    self.log("No.{} {} fid = {}".format(i + 1, cand, self.vis_dict[cand]["fid"]))
+                # progressive widening of the prune range (:684-693)
+                if self.skip_layer_range[1] == 0 and (self.last_best_cand == self.keep_top_k[50][0] or self.epoch > 4):
+                    self.skip_layer_range[1] = self.max_prun / 5
+                elif 0 < self.skip_layer_range[1] < self.max_prun:
+                    self.skip_layer_range[1] += self.max_prun / 5
+                if self.skip_layer_range[0] == 0 and self.epoch > 5:
+                    self.skip_layer_range[0] = self.min_prun
+                self.last_best_cand = self.keep_top_k[50][0]
+                self.log("skip_layer_range_left = {} , skip_layer_range_right {}".format(*self.skip_layer_range))
+                self._selection_done = True
+                if state_path:
+                    self.save_state(state_path)
             if self.epoch + 1 == self.max_epochs:
                 break
             mutation = self.get_mutation(self.select_num, self.mutation_num, self.m_prob)
@@ -379,5 +386,6 @@ class EvolutionSearcher:
             self.candidates += self.get_cross(self.select_num, self.crossover_num)
             self.get_random(self.population_num)
             self.epoch += 1
+            self._selection_done = False
         self.join()
         return self.keep_top_k[50]

@@ -278,9 +278,67 @@ def gen_config1():
                         uint8=((imgs[-1] + 1) * 127.5).clamp(0, 255).to(torch.uint8).permute(0, 2, 3, 1).contiguous().numpy())
 
 
+def gen_config2():
+    """BASELINE config 2 (the benchmarked candidate) at batch 8: full ADM-G 64 + depth-4 classifier, the published
+    10-step schedule with its block-skip mask (GD/sample_imagenet64_classifier_guidance_dynamic_subnet.sh:13-14),
+    classifier_scale 1.0 - the reference's own ddim_sample_loop with the search script's closures
+    (...progressive.py:383-397) on CPU. Also records which (timestep, skip list) pairs the UNet saw."""
+    import torch.nn.functional as F
+
+    model, diffusion = build(ADM_FLAGS)
+    cfg = cfg_of(ADM_FLAGS)
+    sd = weights.make_state_dict(unet_ref.param_shapes(cfg), seed=0)
+    model.load_state_dict(sd)
+    cd = classifier_defaults()
+    cd.update(classifier_depth=4)
+    clf = create_classifier(**cd).eval()
+    ccfg = unet_ref.classifier64_config(depth=4, width=128)
+    csd = weights.make_state_dict(unet_ref.param_shapes(ccfg, encoder_only=True), seed=1)
+    clf.load_state_dict(csd)
+    reset_diffusion = load_reset_diffusion()
+    base = copy.deepcopy(diffusion)
+    B = 8
+    noise = torch.randn(B, 3, 64, 64, generator=torch.Generator().manual_seed(12))
+    y = torch.randint(0, 1000, (B,), generator=torch.Generator().manual_seed(13))
+    cand = CANDIDATES["cand10"]
+    active = copy.deepcopy(base)
+    reset_diffusion(cand["timesteps"], active, base)
+    seen = []
+
+    def cond_fn(x, t, y=None, skip_layers=None, timesteps=None):
+        with torch.enable_grad():
+            x_in = x.detach().requires_grad_(True)
+            logits = clf(x_in, t)
+            log_probs = F.log_softmax(logits, dim=-1)
+            selected = log_probs[range(len(logits)), y.view(-1)]
+            return torch.autograd.grad(selected.sum(), x_in)[0] * 1.0
+
+    def model_fn(x, t, y=None, skip_layers=None, timesteps=None):
+        t_index = active.timestep_map.index(t[0])
+        seen.append((int(t[0]), list(skip_layers[t_index])))
+        return model(x, t, y, skip_layer=skip_layers[t_index])
+
+    import time
+    t0 = time.time()
+    imgs = active.ddim_sample_loop(model_fn, (B, 3, 64, 64), noise=noise, clip_denoised=True,
+                                   model_kwargs={"y": y, "skip_layers": cand["skip_layers"]}, cond_fn=cond_fn,
+                                   device="cpu", return_all_images=True)
+    print(f"config2 reference: {time.time() - t0:.1f} s for {B} images; final std {imgs[-1].std():.4f}; seen {seen}")
+    np.savez_compressed(os.path.join(HERE, "config2_admg64_cand10_guided.npz"), noise=noise.numpy(), y=y.numpy(),
+                        timesteps=np.array(cand["timesteps"], dtype=np.int64),
+                        skip_layers=np.array([",".join(map(str, s)) for s in cand["skip_layers"]]),
+                        seen_t=np.array([s[0] for s in seen], dtype=np.int64),
+                        seen_skip=np.array([",".join(map(str, s[1])) for s in seen]),
+                        final=imgs[-1].numpy(), step1=imgs[1].numpy(), step5=imgs[5].numpy(),
+                        uint8=((imgs[-1] + 1) * 127.5).clamp(0, 255).to(torch.uint8).permute(0, 2, 3, 1).contiguous().numpy())
+
+
 if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "config1":
         gen_config1()
+        sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "config2":
+        gen_config2()
         sys.exit(0)
     torch.manual_seed(0)
     gen_tables()
@@ -289,4 +347,5 @@ if __name__ == "__main__":
     gen_ddim_small()
     gen_unet("admg64", ADM_FLAGS, 1, [(153, []), (676, [30, 10, 39, 4, 15, 46, 49, 54, 8])])
     gen_config1()
+    gen_config2()
     print("done")

@@ -152,6 +152,97 @@ def test_sharded_host_fid_values_reach_every_rank(tmp_path):
         assert np.load(tmp_path / f"v{r}.npy").tolist() == [0.25, 1.25, 2.25, 3.25, 4.25]
 
 
+def _disagree_worker(rank, world, port, tmp):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from concurrent.futures import Future
+
+    from autodiffusion_b200.evaluator import CandidateEvaluator
+
+    ev = object.__new__(CandidateEvaluator)
+    ev.shard_fid, ev.world_size, ev.rank, ev.group = True, world, rank, None
+    f = Future()
+    f.set_result(1.5)  # BOTH ranks claim the candidate: the SUM would silently read 3.0
+    try:
+        ev.resolve([f])
+        out = "no error"
+    except RuntimeError as e:
+        out = str(e)
+    open(os.path.join(tmp, f"d{rank}.txt"), "w").write(out)
+    dist.destroy_process_group()
+
+
+def test_fid_exchange_detects_ownership_disagreement(tmp_path):
+    """if ranks disagree on who finishes a candidate the SUM all-reduce returns 2x the FID or 0.0 (a
+    'perfect' candidate). resolve() all-reduces an owner count beside the values and raises unless it is exactly 1."""
+    world, port = 2, 30700 + (os.getpid() % 500)
+    mp.spawn(_disagree_worker, args=(world, port, str(tmp_path)), nprocs=world, join=True)
+    for r in range(world):
+        assert "instead of exactly one" in open(tmp_path / f"d{r}.txt").read()
+
+
+def test_fid_owner_depends_on_the_candidate_only():
+    from autodiffusion_b200.evaluator import fid_owner
+
+    keys = [str({"timesteps": [i, 2 * i + 1], "skip_layers": [[], [i % 5]]}) for i in range(64)]
+    for world in (1, 2, 8):
+        owners = [fid_owner(k, world) for k in keys]
+        assert all(0 <= o < world for o in owners)
+        assert owners == [fid_owner(k, world) for k in keys]  # no hidden per-rank state (the old `_seq` counter)
+        if world > 1:
+            assert len(set(owners)) == world  # spread over ranks
+
+
+def test_population_schedule_longest_first_with_a_batch_sharded_tail():
+    """BASELINE configs[2]: 50 candidates x 4 batches on 8 ranks. Whole candidates longest-first, the 50 mod 8 tail split
+    by batches: every (candidate, batch) exactly once, 25 batches on every rank (dealing i % world caps at 7 vs 6 = 89 %)."""
+    from autodiffusion_b200.evaluator import schedule_population
+
+    rs = np.random.RandomState(3)
+    for n, nb, world in [(50, 4, 8), (8, 4, 4), (3, 4, 8), (7, 3, 2), (5, 1, 1), (13, 5, 4)]:
+        costs = (1.0 + 0.1 * rs.rand(n)).tolist()
+        whole, shared = schedule_population(costs, nb, world)
+        assert schedule_population(costs, nb, world) == (whole, shared)  # deterministic: every rank computes the same
+        seen = [(i, b) for r in whole for i in whole[r] for b in range(nb)]
+        seen += [(i, b) for i, per in shared for bs in per.values() for b in bs]
+        assert sorted(seen) == [(i, b) for i in range(n) for b in range(nb)]
+        assert len(shared) == (n % world if world > 1 else 0)
+        load = [sum(costs[i] for i in whole[r]) + sum(costs[i] / nb * len(per.get(r, [])) for i, per in shared)
+                for r in range(world)]
+        ideal = sum(costs) / world
+        if n >= world:
+            assert max(load) <= ideal * 1.12, (n, nb, world, load)
+        for r in whole:  # longest first inside a rank
+            assert [costs[i] for i in whole[r]] == sorted((costs[i] for i in whole[r]), reverse=True)
+    whole, shared = schedule_population([1.0] * 50, 4, 8)
+    assert [len(whole[r]) for r in range(8)] == [6] * 8 and len(shared) == 2
+    assert all(sum(len(per.get(r, [])) for _, per in shared) == 1 for r in range(8))
+
+
+def test_eigh_and_sqrtm_agree_when_samples_are_fewer_than_dimensions():
+    """searches use 1000 samples at d = 2048, i.e. rank-deficient covariances; the opt-in eigh form must stay
+    within the north star's +-0.1 of the reference's sqrtm arithmetic there (measured here: ~1e-6 relative)."""
+    from autodiffusion_b200.evaluator import FIDStatistics
+
+    rs = np.random.RandomState(5)
+    d, n = 160, 60
+    f1 = rs.randn(n, d) * (0.5 + rs.rand(d)) + 0.2
+    f2 = rs.randn(4 * d, d) @ (np.eye(d) + 0.05 * rs.randn(d, d))
+    a = FIDStatistics(*fid_ref.compute_statistics(f1))  # singular: rank <= n - 1
+    b = FIDStatistics(*fid_ref.compute_statistics(f2))
+    x, y = a.frechet_distance(b), a.frechet_distance_eigh(b)
+    assert np.linalg.matrix_rank(a.sigma) < d
+    assert abs(x - y) <= 1e-4 * abs(x) and abs(x - y) <= 0.1
+
+
+def test_default_fid_method_is_the_reference_arithmetic():
+    import inspect
+
+    from autodiffusion_b200.evaluator import CandidateEvaluator
+
+    assert inspect.signature(CandidateEvaluator.__init__).parameters["fid_method"].default == "sqrtm"
+
+
 def test_remote_fid_placeholder_refuses_a_direct_result():
     from autodiffusion_b200.evaluator import _RemoteFid
 

@@ -131,26 +131,29 @@ def test_population_sharding_visits_the_same_individuals():
 
 
 def test_save_and_resume(tmp_path):
+    """Resume exactly as scripts/search_candidates.py does - `load_state(path)` then `search(path)` - from a state
+    written inside the loop (after epoch e's selection and prune-range widening). The resumed run must not repeat
+    that selection: same individuals, same top list and prune range as the uninterrupted golden run, no duplicate
+    top-k entries, nothing evaluated twice."""
     g = json.load(open(os.path.join(GOLDEN, "search_trace.json")))["random_init"]
     cfg = dict(g["config"])
-    path = str(tmp_path / "state.pkl")
-    # run 1: stop after 4 epochs (state is written at the end of every epoch's selection)
-    s1 = build(dict(cfg, max_epochs=4), StubEvaluator(False), lambda l: None)
-    random.seed(cfg["seed"])
-    np.random.seed(cfg["seed"])
-    s1.search(state_path=path)
-    # run 2: a fresh process would construct the searcher again and resume; visited individuals are not re-evaluated
-    ev2 = StubEvaluator(False)
-    s2 = build(cfg, ev2, lambda l: None)
-    random.seed(12345)  # whatever the new process seeded: load_state restores both generators
-    s2.load_state(path)
-    assert s2.epoch == 3 and len(s2.vis_dict) == len(s1.vis_dict)
-    # the saved state is the one at epoch 3's selection; continue from the operators of that epoch
-    mutation = s2.get_mutation(s2.select_num, s2.mutation_num, s2.m_prob)
-    s2.candidates = mutation
-    s2.candidates += s2.get_cross(s2.select_num, s2.crossover_num)
-    s2.get_random(s2.population_num)
-    s2.epoch += 1
-    top = s2.search()
-    assert list(s2.vis_dict.keys()) == g["visited"] and top == g["top"]
-    assert not set(ev2.calls) & set(s1.vis_dict.keys())
+    for stop_after in (1, 4):
+        path = str(tmp_path / f"state{stop_after}.pkl")
+        # run 1: dies after `stop_after` epochs (the state file is the one written at that epoch's selection)
+        s1 = build(dict(cfg, max_epochs=stop_after), StubEvaluator(False), lambda l: None)
+        random.seed(cfg["seed"])
+        np.random.seed(cfg["seed"])
+        s1.search(state_path=path)
+        # run 2: a fresh process constructs the searcher again and resumes
+        ev2 = StubEvaluator(False)
+        lines = []
+        s2 = build(cfg, ev2, lines.append)
+        random.seed(12345)  # whatever the new process seeded: load_state restores both generators
+        s2.load_state(path)
+        assert s2.epoch == stop_after - 1 and len(s2.vis_dict) == len(s1.vis_dict)
+        top = s2.search(state_path=path)
+        assert list(s2.vis_dict.keys()) == g["visited"] and top == g["top"]
+        assert s2.skip_layer_range == g["skip_layer_range"] and s2.epoch == g["epoch"]
+        assert len(set(top)) == len(top) and len(set(s2.keep_top_k[s2.select_num])) == len(s2.keep_top_k[s2.select_num])
+        assert not set(ev2.calls) & set(s1.vis_dict.keys())
+        assert not any(l.startswith("epoch = {}".format(stop_after - 1)) for l in lines)  # that epoch was already logged

@@ -176,8 +176,8 @@ def test_schedule_plan_matches_generic_loop_and_evaluator_fid():
     rng = np.random.RandomState(0)
     ref_f = rng.randn(200, 64) * 2 + 5
     ref_stats = FIDStatistics(*fid_ref.compute_statistics(ref_f))
-    ev = CandidateEvaluator(model, base, feature_fn, ref_stats, batch_size=4, num_samples=10, image_size=64, seed=3,
-                            fid_method="sqrtm")  # the reference's arithmetic, compared to 1e-6 below
+    ev = CandidateEvaluator(model, base, feature_fn, ref_stats, batch_size=4, num_samples=10, image_size=64, seed=3)
+    assert ev.fid_method == "sqrtm"  # the default is the reference's arithmetic, compared to 1e-6 below
     fid = ev.get_cand_fid(cand)
     allf = torch.cat(feats_seen).double().numpy()
     assert allf.shape == (10, 64)
@@ -186,8 +186,8 @@ def test_schedule_plan_matches_generic_loop_and_evaluator_fid():
     assert abs(fid - want) <= 1e-6 * max(1.0, abs(want))
     # the default symmetric-eigenproblem form on the same (rank-deficient: 10 samples, 64 dims) statistics: the
     # north star's FID tolerance is +-0.1
-    ev_e = CandidateEvaluator(model, base, feature_fn, ref_stats, batch_size=4, num_samples=10, image_size=64, seed=3)
-    assert ev_e.fid_method == "eigh"
+    ev_e = CandidateEvaluator(model, base, feature_fn, ref_stats, batch_size=4, num_samples=10, image_size=64, seed=3,
+                              fid_method="eigh")
     fid_e = ev_e.get_cand_fid(cand)
     print(f"eigh form: {fid_e:.6f}")
     assert abs(fid_e - want) <= 0.1

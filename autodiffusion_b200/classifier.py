@@ -106,6 +106,68 @@ class _GuidancePlan:
             self.plan.run()
 
 
+class _AutogradPlan:
+    """Forward and input-gradient pass of the classifier as two recorded plans over one private set of activations:
+    what `EncoderUNetModel.forward` runs when torch autograd is watching its input."""
+
+    def __init__(self, model: "EncoderUNetModel", B: int, H: int, W: int):
+        dev = model._device()
+        self.x_in = th.zeros((B, model.in_channels, H, W), dtype=th.float32, device=dev)
+        self.t_in = th.zeros((B,), dtype=th.int64, device=dev)
+        self.grad = th.zeros_like(self.x_in)
+        self.dlogits = th.zeros((B, model.out_channels), dtype=th.float32, device=dev)
+        self.fwd, self.bwd = ops.Plan(), ops.Plan()
+        self.pool = _Pool(dev)
+        self.logits = model.record_guidance(self.fwd, self.x_in, self.t_in, None, self.grad, None, dlogits_in=self.dlogits,
+                                            plan_bwd=self.bwd, pool=self.pool)
+        self.launches_fwd = self.fwd.run()  # validation run (sets kernel attributes)
+        self.launches_bwd = self.bwd.run()
+        self.generation = 0  # bumped by every forward: a backward of an older forward would read overwritten activations
+        self.g_fwd = self.g_bwd = None
+        if os.environ.get("ADB_NO_GRAPH", "0") != "1":
+            th.cuda.current_stream().synchronize()
+            self.g_fwd, self.g_bwd = th.cuda.CUDAGraph(), th.cuda.CUDAGraph()
+            with th.cuda.graph(self.g_fwd):
+                self.fwd.run()
+            with th.cuda.graph(self.g_bwd):
+                self.bwd.run()
+
+    def run_fwd(self):
+        self.g_fwd.replay() if self.g_fwd is not None else self.fwd.run()
+
+    def run_bwd(self):
+        self.g_bwd.replay() if self.g_bwd is not None else self.bwd.run()
+
+
+class _ClassifierFunction(th.autograd.Function):
+    """logits = classifier(x, t) for torch autograd: backward returns the vector-Jacobian product with respect to x from
+    the recorded input-gradient plan (the reference's cond_fn, …progressive.py:383-390, runs `th.autograd.grad(
+    selected.sum(), x_in)` through `self.classifier`). Parameters receive no gradient: the evaluator never trains."""
+
+    @staticmethod
+    def forward(ctx, x, timesteps, model):
+        B, _, H, W = x.shape
+        ap = model._autograd_plan(B, H, W)
+        ap.x_in.copy_(x)
+        ap.t_in.copy_(timesteps)
+        ap.run_fwd()
+        ap.generation += 1
+        ctx.ap, ctx.generation, ctx.model = ap, ap.generation, model
+        model.gpu_launches += ap.launches_fwd
+        return ap.logits.clone()
+
+    @staticmethod
+    def backward(ctx, dlogits):
+        ap = ctx.ap
+        if ap.generation != ctx.generation:
+            raise RuntimeError("EncoderUNetModel: backward through a forward whose saved activations were overwritten by "
+                               "a later forward of the same batch shape (call backward before the next forward)")
+        ap.dlogits.copy_(dlogits)
+        ap.run_bwd()
+        ctx.model.gpu_launches += ap.launches_bwd
+        return ap.grad.clone(), None, None
+
+
 class EncoderUNetModel(nn.Module):
     """unet.py:685-896. Same constructor arguments and state_dict keys; `forward(x, timesteps)` returns the
     [N, out_channels] logits, `input_gradient(x, timesteps, y, scale)` the guidance gradient."""
@@ -291,23 +353,32 @@ class EncoderUNetModel(nn.Module):
 
     # ---- recording ----
     def record_guidance(self, plan: ops.Plan, x_in: th.Tensor, t_in: th.Tensor, y_in: Optional[th.Tensor],
-                        grad_out: Optional[th.Tensor], scale: Optional[float]) -> th.Tensor:
+                        grad_out: Optional[th.Tensor], scale: Optional[float], dlogits_in: Optional[th.Tensor] = None,
+                        plan_bwd: Optional[ops.Plan] = None, pool: Optional[_Pool] = None) -> th.Tensor:
         """Record logits = classifier(x_in, t_in) and, when `grad_out` is given,
         grad_out = d(log_softmax(logits)[range(B), y_in].sum() * scale) / d x_in into `plan`.
-        x_in fp32 NCHW, t_in / y_in int64 [B], grad_out fp32 NCHW. Returns the (static) logits tensor."""
+        x_in fp32 NCHW, t_in / y_in int64 [B], grad_out fp32 NCHW. Returns the (static) logits tensor.
+
+        `dlogits_in` (fp32 [B, out_channels]): instead of the log-softmax selection, back-propagate this caller-filled
+        d(loss)/d(logits) - the vector-Jacobian product torch autograd asks for (`forward` under `requires_grad`).
+        `plan_bwd`: record the input-gradient pass into a second plan (it then runs when autograd calls backward);
+        `pool`: a private activation pool, so that nothing recorded elsewhere can reuse the saved activations between the
+        two runs."""
         if self._device().type != "cuda":
             raise RuntimeError("EncoderUNetModel runs on a CUDA device only (autodiffusion_b200 has no CPU path)")
         if self._packed_generation != self._generation:
             self._pack()
         want_grad = grad_out is not None
         if want_grad:
-            assert y_in is not None and scale is not None
+            assert dlogits_in is not None or (y_in is not None and scale is not None)
         B, _, H, W = x_in.shape
         dev = self._device()
         P = self._packed
-        if self._pool is None or self._pool.device != dev:
-            self._pool = _Pool(dev)
-        ctx = _Ctx(self._pool, plan)
+        if pool is None:
+            if self._pool is None or self._pool.device != dev:
+                self._pool = _Pool(dev)
+            pool = self._pool
+        ctx = _Ctx(pool, plan)
         mc = self.model_channels
         plan.keep(x_in, t_in, y_in, grad_out)
 
@@ -474,7 +545,11 @@ class EncoderUNetModel(nn.Module):
             return logits
 
         # ---------------- backward (data gradients only) ----------------
-        dlog = ops.logsoftmax_grad(logits, y_in, scale, plan=plan)
+        if plan_bwd is not None:  # the closures above read `plan` when they are called: from here on, the second plan
+            plan = plan_bwd
+            ctx.plan = plan_bwd
+            plan.keep(x_in, t_in, grad_out, arena, bscratch, dlogits_in)
+        dlog = dlogits_in if dlogits_in is not None else ops.logsoftmax_grad(logits, y_in, scale, plan=plan)
         dout0 = ops.linear_tc(dlog, P["pool_wc_t"], None, C, plan=plan)
         dqkv0, dkv = ops.pool_attention_backward(dout0, probs, qkv0, kv, plan=plan)
         dmean = ops.linear_tc(dqkv0, P["pool_wqkv_t"], None, C, plan=plan)
@@ -506,12 +581,33 @@ class EncoderUNetModel(nn.Module):
             self._plans[key] = gp
         return gp
 
+    def _autograd_plan(self, B: int, H: int, W: int) -> _AutogradPlan:
+        if self._packed_generation != self._generation:
+            self._pack()
+        key = (B, H, W, "autograd")
+        ap = self._plans.get(key)
+        if ap is None:
+            with th.no_grad():
+                ap = _AutogradPlan(self, B, H, W)
+            self._plans[key] = ap
+        return ap
+
     def forward(self, x, timesteps):
-        """unet.py:861-896: [N, C, H, W] fp32, timesteps [N] -> logits [N, out_channels]."""
+        """unet.py:861-896: [N, C, H, W] fp32, timesteps [N] -> logits [N, out_channels]. When autograd is recording and
+        `x` requires grad, the result carries a graph whose backward is the recorded input-gradient pass."""
         if not x.is_cuda:
             raise RuntimeError("EncoderUNetModel.forward: input must be a CUDA tensor (no CPU path)")
         B, _, H, W = x.shape
         assert timesteps.shape == (B,)
+        tr = self.__dict__.get("_trace")
+        if tr is not None:  # fastpath.py: record the call, run nothing, return logits that report what flows back
+            from .fastpath import _TracedLogits
+
+            rec = {}
+            tr.append((x, timesteps, rec))
+            return _TracedLogits.apply(x, self.out_channels, rec)
+        if th.is_grad_enabled() and x.requires_grad:
+            return _ClassifierFunction.apply(x.float().contiguous(), timesteps, self)
         gp = self._plan_for(B, H, W, None)
         gp.x_in.copy_(x)
         gp.t_in.copy_(timesteps)

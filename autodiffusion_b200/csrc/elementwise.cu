@@ -475,7 +475,8 @@ int ddim_step_submit(adb_plan* plan, const float* x, const float* model_out, int
 int pack_uint8_submit(adb_plan* plan, const float* sample, uint8_t* out, int n, int c, int hw,
                       cudaStream_t stream) {
   ADB_REQUIRE(sample && out && n > 0 && c > 0 && hw > 0, "pack_uint8: bad arguments");
-  return submit(plan, stream, "pack_uint8", 0.0, 0.0, [=](cudaStream_t s) -> int {
+  // compulsory traffic: the fp32 sample read once, one byte per element written
+  return submit(plan, stream, "pack_uint8", 0.0, 5.0 * (double)n * c * hw, [=](cudaStream_t s) -> int {
     const size_t total = (size_t)n * hw;
     size_t blocks = (total + 255) / 256;
     const size_t cap = (size_t)num_sms() * 8;

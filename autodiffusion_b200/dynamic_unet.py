@@ -834,6 +834,10 @@ class Dynamic_UNetModel(nn.Module):
         assert timesteps.shape == (B,)
         if y is not None:
             assert y.shape == (B,)
+        tr = self.__dict__.get("_trace")
+        if tr is not None:  # fastpath.py: record the call, run nothing, hand back the sentinel
+            tr.append((x, timesteps, y, list(skip_layer)))
+            return self.io_buffers(B, H, W).out
         up = self.get_plan(B, H, W, skip_layer)
         up.x_in.copy_(x)
         up.t_in.copy_(timesteps)  # integer timesteps (rescale_timesteps=False in every reference config)

@@ -43,7 +43,7 @@ from .classifier import ClassifierGuidance, EncoderUNetModel
 from .evaluator import CandidateEvaluator, FIDStatistics
 from .respace import space_timesteps
 
-__all__ = ["EvolutionSearcher"]
+__all__ = ["EvolutionSearcher", "sample_active_subnet", "draw_population"]
 
 _MAX_REJECTIONS = int(1e6)
 
@@ -52,6 +52,59 @@ def _choice(seq):
     """The reference's module-level `choice` (:46-47): numpy's global RNG, not `random.choice`."""
     seq = tuple(seq)
     return seq[np.random.randint(len(seq))]
+
+
+def sample_active_subnet(n_steps: int, L: int, max_index_number: int, skip_layer_range):
+    """A random individual under the (step, block) index budget (…progressive.py:284-338): timesteps from a shuffled
+    order of the `n_steps` base steps; per step a skip list of int(u * L) randomly chosen block ids, u uniform in
+    `skip_layer_range`; steps are added while the budget `max_index_number` of executed (step, block) slots allows.
+    Draws from the global `random` / `numpy.random` generators in the reference's order."""
+    order = list(range(n_steps))
+    random.shuffle(order)
+    lo, hi = skip_layer_range
+    used, t_idx = 0, 0
+    skip_lists, timesteps = [], []
+    for _ in range(100000):
+        n_skip = -10000
+        tries = 0
+        while used + L - n_skip > max_index_number:
+            tries += 1
+            n_skip = int((np.random.random_sample() * (hi - lo) + lo) * L)
+            if tries > _MAX_REJECTIONS:
+                raise RuntimeError("sample_active_subnet: no skip count fits the remaining index budget "
+                                   f"(used {used} of {max_index_number}, range {list(skip_layer_range)})")
+        layers = list(range(L))
+        random.shuffle(layers)
+        skip_lists.append(layers[:n_skip])
+        timesteps.append(order[t_idx])
+        t_idx += 1
+        used += L - n_skip
+        room = used + L - int(L * hi)
+        if room > max_index_number:
+            break
+        if room == max_index_number:
+            layers = list(range(L))
+            random.shuffle(layers)
+            skip_lists.append(layers[:int(L * hi)])
+            timesteps.append(order[t_idx])
+            break
+    else:
+        raise RuntimeError("sample_active_subnet did not terminate")
+    return {"timesteps": timesteps, "skip_layers": skip_lists}
+
+
+def draw_population(n: int, time_step: int, layer_num: int, max_prun: float, seed: int = 0, n_steps: int = 1000):
+    """`n` random individuals as the search draws its population once the prune range is fully open
+    (`skip_layer_range = [0, max_prun]`, budget `time_step * layer_num`): BASELINE configs[2]'s workload. The global
+    generators are seeded for the draw and restored afterwards."""
+    st_py, st_np = random.getstate(), np.random.get_state()
+    random.seed(seed)
+    np.random.seed(seed)
+    try:
+        return [sample_active_subnet(n_steps, layer_num, time_step * layer_num, [0, max_prun]) for _ in range(n)]
+    finally:
+        random.setstate(st_py)
+        np.random.set_state(st_np)
 
 
 class EvolutionSearcher:
@@ -176,40 +229,8 @@ class EvolutionSearcher:
     # ---- individuals ----
     def sample_active_subnet(self):
         """A random individual under the (step, block) index budget `max_index_number` (:284-338)."""
-        n_steps = self.base_diffusion.original_num_steps
-        order = list(range(n_steps))
-        random.shuffle(order)
-        L = self.model_layers
-        lo, hi = self.skip_layer_range
-        used, t_idx = 0, 0
-        skip_lists, timesteps = [], []
-        for _ in range(100000):
-            n_skip = -10000
-            tries = 0
-            while used + L - n_skip > self.max_index_number:
-                tries += 1
-                n_skip = int((np.random.random_sample() * (hi - lo) + lo) * L)
-                if tries > _MAX_REJECTIONS:
-                    raise RuntimeError("sample_active_subnet: no skip count fits the remaining index budget "
-                                       f"(used {used} of {self.max_index_number}, range {self.skip_layer_range})")
-            layers = list(range(L))
-            random.shuffle(layers)
-            skip_lists.append(layers[:n_skip])
-            timesteps.append(order[t_idx])
-            t_idx += 1
-            used += L - n_skip
-            room = used + L - int(L * hi)
-            if room > self.max_index_number:
-                break
-            if room == self.max_index_number:
-                layers = list(range(L))
-                random.shuffle(layers)
-                skip_lists.append(layers[:int(L * hi)])
-                timesteps.append(order[t_idx])
-                break
-        else:
-            raise RuntimeError("sample_active_subnet did not terminate")
-        return {"timesteps": timesteps, "skip_layers": skip_lists}
+        return sample_active_subnet(self.base_diffusion.original_num_steps, self.model_layers, self.max_index_number,
+                                    self.skip_layer_range)
 
     def _fill(self, num, tag):
         self.log("random select ........")

@@ -12,6 +12,12 @@ GD/search_dynamic_unet_imagenet64_classifier_guidance_progressive.py (:720-830):
         --model_path 64x64_diffusion.pt --classifier_path 64x64_classifier.pt --ref_path ref_stats.npz \
         --time_step 10 --max_prun 0.1 --num_samples 1000 --batch_size 250 --save_dir out/
 
+`--mode timesteps` runs the timestep-only drivers instead (full architecture, individuals = timestep lists):
+GD/search_imagenet64_classifier_guidance.py (classifier-guided; `--search_space "[926, 153, ...]"` builds the +-N/100
+window around those steps as its `__main__` does, :645-668) or, with `--mode timesteps_uncond`,
+GD/search_uncondition_model.py (no classifier, `--init_x "[644, 737, ...]"`), e.g. the LSUN-bedroom search
+(GD/search_lsun_bedroom.sh).
+
 Differences, all deliberate: one process per GPU (the reference forces world size 1, :757-760) with a
 candidate's batches sharded over ranks; FID statistics from `--ref_path` as an .npz with `mu`, `sigma`
 (the reference unpickles an object, :201-203); the Inception extractor is supplied by
@@ -44,7 +50,8 @@ def create_argparser():
                     time_step=100, seed=0, max_epochs=20, select_num=10, population_num=50, m_prob=0.1, crossover_num=25,
                     mutation_num=35, classifier_path="", classifier_scale=1.0, max_fid=48.0, use_ddim_init_x=False,
                     index_step=None, max_prun=0.0, min_prun=0.0, ref_path="", feature_module="", feature_dim=2048,
-                    state_path="", randomize_zero_init=False)
+                    state_path="", randomize_zero_init=False, mode="time_arch", search_space="", init_x="",
+                    fid_method="sqrtm")
     defaults.update(model_and_diffusion_defaults())
     defaults.update(classifier_defaults())
     parser = argparse.ArgumentParser()
@@ -95,12 +102,14 @@ def main():
     model.to(dev).eval()
     if args.use_fp16:
         model.convert_to_fp16()
-    classifier = create_classifier(**args_to_dict(args, classifier_defaults().keys()))
-    if args.classifier_path:
-        classifier.load_state_dict(th.load(args.classifier_path, map_location="cpu"))
-    elif args.randomize_zero_init:
-        _randomize(classifier, 2)
-    classifier.to(dev).eval()
+    classifier = None
+    if args.mode != "timesteps_uncond":
+        classifier = create_classifier(**args_to_dict(args, classifier_defaults().keys()))
+        if args.classifier_path:
+            classifier.load_state_dict(th.load(args.classifier_path, map_location="cpu"))
+        elif args.randomize_zero_init:
+            _randomize(classifier, 2)
+        classifier.to(dev).eval()
 
     if args.feature_module:
         mod, fn = args.feature_module.split(":")
@@ -120,9 +129,30 @@ def main():
         ref_stats = FIDStatistics(0.05 * rs.randn(d), a @ a.T * 0.05 + 0.02 * np.eye(d))
 
     t0 = time.time()
-    searcher = EvolutionSearcher(args, model=model, base_diffusion=diffusion, time_step=args.time_step,
-                                 classifier=classifier, index_step=args.index_step, feature_fn=feature_fn,
-                                 ref_stats=ref_stats, log=log)
+    from autodiffusion_b200.classifier import ClassifierGuidance
+    from autodiffusion_b200.evaluator import CandidateEvaluator
+
+    evaluator = CandidateEvaluator(
+        model, diffusion, feature_fn, ref_stats, batch_size=args.batch_size, num_samples=args.num_samples,
+        image_size=args.image_size, class_cond=args.class_cond, clip_denoised=args.clip_denoised, seed=args.seed,
+        cond_fn=None if classifier is None else ClassifierGuidance(classifier, args.classifier_scale),
+        fid_method=args.fid_method)  # "sqrtm" = the reference's arithmetic; "eigh" = the cheaper symmetric form
+    if args.mode == "time_arch":
+        searcher = EvolutionSearcher(args, model=model, base_diffusion=diffusion, time_step=args.time_step,
+                                     classifier=classifier, index_step=args.index_step, evaluator=evaluator, log=log)
+    else:
+        from autodiffusion_b200.respace import space_timesteps
+        from autodiffusion_b200.timestep_search import TimestepSearcher, build_search_space
+
+        space = None
+        if args.search_space:
+            init = list(space_timesteps(diffusion.original_num_steps, ("ddim" if args.use_ddim else "") + str(args.time_step))) \
+                if args.use_ddim_init_x else None
+            space = build_search_space(eval(args.search_space), diffusion.original_num_steps, init)
+            log("search space: " + str(space))
+        searcher = TimestepSearcher(args, model=model, base_diffusion=diffusion, time_step=args.time_step, classifier=classifier,
+                                    search_space=space, variant="uncondition" if args.mode == "timesteps_uncond" else "imagenet64",
+                                    evaluator=evaluator, log=log)
     if args.state_path and os.path.exists(args.state_path):
         searcher.load_state(args.state_path)
         log("resumed from {} at epoch {} ({} individuals visited)".format(args.state_path, searcher.epoch, len(searcher.vis_dict)))

@@ -5,9 +5,10 @@ Reference for logits and gradients: the CPU oracle's `encoder_forward` / `classi
 tests/golden/make_golden.py) under torch autograd in fp32. Reference for guided sampling: the
 reference's own runs (tests/golden/ddim_small.npz, config1_admg64_guided.npz).
 
-Tolerances (bf16 activations and gradients, bf16 tensor-core operands, vs fp32 autograd): logits
-relative RMS <= 2 %; guidance gradient relative RMS <= 5 % and cosine similarity >= 0.995 per
-image; guided final samples PSNR >= 30 dB.
+Tolerances (bf16 activations and gradients, bf16 tensor-core operands, vs fp32 autograd) = measured on B200 minus a
+margin: logits relative RMS <= 1 % (measured 0.57-0.67 %); guidance gradient relative RMS <= 2.8 % (1.85-1.92 %) and
+cosine similarity >= 0.9993 per image (0.9998); guided final samples PSNR >= 42 / 40 dB on the small pair (45.0 / 43.0),
+>= 44 dB for config 1 (47.1), >= 41 dB for the benchmarked 10-step candidate.
 """
 import copy
 
@@ -16,7 +17,7 @@ import pytest
 import torch
 
 from oracle import unet_ref, weights
-from tests.util import ADM_FLAGS, SMALL_FLAGS, build_ours, golden, oracle_weights, parse_skip_list, psnr
+from tests.util import ADM_FLAGS, SMALL_FLAGS, build_ours, golden, no_fast_path, oracle_weights, parse_skip_list, psnr
 
 pytestmark = pytest.mark.gpu
 
@@ -47,7 +48,7 @@ def test_classifier_logits_and_input_gradient_match_autograd(depth, width, B):
     rel = ((logits - ref_logits).pow(2).mean().sqrt() / ref_logits.pow(2).mean().sqrt()).item()
     print(f"classifier d{depth} w{width}: logits rel_rms={rel:.4g} max_abs={(logits - ref_logits).abs().max().item():.4g} "
           f"ref_std={ref_logits.std().item():.4g}; launches/forward={clf.gpu_launches}")
-    assert rel <= 0.02
+    assert rel <= 0.01
     for scale in (1.0, 2.5):
         ref_grad = unet_ref.classifier_cond_fn(csd, ccfg, scale)(x, t, y=y)
         grad = clf.input_gradient(x.cuda(), t.cuda(), y.cuda(), scale).cpu()
@@ -55,7 +56,7 @@ def test_classifier_logits_and_input_gradient_match_autograd(depth, width, B):
         rel = ((grad - ref_grad).pow(2).mean().sqrt() / ref_grad.pow(2).mean().sqrt()).item()
         cos = torch.nn.functional.cosine_similarity(grad.flatten(1), ref_grad.flatten(1), dim=1)
         print(f"  scale {scale}: grad rel_rms={rel:.4g} cos(min)={cos.min().item():.5f} |ref|max={ref_grad.abs().max().item():.4g}")
-        assert rel <= 0.05 and cos.min().item() >= 0.995
+        assert rel <= 0.028 and cos.min().item() >= 0.9993
     # the callable form the search scripts pass as cond_fn
     from autodiffusion_b200.classifier import ClassifierGuidance
 
@@ -90,9 +91,10 @@ def test_guided_sampling_with_native_classifier_matches_reference(name):
 
     noise, y = torch.from_numpy(g["noise"]).cuda(), torch.from_numpy(g["y"]).cuda()
     ref = torch.from_numpy(g[f"{name}/final"])
-    out = active.ddim_sample_loop(model_fn, tuple(noise.shape), noise=noise, clip_denoised=True,
-                                  model_kwargs={"y": y, "skip_layers": skips}, cond_fn=cond_fn,
-                                  device=torch.device("cuda")).cpu()
+    with no_fast_path():
+        out = active.ddim_sample_loop(model_fn, tuple(noise.shape), noise=noise, clip_denoised=True,
+                                      model_kwargs={"y": y, "skip_layers": skips}, cond_fn=cond_fn,
+                                      device=torch.device("cuda")).cpu()
     p1 = psnr(out, ref)
     act2, per_step = resolve_candidate({"timesteps": ts, "skip_layers": skips}, base)
     plan = SchedulePlan(model, act2, per_step, noise.shape[0], cond_fn=cond_fn, pack_uint8=True)
@@ -102,7 +104,9 @@ def test_guided_sampling_with_native_classifier_matches_reference(name):
     d8 = np.abs(plan.u8.cpu().numpy().astype(np.int32) - g[f"{name}/uint8"].astype(np.int32))
     print(f"guided sampling ({name}) native classifier: generic loop psnr={p1:.2f} dB, one-graph plan psnr={p2:.2f} dB, "
           f"uint8 max diff {d8.max()} LSB (mean {d8.mean():.3f}); kernels per candidate: {plan.launches}")
-    assert p1 >= 30.0 and p2 >= 30.0
+    bar = {"guided": 42.0, "dedup": 40.0}[name]  # measured 45.0 / 43.0 dB
+    assert p1 >= bar and p2 >= bar
+    assert d8.mean() <= 0.65  # measured 0.41 / 0.48 LSB
     assert (out - out2).abs().max().item() <= 1e-4  # same kernels, same order
 
 
@@ -126,4 +130,5 @@ def test_config1_full_admg64_with_native_classifier():
     d8 = np.abs(plan.u8.cpu().numpy().astype(np.int32) - g["uint8"].astype(np.int32))
     print(f"config1 native classifier guidance: max_abs={(out - ref).abs().max().item():.4g} psnr={p:.2f} dB; uint8 max diff "
           f"{d8.max()} LSB, within 1 LSB: {(d8 <= 1).mean() * 100:.1f}%; kernels per candidate: {plan.launches}")
-    assert p >= 30.0
+    assert p >= 44.0  # measured 47.1 dB
+    assert d8.mean() <= 0.45 and (d8 <= 1).mean() >= 0.90  # measured 93.7 % within 1 LSB

@@ -1,8 +1,9 @@
 """GPU parity of the Stable-Diffusion-v1 family (BASELINE configs[4]) against fixtures recorded from the unmodified
 reference (tests/golden/sd_small.npz, sd_full.npz; generator: tests/golden/make_sd_golden.py) and against the CPU
-oracle on fresh inputs. Bars (bf16 tensor-core torso vs the reference's fp32): whole-UNet relative RMS <= 2 %,
-max-abs <= 12 % of the output std; final latents of the CFG-7.5 searched DDIM loop PSNR >= 30 dB (peak = the
-reference latents' range); schedule tables and the update step bit-exact (tests/test_sd_ops_gpu.py)."""
+oracle on fresh inputs. Bars = what was measured on B200 minus a 3 dB / 30 % margin (bf16 tensor-core torso vs the
+reference's fp32): whole-UNet relative RMS <= 1.8 % (measured 1.3-1.5 %), max-abs <= 9 % of the output std (5.9-7.1 %);
+final latents of the CFG-7.5 searched samplers PSNR >= 45 dB (measured 48.0-48.9 dB; peak = the reference latents'
+range), >= 59 dB without guidance (62-66 dB); schedule tables and the update step bit-exact (tests/test_sd_ops_gpu.py)."""
 import numpy as np
 import pytest
 import torch
@@ -40,7 +41,7 @@ def test_sd_small_forward_matches_reference():
     m, _ = _build(SMALL)
     out = m(torch.tensor(g["x"]).to(DEV), torch.tensor(g["t"]).to(DEV), context=torch.tensor(g["ctx"]).to(DEV)).cpu()
     rel, mx = _report(out, torch.tensor(g["out"]), "SD small UNet forward vs reference")
-    assert rel <= 0.02 and mx <= 0.12
+    assert rel <= 0.018 and mx <= 0.09  # measured: rel_rms 1.3-1.5 %, max_abs 5.9-7.1 % of the output std
     assert m.gpu_launches > 0
 
 
@@ -62,7 +63,7 @@ def test_sd_small_cfg_ddim_matches_reference():
     mse = ((out.double() - ref.double()) ** 2).mean().item()
     psnr = 10 * np.log10(peak * peak / mse)
     print(f"SD small 4-step CFG-7.5 DDIM vs reference: PSNR {psnr:.2f} dB (peak {peak:.3g}), max_abs {(out - ref).abs().max().item():.4g}")
-    assert psnr >= 30.0
+    assert psnr >= 45.0  # measured 48.4 dB
     assert [int(t) for t in sampler.ddim_timesteps] == sorted(cand.tolist())  # searched steps: exact
 
 
@@ -83,7 +84,7 @@ def test_sd_small_cfg_plms_matches_reference():
     peak = (ref.max() - ref.min()).item()
     psnr = 10 * np.log10(peak * peak / ((out.double() - ref.double()) ** 2).mean().item())
     print(f"SD small 6-step CFG-7.5 PLMS vs reference: PSNR {psnr:.2f} dB (peak {peak:.3g})")
-    assert psnr >= 30.0
+    assert psnr >= 45.0  # measured 48.4 dB
 
     class Foreign:
         num_timesteps, betas, alphas_cumprod, alphas_cumprod_prev, device = (ld.num_timesteps, ld.betas, ld.alphas_cumprod,
@@ -122,7 +123,7 @@ def test_sd_small_cfg_dpm_solver_matches_reference():
     peak = (ref.max() - ref.min()).item()
     psnr = 10 * np.log10(peak * peak / ((out.double() - ref.double()) ** 2).mean().item())
     print(f"SD small 6-evaluation CFG-7.5 DPM-Solver++(2M) vs reference: PSNR {psnr:.2f} dB (peak {peak:.3g})")
-    assert psnr >= 30.0
+    assert psnr >= 45.0  # measured 48.0 dB
 
     class Foreign:
         num_timesteps, betas, alphas_cumprod, alphas_cumprod_prev, device = (ld.num_timesteps, ld.betas, ld.alphas_cumprod,
@@ -165,7 +166,7 @@ def test_sd_no_guidance_odd_batch_and_shared_forward():
     peak = (ref.max() - ref.min()).item()
     psnr = 10 * np.log10(peak * peak / ((a1.double() - ref.double()) ** 2).mean().item())
     print(f"SD small 3-step DDIM without guidance, batch 3, 5 context tokens vs oracle: PSNR {psnr:.2f} dB")
-    assert psnr >= 30.0
+    assert psnr >= 60.0  # measured 63.8 dB
 
 
 def test_sd_generic_apply_model_loop_matches_plan():
@@ -198,7 +199,7 @@ def test_sd_full_forward_matches_reference():
     m, _ = _build(R.sd_v1_config())
     out = m(torch.tensor(g["x"]).to(DEV), torch.tensor(g["t"]).to(DEV), context=torch.tensor(g["ctx"]).to(DEV)).cpu()
     rel, mx = _report(out, torch.tensor(g["out"]), "SD-v1 UNet (859.5M) forward vs reference")
-    assert rel <= 0.02 and mx <= 0.12
+    assert rel <= 0.018 and mx <= 0.09  # measured: rel_rms 1.3-1.5 %, max_abs 5.9-7.1 % of the output std
 
 
 def test_sd_full_forward_batch_vs_oracle():
@@ -212,7 +213,7 @@ def test_sd_full_forward_batch_vs_oracle():
     ref = R.unet_forward(sd, cfg, x, t, c)
     out = m(x.to(DEV), t.to(DEV), context=c.to(DEV)).cpu()
     rel, mx = _report(out, ref, "SD-v1 UNet forward batch 3 vs oracle")
-    assert rel <= 0.02 and mx <= 0.12
+    assert rel <= 0.018 and mx <= 0.09  # measured: rel_rms 1.3-1.5 %, max_abs 5.9-7.1 % of the output std
 
 
 @pytest.mark.parametrize("sampler,cand,scale", [
@@ -252,7 +253,8 @@ def test_sd_sampler_edge_cases_vs_oracle(sampler, cand, scale):
     peak = (ref.max() - ref.min()).item()
     psnr = 10 * np.log10(peak * peak / max(((out.double() - ref.double()) ** 2).mean().item(), 1e-30))
     print(f"{sampler} cand={cand if len(cand) < 6 else str(cand[:3]) + '...'} scale={scale}: PSNR {psnr:.2f} dB")
-    assert torch.isfinite(out).all() and psnr >= 30.0
+    # measured: 47.6-49.2 dB with CFG 7.5 (the guidance scale multiplies the eps error), 62-66 dB at scale 1.0
+    assert torch.isfinite(out).all() and psnr >= (44.5 if scale > 1.0 else 59.0)
 
 
 def test_sd_candidate_evaluator_fid_matches_numpy_on_the_same_latents():

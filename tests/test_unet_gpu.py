@@ -2,10 +2,16 @@
 drop-in API (create_model_and_diffusion -> model(x, t, y, skip_layer) / diffusion.ddim_sample_loop),
 against the reference's own outputs (golden fixtures) and the CPU oracle.
 
-Tolerance (stated, bf16 tensor-core operands + bf16 activations vs the fp32 reference, random-init
-weights, 58 blocks deep): relative RMS error <= 2% and max-abs error <= 12% of the output's std for
-one forward; PSNR >= 30 dB (peak-to-peak 2.0) on final samples. Index gathers / skip decisions exact.
+Tolerances (bf16 tensor-core operands + bf16 activations vs the fp32 reference, random-init weights, 58 blocks
+deep) are the values measured on B200 minus a margin of 3 dB / 30 %, so a regression of a few dB fails:
+one forward - relative RMS error <= 1.5 % (measured 0.8-1.2 %), max-abs error <= 8 % of the output's std (3.8-6.3 %);
+final samples - PSNR (peak-to-peak 2.0) >= 42 dB for 4-step schedules (measured 45.0 / 47.1), >= 40 dB with a repeated
+timestep (43.0), >= 35 dB for the 2-step schedule whose first step sits at t = 971 (38.0; see
+test_sample_error_is_the_eps_error_amplified for why that one is inherently lower); uint8 images: mean |diff| <= 0.65 LSB.
+Index gathers / skip decisions exact.
 """
+PSNR_BAR = {"guided": 42.0, "dedup": 40.0, "noguide": 35.0}
+FWD_RMS, FWD_MAX = 0.015, 0.08
 import copy
 
 import numpy as np
@@ -13,7 +19,7 @@ import pytest
 import torch
 
 from oracle import diffusion_ref, unet_ref, weights
-from tests.util import ADM_FLAGS, SMALL_FLAGS, build_ours, cfg_of, golden, oracle_weights, parse_skip_list, psnr
+from tests.util import ADM_FLAGS, SMALL_FLAGS, build_ours, cfg_of, golden, no_fast_path, oracle_weights, parse_skip_list, psnr
 
 pytestmark = pytest.mark.gpu
 
@@ -41,7 +47,7 @@ def test_unet_forward_matches_reference_outputs(tag, flags):
         torch.cuda.synchronize()
         assert out.shape == g[f"out{i}"].shape and out.dtype == torch.float32
         rel_rms, mx, std = _report(f"unet {tag} t={int(g[f't{i}'])} skip={skip}", out.cpu(), torch.from_numpy(g[f"out{i}"]))
-        assert rel_rms <= 0.02 and mx <= 0.12 * std
+        assert rel_rms <= FWD_RMS and mx <= FWD_MAX * std
     assert model.gpu_launches > 0
 
 
@@ -76,7 +82,7 @@ def test_load_state_dict_repacks_weights():
         ref = unet_ref.unet_forward(sd2, cfg, x.cpu(), t.cpu(), y.cpu(), [])
     assert not torch.equal(a, b)
     rel_rms, mx, std = _report("after load_state_dict", b.cpu(), ref)
-    assert rel_rms <= 0.02
+    assert rel_rms <= FWD_RMS
 
 
 @pytest.mark.parametrize("name", ["guided", "dedup", "noguide"])
@@ -118,12 +124,59 @@ def test_ddim_sample_loop_matches_reference(name):
     p = psnr(final, ref)
     print(f"ddim {name}: max_abs={(final - ref).abs().max().item():.4g} psnr={p:.2f}dB "
           f"step1 max_abs={(outs[1].cpu() - torch.from_numpy(g[f'{name}/step1'])).abs().max().item():.4g}")
-    assert p >= 30.0
+    assert p >= PSNR_BAR[name]
     from autodiffusion_b200 import ops
 
     u8 = ops.pack_uint8(outs[-1].contiguous()).cpu().numpy().astype(np.int32)
     diff = np.abs(u8 - g[f"{name}/uint8"].astype(np.int32))
-    print(f"uint8: max diff {diff.max()} LSB, mean {diff.mean():.3f}")
+    print(f"uint8: max diff {diff.max()} LSB, mean {diff.mean():.3f}, within 1 LSB {(diff <= 1).mean() * 100:.1f}%")
+    assert diff.mean() <= 0.65  # measured 0.40-0.49 LSB
+
+
+def test_sample_error_is_the_eps_error_amplified():
+    """Round-1 smoke printed max_abs = 0.461 at 38.3 dB: ~19x the RMS error. Located (scripts/diag_outlier.py): it is
+    the first step of that 2-step candidate, t = 971, where pred_xstart = A x_t - Bm eps has Bm = sqrt(1/abar - 1) = 22.9.
+    The UNet's eps error there is ordinary (rms ~0.0065 = 1.2 % of eps' std, max ~0.03) but reaches x_{t-1} multiplied by
+    Bm on the ~3 % of pixels whose x0 is not clipped to +-1; at t = 85 (Bm = 0.147) the same eps error is invisible.
+    Asserted here: (1) the eps error itself is at the single-forward bar at both timesteps, (2) the error one fused step
+    adds is bounded by Bm x |eps error| pixel by pixel, (3) the percentiles of the final error."""
+    from autodiffusion_b200 import ops
+    from autodiffusion_b200.gaussian_diffusion import ddim_coefficients
+    from autodiffusion_b200.sampler import sample_candidate
+
+    cfg, sd = oracle_weights(SMALL_FLAGS)
+    model, diffusion = build_ours(SMALL_FLAGS, sd)
+    cand = {"timesteps": [85, 971], "skip_layers": [[0], [3, 7]]}
+    B = 2
+    noise = torch.randn(B, 3, 64, 64, generator=torch.Generator().manual_seed(2))
+    y = torch.randint(0, 1000, (B,), generator=torch.Generator().manual_seed(3))
+    out = sample_candidate(model, diffusion, cand, (B, 3, 64, 64), noise.cuda(), y.cuda()).cpu()
+    base = diffusion_ref.base_tables("cosine", 1000)
+    tmap, nb = diffusion_ref.respace(base["alphas_cumprod"], cand["timesteps"])
+    tb = diffusion_ref.diffusion_tables(nb)
+    unet = lambda x, t, yy, skip: unet_ref.unet_forward(sd, cfg, x, t, yy, skip)
+    refs = diffusion_ref.ddim_sample_loop(diffusion_ref.make_model_fn(unet, tmap), noise.shape, tb, tmap, noise, True,
+                                          model_kwargs={"y": y, "skip_layers": cand["skip_layers"]}, return_all=True)
+    for n, i in enumerate(range(len(tmap))[::-1]):
+        bm = float(np.float32(tb["sqrt_recipm1_alphas_cumprod"][i]))
+        x_t = refs[n]  # the ORACLE's x_t: this step's contribution alone
+        tt = torch.full((B,), tmap[i], dtype=torch.long)
+        with torch.no_grad():
+            eps_ref = unet(x_t, tt, y, cand["skip_layers"][i])[:, :3]
+        mo = model(x_t.cuda(), tt.cuda(), y.cuda(), skip_layer=cand["skip_layers"][i])
+        e_eps = (mo.cpu()[:, :3] - eps_ref)
+        rel = (e_eps.pow(2).mean().sqrt() / eps_ref.pow(2).mean().sqrt()).item()
+        x_prev = ops.ddim_step(x_t.cuda().contiguous(), mo.contiguous(), None, ddim_coefficients(tb, i), True).cpu()
+        e_prev = (x_prev - refs[n + 1]).abs()
+        print(f"t={tmap[i]}: Bm={bm:.4g} eps rel_rms={rel:.4g} max|eps err|={e_eps.abs().max().item():.4g} "
+              f"max|x_prev err|={e_prev.max().item():.4g} (Bm x max eps err = {bm * e_eps.abs().max().item():.4g})")
+        assert rel <= FWD_RMS
+        # |d x_prev| <= (sqrt(abar_prev) Bm + sqrt(1 - abar_prev)) |d eps| <= (Bm + 1) |d eps|, pixel by pixel
+        assert (e_prev <= (bm + 1.0) * e_eps.abs() * 1.001 + 5e-5).all()  # + fp32 rounding of A x - Bm eps at |x0| ~ 100
+    err = (out - refs[-1]).abs().flatten()
+    p99, p999 = float(torch.quantile(err, 0.99)), float(torch.quantile(err, 0.999))
+    print(f"final: psnr={psnr(out, refs[-1]):.2f} dB p99={p99:.4g} p99.9={p999:.4g} max={err.max().item():.4g}")
+    assert psnr(out, refs[-1]) >= 35.0 and p99 <= 0.2 and p999 <= 0.45  # measured 38.3 dB, 0.135, 0.30
 
 
 def test_schedule_plan_matches_generic_loop_and_evaluator_fid():
@@ -151,8 +204,9 @@ def test_schedule_plan_matches_generic_loop_and_evaluator_fid():
         return 0.05 * torch.tanh(x) * (1.0 + y.float().view(-1, 1, 1, 1) / 1000.0) * (t.float().view(-1, 1, 1, 1) / 1000.0)
 
     for cf in (None, cond_fn):
-        ref = active.ddim_sample_loop(model_fn, (B, 3, 64, 64), noise=noise, clip_denoised=True, cond_fn=cf,
-                                      model_kwargs={"y": y, "skip_layers": cand["skip_layers"]}, device=torch.device("cuda"))
+        with no_fast_path():  # the per-step loop, closures called once per step
+            ref = active.ddim_sample_loop(model_fn, (B, 3, 64, 64), noise=noise, clip_denoised=True, cond_fn=cf,
+                                          model_kwargs={"y": y, "skip_layers": cand["skip_layers"]}, device=torch.device("cuda"))
         act2, per_step = resolve_candidate(cand, base)
         assert per_step == [[], [2, 9], [], [5, 12, 17]] and act2.timestep_map == active.timestep_map
         plan = SchedulePlan(model, act2, per_step, B, cond_fn=cf, pack_uint8=True)
@@ -227,7 +281,7 @@ def test_lsun_style_unconditional_legacy_attention():
         with torch.no_grad():
             ref = unet_ref.unet_forward(sd, cfg, x, t, None, [] if not dyn else [1, 4])
         rel_rms, mx, std = _report(f"lsun-style dyn={dyn}", out.cpu(), ref)
-        assert rel_rms <= 0.02 and mx <= 0.12 * std
+        assert rel_rms <= FWD_RMS and mx <= FWD_MAX * std
         with pytest.raises(AssertionError):
             model(x.cuda(), t.cuda(), torch.zeros(3, dtype=torch.long).cuda())  # y given to an unconditional model
     assert diffusion.num_timesteps == 1000 and abs(diffusion.betas[0] - 1e-4) < 1e-12
@@ -264,7 +318,7 @@ def test_config1_full_admg64_guided_matches_reference():
     p = psnr(final, ref)
     print(f"config1 (generic loop): max_abs={(final - ref).abs().max().item():.4g} psnr={p:.2f} dB; "
           f"step1 max_abs={(outs[1].cpu() - torch.from_numpy(g['step1'])).abs().max().item():.4g}")
-    assert p >= 30.0
+    assert p >= 44.0  # measured 47.1 dB
     act2, per_step = resolve_candidate({"timesteps": ts, "skip_layers": skips}, base)
     plan = SchedulePlan(model, act2, per_step, noise.shape[0], cond_fn=cond_fn, pack_uint8=True)
     out2 = plan.run(noise, y).clone().cpu()
@@ -272,7 +326,11 @@ def test_config1_full_admg64_guided_matches_reference():
     d8 = np.abs(plan.u8.cpu().numpy().astype(np.int32) - g["uint8"].astype(np.int32))
     print(f"config1 (SchedulePlan): psnr={p2:.2f} dB; uint8 max diff {d8.max()} LSB, mean {d8.mean():.3f}, "
           f"pixels within 1 LSB: {(d8 <= 1).mean() * 100:.1f}%")
-    assert p2 >= 30.0
+    assert p2 >= 44.0  # measured 47.1 dB
+    assert d8.mean() <= 0.45 and (d8 <= 1).mean() >= 0.90  # measured: mean 0.32 LSB, 93.7 % of pixels within 1 LSB
+    err = (out2 - ref).abs().flatten().double().numpy()
+    print(f"config1 error percentiles: p99={np.percentile(err, 99):.4g} p99.9={np.percentile(err, 99.9):.4g} max={err.max():.4g}")
+    assert np.percentile(err, 99) <= 0.05 and np.percentile(err, 99.9) <= 0.1
 
 
 def test_fid_of_a_fixed_candidate_within_tolerance_of_the_oracle():
@@ -342,7 +400,7 @@ def test_lsun256_full_size_forward_and_sampling():
     with torch.no_grad():
         ref = unet_ref.unet_forward(sd, cfg, x, t, None, [])
     rel_rms, mx, std = _report("lsun256 full size", out.cpu(), ref)
-    assert rel_rms <= 0.02 and mx <= 0.12 * std
+    assert rel_rms <= 0.011 and mx <= 0.06 * std  # measured 0.77 %, 4.1 %
     cand = {"timesteps": [644, 67], "skip_layers": [[], []]}
     ours = sample_candidate(model, diffusion, cand, (1, 3, 256, 256), x.cuda(), None).cpu()
     base = diffusion_ref.base_tables("linear", 1000)
@@ -354,4 +412,4 @@ def test_lsun256_full_size_forward_and_sampling():
                                               model_kwargs={"y": None, "skip_layers": cand["skip_layers"]})
     p = psnr(ours, ref2)
     print(f"lsun256 2-step sampling: psnr={p:.2f} dB max_abs={(ours - ref2).abs().max().item():.4g}")
-    assert p >= 30.0
+    assert p >= 42.5  # measured 45.9 dB

@@ -1,4 +1,5 @@
 """Shared helpers for the tests: fixtures, oracle weights and builders."""
+import contextlib
 import os
 
 import numpy as np
@@ -49,3 +50,17 @@ def parse_skip_list(arr):
 def psnr(a: torch.Tensor, b: torch.Tensor, peak: float = 2.0) -> float:
     mse = ((a.double() - b.double()) ** 2).mean().item()
     return float("inf") if mse == 0 else 10.0 * np.log10(peak * peak / mse)
+
+
+@contextlib.contextmanager
+def no_fast_path():
+    """Force `ddim_sample_loop` onto the generic per-step loop (fastpath.py honours ADB_NO_FAST_PATH at every call)."""
+    old = os.environ.get("ADB_NO_FAST_PATH")
+    os.environ["ADB_NO_FAST_PATH"] = "1"
+    try:
+        yield
+    finally:
+        if old is None:
+            os.environ.pop("ADB_NO_FAST_PATH", None)
+        else:
+            os.environ["ADB_NO_FAST_PATH"] = old

@@ -21,7 +21,7 @@ LIB_PATH = Path(os.environ["ADB_LIB_PATH"]) if os.environ.get("ADB_LIB_PATH") el
 HEADER = _PKG.parent / "include" / "adb200.h"
 
 SOURCES = ["host.cu", "conv_igemm.cu", "attention.cu", "attention2.cu", "groupnorm.cu", "elementwise.cu", "moments.cu",
-           "attention_bwd.cu", "backward.cu", "attention_sd.cu", "sd_ops.cu"]
+           "attention_bwd.cu", "backward.cu", "attention_sd.cu", "sd_ops.cu", "inception_ops.cu"]
 
 NVCC_FLAGS = [
     "-O3",
@@ -215,6 +215,10 @@ SYMBOLS = {
     "adb_dpm_update": (_I, [_P, _P, _P, _P, _P, C.c_size_t, _I, C.c_float, C.c_float, C.c_float, C.c_float, _P]),
     "adb_cfg_combine": (_I, [_P, _P, _P, C.c_size_t, _I, C.c_float, _P]),
     "adb_plms_update": (_I, [_P, _P, _P, _P, _P, _P, _I, C.POINTER(C.c_float), _P, _P, C.c_size_t, _P]),
+    "adb_resize_bilinear_u8": (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _P]),
+    "adb_gather_patches": (_I, [_P, C.POINTER(_P), C.POINTER(_I), C.POINTER(_I), _I, _P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P]),
+    "adb_pool3x3": (_I, [_P, C.POINTER(_P), C.POINTER(_I), C.POINTER(_I), _I, _P, _I, _I, _I, _I, _I, _I, _P]),
+    "adb_global_avgpool": (_I, [_P, C.POINTER(_P), C.POINTER(_I), C.POINTER(_I), _I, _P, _I, _I, _P]),
 }
 
 _lib = None

@@ -436,8 +436,10 @@ int gn_backward_submit(adb_plan* plan, const adb_gn_bwd_desc* d, cudaStream_t st
   p.splits = splits;
   const double elems = (double)d->n * P * d->c;
   const double dscale = d->resample == ADB_RESAMPLE_AVGPOOL2 ? 0.25 : 1.0;
-  // x twice, dout twice, add once, dx once (2 bytes each)
-  const double bytes = 2.0 * elems * (2.0 + 2.0 * dscale + (d->add_mode == ADB_RES_NONE ? 0.0 : (d->add_mode == ADB_RES_AVGPOOL2 ? 0.25 : 1.0)) + 1.0);
+  // ALGORITHMIC traffic (the roofline numerator): x, dout, add read once, dx written once, 2 bytes each. The two passes
+  // below execute 1.5x that (x and dout are read by both): a cluster-per-sample single-launch form that re-reads its slice
+  // from L2 was measured SLOWER (0.36-0.40 ms vs 0.31 ms at 256 x 64x64x128; profiles/README.md) and is not kept.
+  const double bytes = 2.0 * elems * (1.0 + dscale + (d->add_mode == ADB_RES_NONE ? 0.0 : (d->add_mode == ADB_RES_AVGPOOL2 ? 0.25 : 1.0)) + 1.0);
   return submit(plan, stream, "groupnorm_bwd", 0.0, bytes, [p](cudaStream_t s) -> int {
     dim3 grid(p.splits, p.n);
     const size_t smem = 6 * (size_t)p.C * sizeof(float);

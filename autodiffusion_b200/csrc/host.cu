@@ -131,6 +131,11 @@ int timestep_embedding_f32_submit(adb_plan*, const float*, const float*, float*,
 int dpm_x0_submit(adb_plan*, const float*, const float*, float*, size_t, int, float, float, float, cudaStream_t);
 int dpm_update_submit(adb_plan*, const float*, const float*, const float*, float*, size_t, int, float, float, float, float,
                       cudaStream_t);
+int gather_patches_submit(adb_plan*, const void* const*, const int*, const int*, int, void*, int, int, int, int, int, int, int,
+                          int, int, cudaStream_t);
+int pool3x3_submit(adb_plan*, const void* const*, const int*, const int*, int, void*, int, int, int, int, int, int, cudaStream_t);
+int global_avgpool_submit(adb_plan*, const void* const*, const int*, const int*, int, float*, int, int, cudaStream_t);
+int resize_bilinear_u8_submit(adb_plan*, const uint8_t*, void*, int, int, int, int, int, cudaStream_t);
 int plms_update_submit(adb_plan*, const float*, const float*, const float*, const float*, const float*, int, const float*,
                        float*, float*, size_t, cudaStream_t);
 
@@ -370,6 +375,27 @@ int adb_dpm_update(adb_plan* plan, const float* x, const float* m0, const float*
 
 int adb_pad_context(adb_plan* plan, const float* ctx, void* out, int n, int t, int c, int t_pad, adb_stream stream) {
   return pad_context_submit(plan, ctx, out, n, t, c, t_pad, static_cast<cudaStream_t>(stream));
+}
+
+int adb_resize_bilinear_u8(adb_plan* plan, const uint8_t* in, void* out, int n, int h, int w, int oh, int ow,
+                           adb_stream stream) {
+  return resize_bilinear_u8_submit(plan, in, out, n, h, w, oh, ow, static_cast<cudaStream_t>(stream));
+}
+
+int adb_gather_patches(adb_plan* plan, const void* const* ptrs, const int* chans, const int* relu, int nsrc, void* out,
+                       int n, int h, int w, int kh, int kw, int stride, int ph, int pw, int k_pad, adb_stream stream) {
+  return gather_patches_submit(plan, ptrs, chans, relu, nsrc, out, n, h, w, kh, kw, stride, ph, pw, k_pad,
+                               static_cast<cudaStream_t>(stream));
+}
+
+int adb_pool3x3(adb_plan* plan, const void* const* ptrs, const int* chans, const int* relu, int nsrc, void* out, int n,
+                int h, int w, int stride, int pad, int mode, adb_stream stream) {
+  return pool3x3_submit(plan, ptrs, chans, relu, nsrc, out, n, h, w, stride, pad, mode, static_cast<cudaStream_t>(stream));
+}
+
+int adb_global_avgpool(adb_plan* plan, const void* const* ptrs, const int* chans, const int* relu, int nsrc, float* out,
+                       int n, int hw, adb_stream stream) {
+  return global_avgpool_submit(plan, ptrs, chans, relu, nsrc, out, n, hw, static_cast<cudaStream_t>(stream));
 }
 
 int adb_memset0(adb_plan* plan, void* ptr, size_t bytes, adb_stream stream) {

@@ -198,8 +198,8 @@ class GaussianDiffusion:
         CUDA graph (fastpath.py); every other call takes the per-step loop below."""
         if not return_all_images and not progress and denoised_fn is None and eta == 0.0 \
                 and self.model_mean_type == ModelMeanType.EPSILON and self.num_timesteps <= 64:  # searched schedules: 4-15 steps
-            if device is None:
-                device = next(model.parameters()).device
+            if device is None:  # the reference needs `model.parameters()` here (:683-684); a given x_T also settles it
+                device = noise.device if noise is not None else next(model.parameters()).device
             assert isinstance(shape, (tuple, list))
             if noise is None:
                 noise = th.randn(*shape, device=device)  # drawn once, whichever path runs (:686-689)

@@ -37,6 +37,7 @@ __all__ = [
     "logsoftmax_grad", "pack_conv_weight_dgrad", "pack_linear_weight_split", "linear_tc",
     "pack_stem_weight", "stem_conv_tc",
     "attention_sd", "layernorm", "geglu", "cfg_ddim_step", "pad_context", "cfg_combine", "plms_update", "dpm_x0", "dpm_update",
+    "resize_bilinear_u8", "gather_patches", "pool3x3", "global_avgpool",
 ]
 
 
@@ -786,4 +787,76 @@ def dpm_update(x: torch.Tensor, m0: torch.Tensor, m1: Optional[torch.Tensor], or
                                          float(c0), float(c1), float(c2), float(inv_r0), _stream()), "adb_dpm_update")
     if plan is not None:
         plan.keep(x, m0, m1, out)
+    return out
+
+
+# ---- Inception-V3 pool_3 extractor (SURVEY 8f N2) ----
+def _sources(srcs):
+    """[(bf16 NHWC tensor, relu_on_load), ...] -> ctypes arrays (ptrs, chans, relu), n, h, w, total channels."""
+    n, h, w = srcs[0][0].shape[:3]
+    k = len(srcs)
+    ptrs, chans, relu = (C.c_void_p * k)(), (C.c_int * k)(), (C.c_int * k)()
+    for i, (t, r) in enumerate(srcs):
+        assert tuple(t.shape[:3]) == (n, h, w), "concatenated sources share n, h, w"
+        ptrs[i] = _dev(t, f"src{i}", torch.bfloat16)
+        chans[i] = t.shape[3]
+        relu[i] = int(bool(r))
+    return ptrs, chans, relu, n, h, w, sum(t.shape[3] for t, _ in srcs)
+
+
+def resize_bilinear_u8(u8: torch.Tensor, oh: int, ow: int, out: Optional[torch.Tensor] = None,
+                       plan: Optional[Plan] = None) -> torch.Tensor:
+    """uint8 NHWC [n, h, w, 3] -> bf16 NHWC [n, oh, ow, 8] (3 channels + zero padding), bilinear (align_corners=False),
+    normalised to [-1, 1]."""
+    n, h, w, c = u8.shape
+    assert c == 3
+    if out is None:
+        out = torch.empty((n, oh, ow, 8), dtype=torch.bfloat16, device=u8.device)
+    _lib.check(_lib.lib().adb_resize_bilinear_u8(_ph(plan), _dev(u8, "u8", torch.uint8), _dev(out, "out", torch.bfloat16),
+                                                 n, h, w, oh, ow, _stream()), "adb_resize_bilinear_u8")
+    if plan is not None:
+        plan.keep(u8, out)
+    return out
+
+
+def gather_patches(srcs, kh: int, kw: int, stride: int = 1, ph: int = 0, pw: int = 0, out: Optional[torch.Tensor] = None,
+                   plan: Optional[Plan] = None) -> torch.Tensor:
+    """im2col over a channel concatenation of sources [(tensor, relu_on_load)]: -> bf16 [n*ho*wo, 1, 1, k_pad]
+    (the 1-tap operand layout of `conv_igemm`), k_pad = kh*kw*channels rounded up to 8."""
+    ptrs, chans, relu, n, h, w, ctot = _sources(srcs)
+    ho, wo = (h + 2 * ph - kh) // stride + 1, (w + 2 * pw - kw) // stride + 1
+    k_pad = (kh * kw * ctot + 7) // 8 * 8
+    if out is None:
+        out = torch.empty((n * ho * wo, 1, 1, k_pad), dtype=torch.bfloat16, device=srcs[0][0].device)
+    assert out.numel() == n * ho * wo * k_pad
+    _lib.check(_lib.lib().adb_gather_patches(_ph(plan), ptrs, chans, relu, len(srcs), _dev(out, "out", torch.bfloat16),
+                                             n, h, w, kh, kw, stride, ph, pw, k_pad, _stream()), "adb_gather_patches")
+    if plan is not None:
+        plan.keep(*[t for t, _ in srcs], out)
+    return out
+
+
+def pool3x3(srcs, stride: int, pad: int, mode: int, out: Optional[torch.Tensor] = None,
+            plan: Optional[Plan] = None) -> torch.Tensor:
+    """mode 0 max / 1 average over 9 / 2 average over in-image taps; -> bf16 [n, ho, wo, channels]."""
+    ptrs, chans, relu, n, h, w, ctot = _sources(srcs)
+    ho, wo = (h + 2 * pad - 3) // stride + 1, (w + 2 * pad - 3) // stride + 1
+    if out is None:
+        out = torch.empty((n, ho, wo, ctot), dtype=torch.bfloat16, device=srcs[0][0].device)
+    _lib.check(_lib.lib().adb_pool3x3(_ph(plan), ptrs, chans, relu, len(srcs), _dev(out, "out", torch.bfloat16), n, h, w,
+                                      stride, pad, mode, _stream()), "adb_pool3x3")
+    if plan is not None:
+        plan.keep(*[t for t, _ in srcs], out)
+    return out
+
+
+def global_avgpool(srcs, out: Optional[torch.Tensor] = None, plan: Optional[Plan] = None) -> torch.Tensor:
+    """-> fp32 [n, channels]: mean over all pixels (ReLU on load per source)."""
+    ptrs, chans, relu, n, h, w, ctot = _sources(srcs)
+    if out is None:
+        out = torch.empty((n, ctot), dtype=torch.float32, device=srcs[0][0].device)
+    _lib.check(_lib.lib().adb_global_avgpool(_ph(plan), ptrs, chans, relu, len(srcs), _dev(out, "out", torch.float32), n,
+                                             h * w, _stream()), "adb_global_avgpool")
+    if plan is not None:
+        plan.keep(*[t for t, _ in srcs], out)
     return out

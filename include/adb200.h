@@ -331,6 +331,30 @@ int adb_dpm_update(adb_plan* plan, const float* x, const float* m0, const float*
  * K/V projection GEMMs and adb_attention_sd read. */
 int adb_pad_context(adb_plan* plan, const float* ctx, void* out, int n, int t, int c, int t_pad, adb_stream stream);
 
+/* ---- Inception-V3 pool_3 feature extractor on the device ----
+ * Replaces the TensorFlow graph evaluation of evaluations/evaluator_v1.py:252-280, 665-679 (pool_3 of
+ * classify_image_graph_def.pb) and pytorch-fid's InceptionV3 of "Stable Diffusion"/scripts/search_ea.py:95-127, 171-182.
+ * Every convolution = adb_gather_patches + adb_conv_igemm (1 tap over the patch rows, BatchNorm folded into the
+ * packed weights and bias); a conv writes its pre-activation and consumers apply ReLU on load.
+ * "Sources" are up to 4 bf16 NHWC tensors of equal n, h, w read as one channel concatenation (th.cat is never
+ * materialised): ptrs[i], chans[i] (multiples of 8), relu[i] != 0 -> max(x, 0) on load. */
+
+/* uint8 NHWC [n, h, w, 3] -> bf16 NHWC [n, oh, ow, 8] (channels 3..7 zero), bilinear with half-pixel centres
+ * (F.interpolate(..., mode="bilinear", align_corners=False), as pytorch-fid resizes to 299 x 299), then x / 127.5 - 1. */
+int adb_resize_bilinear_u8(adb_plan* plan, const uint8_t* in, void* out, int n, int h, int w, int oh, int ow,
+                           adb_stream stream);
+/* im2col: out bf16 [n * ho * wo, k_pad], row = (ky, kx) taps x concatenated channels, zero tail up to k_pad (a multiple
+ * of 8), taps outside the image zero; ho = (h + 2 ph - kh) / stride + 1 (wo likewise). */
+int adb_gather_patches(adb_plan* plan, const void* const* ptrs, const int* chans, const int* relu, int nsrc, void* out,
+                       int n, int h, int w, int kh, int kw, int stride, int ph, int pw, int k_pad, adb_stream stream);
+/* 3x3 pooling, stride 1 or 2, padding 0 or 1. mode 0: max; 1: average over 9 (count_include_pad, torchvision);
+ * 2: average over the in-image taps (the FID Inception). out bf16 [n, ho, wo, sum chans]. */
+int adb_pool3x3(adb_plan* plan, const void* const* ptrs, const int* chans, const int* relu, int nsrc, void* out, int n,
+                int h, int w, int stride, int pad, int mode, adb_stream stream);
+/* global average pool over hw pixels: out fp32 [n, sum chans] (pool_3). */
+int adb_global_avgpool(adb_plan* plan, const void* const* ptrs, const int* chans, const int* relu, int nsrc, float* out,
+                       int n, int hw, adb_stream stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -27,7 +27,7 @@ def timeit(fn, n=10, warm=3):
     return e0.elapsed_time(e1) / n
 
 
-for (t, heads) in [(1024, 4), (256, 6), (64, 8)]:
+for (t, heads) in [(1024, 4), (1024, 6), (256, 6), (64, 8)]:
     c = heads * 64
     qkv = torch.randn(B * t, 3 * c, device=dev, generator=g).bfloat16()
     dout = torch.randn(B * t, c, device=dev, generator=g).bfloat16()
@@ -41,7 +41,7 @@ for (t, heads) in [(1024, 4), (256, 6), (64, 8)]:
     print(f"attention b{B} t{t} h{heads}: fwd {ms_f:.3f} ms ({fl / ms_f / 1e9:.0f} TF/s)  bwd {ms_b:.3f} ms "
           f"({2 * fl / ms_b / 1e9:.0f} TF/s algorithmic, {3.5 * fl / ms_b / 1e9:.0f} executed)")
 
-for (r, c) in [(64, 128), (32, 256)]:
+for (r, c) in [(64, 128), (32, 256), (16, 384), (8, 512)]:
     x = torch.randn(B, r, r, c, device=dev, generator=g).bfloat16()
     dy = torch.randn(B, r, r, c, device=dev, generator=g).bfloat16()
     gamma, beta = torch.ones(c, device=dev), torch.zeros(c, device=dev)
@@ -50,5 +50,16 @@ for (r, c) in [(64, 128), (32, 256)]:
     dx = torch.empty_like(x)
     bst = torch.empty_like(stats)
     ms = timeit(lambda: ops.gn_backward(x, stats, gamma, beta, dy, add=dy, add_mode=ops.RES_SAME, dx=dx, bstats=bst))
-    by = x.numel() * 2 * 6
-    print(f"gn_backward b{B} {r}x{r}x{c}: {ms:.3f} ms ({by / ms / 1e6:.0f} GB/s of the 12 B/element it moves)")
+    by = x.numel() * 2 * 4
+    print(f"gn_backward b{B} {r}x{r}x{c}: {ms:.3f} ms ({by / ms / 1e6:.0f} GB/s algorithmic: x, dout, add read once, dx written)")
+
+for (r, c, film) in [(64, 192, True), (32, 384, True), (16, 576, False), (8, 768, False)]:
+    x = torch.randn(B, r, r, c, device=dev, generator=g).bfloat16()
+    gamma, beta = torch.ones(c, device=dev), torch.zeros(c, device=dev)
+    stats = torch.empty(B, 32, 2, dtype=torch.float64, device=dev)
+    y = torch.empty_like(x)
+    ops.groupnorm(x, gamma, beta, stats=stats)
+    ss = torch.randn(B, 2 * c, device=dev, generator=g) * 0.1 if film else None
+    kw = dict(scale_shift=ss, ss_stride=2 * c) if film else {}
+    ms = timeit(lambda: ops.groupnorm(x, gamma, beta, out=y, stats=stats, stats_ready=True, **kw))
+    print(f"groupnorm_apply b{B} {r}x{r}x{c} film={film}: {ms:.3f} ms ({x.numel() * 4 / ms / 1e6:.0f} GB/s)")

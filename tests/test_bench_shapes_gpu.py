@@ -90,7 +90,7 @@ def test_conv3x3_batch256(res, cin, cout):
     want = torch.stack([o64.sum((1, 3)), (o64 * o64).sum((1, 3))], dim=-1)
     rel = ((stats - want).abs().max() / want.abs().max()).item()
     print(f"  fused GroupNorm sums: max rel err {rel:.3g}")
-    assert rel <= 1e-9
+    assert rel <= 1e-6  # fp32 partial sums per 128-row tile, fp64 across tiles (measured 4e-8 .. 1.2e-7)
 
 
 def test_conv_fused_skip_concat_batch256():
@@ -316,13 +316,13 @@ def test_benchmarked_candidate_at_batch256_reproduces_the_reference_images():
     print(f"cand10 guided @ batch 256, rows 0-7 vs the reference run: psnr={p:.2f} dB max_abs={err.max():.4g} "
           f"p99={np.percentile(err, 99):.4g} p99.9={np.percentile(err, 99.9):.4g}; uint8 mean |diff| {d8.mean():.3f} LSB, "
           f"within 1 LSB {(d8 <= 1).mean() * 100:.1f}%, max {d8.max()}")
-    assert p >= 40.0
-    assert np.percentile(err, 99) <= 0.06 and np.percentile(err, 99.9) <= 0.15
-    assert d8.mean() <= 0.6 and (d8 <= 1).mean() >= 0.88
+    assert p >= 41.5  # measured 44.5 dB
+    assert np.percentile(err, 99) <= 0.08 and np.percentile(err, 99.9) <= 0.22  # measured 0.056 / 0.147 (t = 971: Bm = 22.9)
+    assert d8.mean() <= 0.5 and (d8 <= 1).mean() >= 0.91  # measured 0.33 LSB, 94.4 %
     # batch 8 through the same code path
     plan8 = SchedulePlan(model, active, per_step, 8, cond_fn=guide, pack_uint8=True)
     out8 = plan8.run(noise[:8].contiguous(), y[:8].contiguous()).clone().cpu()
     p8 = psnr(out8, ref)
     cross = psnr(out8, got)
     print(f"  batch 8: psnr={p8:.2f} dB vs the reference; batch-256 rows vs batch-8 rows: {cross:.2f} dB")
-    assert p8 >= 40.0 and cross >= 40.0
+    assert p8 >= 41.5 and cross >= 55.0  # measured 44.5 / 58.6 dB (fp64 atomics order differs between the two batches)

@@ -251,26 +251,35 @@ def test_remote_fid_placeholder_refuses_a_direct_result():
 
 
 def test_inception_pool3_feature_extractor_contract():
-    """uint8 NHWC in, fp32 [B, 2048] out, deterministic for a seed, rejects anything that is not uint8 NHWC RGB."""
+    """The native extractor: torchvision's parameter names (pt_inception-2015-12-05 loads unchanged), deterministic for a
+    seed, rejects anything that is not uint8 NHWC RGB, and has no CPU path."""
     from autodiffusion_b200.inception import InceptionPool3
+    from oracle.inception_ref import InceptionPool3Ref
 
     m = InceptionPool3(seed=0)
+    ref = InceptionPool3Ref(seed=0)
+    want = {k: tuple(v.shape) for k, v in ref.net.state_dict().items()}
+    assert {k: tuple(v.shape) for k, v in m.state_dict().items()} == want
+    assert torch.equal(m.Mixed_6c.branch7x7dbl_3.conv.weight, InceptionPool3(seed=0).Mixed_6c.branch7x7dbl_3.conv.weight)
+    assert not torch.equal(m.Conv2d_1a_3x3.conv.weight, InceptionPool3(seed=1).Conv2d_1a_3x3.conv.weight)
     u8 = torch.randint(0, 256, (2, 64, 64, 3), dtype=torch.uint8, generator=torch.Generator().manual_seed(0))
-    f = m(u8)
-    assert f.shape == (2, 2048) and f.dtype == torch.float32 and torch.isfinite(f).all()
-    assert torch.equal(f, InceptionPool3(seed=0)(u8)) and not torch.equal(f, InceptionPool3(seed=1)(u8))
     with pytest.raises(ValueError):
         m(u8.float())
     with pytest.raises(ValueError):
         m(u8.permute(0, 3, 1, 2))
+    with pytest.raises(RuntimeError):
+        m(u8)  # CPU tensor: there is no fallback
+    f = ref(u8)  # the oracle graph itself: uint8 NHWC in, fp32 [B, 2048] out
+    assert f.shape == (2, 2048) and f.dtype == torch.float32 and torch.isfinite(f).all()
 
 
 def test_inception_fid_variant_pooling():
     """The three pooling details that turn torchvision's Inception into the FID graph (pytorch-fid's FIDInceptionA/C/E):
-    padding-excluding 3x3 average pools (a constant input stays constant up to the border) and a max pool in Mixed_7c."""
-    from autodiffusion_b200.inception import InceptionPool3
+    padding-excluding 3x3 average pools (a constant input stays constant up to the border) and a max pool in Mixed_7c.
+    (Oracle-side check; the native kernels are compared with this graph in tests/test_inception_gpu.py.)"""
+    from oracle.inception_ref import InceptionPool3Ref
 
-    fid, tv = InceptionPool3(seed=0).net, InceptionPool3(seed=0, fid_variant=False).net
+    fid, tv = InceptionPool3Ref(seed=0).net, InceptionPool3Ref(seed=0, fid_variant=False).net
     with torch.no_grad():
         x = torch.ones(1, 192, 9, 9)
         pf, pt = fid.Mixed_5b._forward(x)[3], tv.Mixed_5b._forward(x)[3]

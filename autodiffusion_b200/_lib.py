@@ -21,7 +21,7 @@ LIB_PATH = Path(os.environ["ADB_LIB_PATH"]) if os.environ.get("ADB_LIB_PATH") el
 HEADER = _PKG.parent / "include" / "adb200.h"
 
 SOURCES = ["host.cu", "conv_igemm.cu", "attention.cu", "attention2.cu", "groupnorm.cu", "elementwise.cu", "moments.cu",
-           "attention_bwd.cu", "backward.cu", "attention_sd.cu", "sd_ops.cu", "inception_ops.cu"]
+           "attention_bwd.cu", "attention_bwd_fused.cu", "backward.cu", "attention_sd.cu", "sd_ops.cu", "inception_ops.cu"]
 
 NVCC_FLAGS = [
     "-O3",
@@ -199,6 +199,8 @@ SYMBOLS = {
     "adb_split_bf16": (_I, [_P, _P, _P, _P, C.c_size_t, _I, _P]),
     "adb_attention_lse": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _P]),
     "adb_attention_backward": (_I, [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _P]),
+    "adb_attention_backward_ws": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _P]),
+    "adb_set_attention_backward_fused": (_I, [_I]),
     "adb_gn_backward": (_I, [_P, C.POINTER(GnBwdDesc), _P]),
     "adb_pool_prepare": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _P]),
     "adb_pool_attention": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _P]),

@@ -499,9 +499,10 @@ class EncoderUNetModel(nn.Module):
                 ops.conv_igemm([(dout, 1)], pk.wprojt, None, c, out=da, plan=plan)
                 dqkv = ctx.alloc((n, h, w, 3 * c))
                 dsum = ctx.alloc((n * heads, t), dtype=th.float32)
+                ws = ctx.alloc((n * t, c), dtype=th.float32) if t % 128 == 0 else None  # dQ partials of the single-pass kernel
                 ops.attention_backward(qkv.view(n * t, 3 * c), a.view(n * t, c), da.view(n * t, c), lse, n, t, heads, legacy,
-                                       dqkv=dqkv.view(n * t, 3 * c), dsum=dsum, plan=plan)
-                for tns in (da, dsum, a, qkv, lse):
+                                       dqkv=dqkv.view(n * t, 3 * c), dsum=dsum, plan=plan, dq_ws=ws)
+                for tns in (da, dsum, a, qkv, lse) + ((ws,) if ws is not None else ()):
                     ctx.release(tns)
                 dg = ctx.alloc((n, h, w, c))
                 ops.conv_igemm([(dqkv, 1)], pk.wqkvt, None, c, out=dg, plan=plan)

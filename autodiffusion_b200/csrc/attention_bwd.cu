@@ -16,6 +16,7 @@
 // P / dS *in place* in TMEM, and the gradient products take that as their A operand (TS form)
 // with the row-major K / Q / dO tiles as MN-major B operands - no transposes, no staging of P.
 // tcgen05.mma ops of one thread execute in order, which makes the in-place aliasing safe.
+#include <stdlib.h>
 #include <string.h>
 
 #include "common.cuh"
@@ -411,8 +412,31 @@ __global__ void __launch_bounds__(256) attn_rowdot_kernel(const __nv_bfloat16* _
 
 }  // namespace
 
+int attention_backward_fused_launch(const void* qkv, const void* dout, const float* lse, const float* dsum, void* dqkv,
+                                    float* dq_acc, int b, int t, int heads, int legacy_order, cudaStream_t s,
+                                    const CUtensorMap* tm_qkv128, const CUtensorMap* tm_qkv64, const CUtensorMap* tm_do64);
+
+// Which form adb_attention_backward_ws runs. The single-pass kernel is OPT-IN (ADB_ATTN_BWD_FUSED=1 or
+// adb_set_attention_backward_fused(1)): it is 11 % faster in isolation at T = 1024 (1.47 vs 1.65 ms at batch 256, 4 heads)
+// and 10 % inside a guided candidate (94 vs 104 ms of a 975 ms step), but its dQ partials meet in L2 reductions whose
+// order is not fixed, so two runs of the same candidate differ at fp32-rounding level (0.8 % relative on the guidance
+// gradient after the bf16 roundings downstream) - and the search wants a seed to reproduce its FIDs exactly.
+// set < 0: query only. Returns the mode in force.
+int attention_backward_fused_mode(int set) {
+  static int mode = -1;
+  if (mode < 0) {
+    const char* e = getenv("ADB_ATTN_BWD_FUSED");
+    mode = (e && e[0] == '1') ? 1 : 0;
+  }
+  if (set >= 0) mode = set ? 1 : 0;
+  return mode;
+}
+
+// dq_ws: optional fp32 [b*t, heads*64] workspace. With it, t a multiple of 128 and the fused mode on, the single-pass
+// kernel of attention_bwd_fused.cu runs; otherwise the two-kernel form below.
 int attention_backward_submit(adb_plan* plan, const void* qkv, const void* out, const void* dout, const float* lse,
-                              float* dsum, void* dqkv, int b, int t, int heads, int legacy_order, cudaStream_t stream) {
+                              float* dsum, void* dqkv, float* dq_ws, int b, int t, int heads, int legacy_order,
+                              cudaStream_t stream) {
   ADB_REQUIRE(qkv && out && dout && lse && dsum && dqkv && b > 0 && heads > 0, "attention_backward: bad arguments");
   ADB_REQUIRE(t == 64 || (t >= 128 && t % 128 == 0), "attention_backward: sequence length %d unsupported (64 or a multiple of 128)", t);
   const int C = heads * HD;
@@ -450,6 +474,21 @@ int attention_backward_submit(adb_plan* plan, const void* qkv, const void* out, 
   // algorithmic work = the four gradient products autograd executes (dP, dV, dQ, dK: 2*T*T*64 each); the S
   // recomputation (twice) and the second dP these kernels do instead of storing P are not counted
   const double flops = 8.0 * (double)b * heads * (double)t * (double)t * HD;
+  if (attention_backward_fused_mode(-1) && dq_ws != nullptr && t % 128 == 0) {
+    const int legacy = legacy_order ? 1 : 0;
+    return submit(plan, stream, "attention_bwd", flops, 0.0,
+                  [bp, qkv, o, dO, lse, dsum, dqkv, dq_ws, b, t, heads, legacy](cudaStream_t s) -> int {
+      const size_t vecs = (size_t)b * t * (heads * HD / 8);
+      size_t blocks = (vecs + 255) / 256;
+      const size_t cap = (size_t)num_sms() * 16;
+      if (blocks > cap) blocks = cap;
+      attn_rowdot_kernel<<<(unsigned)blocks, 256, 0, s>>>(o, dO, dsum, b, t, heads);
+      ADB_CUDA(cudaGetLastError());
+      const int r = attention_backward_fused_launch(qkv, dO, lse, dsum, dqkv, dq_ws, b, t, heads, legacy, s, &bp.tmQKV128,
+                                                    &bp.tmQKV64, &bp.tmDO64);
+      return r < 0 ? r : r + 1;
+    });
+  }
   return submit(plan, stream, "attention_bwd", flops, 0.0, [bp, o, dO, dsum, b, t, heads](cudaStream_t s) -> int {
     static bool attr_set = false;
     if (!attr_set) {

@@ -94,12 +94,58 @@ int make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t*
   return ADB_OK;
 }
 
+// fp32 tensor (e.g. the dQ workspace the fused attention backward reduces into with cp.reduce.async.bulk.tensor)
+int make_tmap_f32(CUtensorMap* out, const void* base, int rank, const uint64_t* dims,
+                  const uint64_t* strides_bytes, const uint32_t* box, int swizzle_bytes) {
+  auto fn = get_encode_fn();
+  if (!fn) {
+    set_error("cuTensorMapEncodeTiled not available from the driver");
+    return ADB_ERR_CUDA;
+  }
+  if ((reinterpret_cast<uintptr_t>(base) & 15u) != 0) {
+    set_error("TMA base pointer %p is not 16-byte aligned", base);
+    return ADB_ERR_INVALID;
+  }
+  cuuint64_t gdim[5];
+  cuuint64_t gstr[4];
+  cuuint32_t bx[5];
+  cuuint32_t estr[5];
+  for (int i = 0; i < rank; ++i) {
+    gdim[i] = dims[i];
+    bx[i] = box[i];
+    estr[i] = 1;
+    if (box[i] == 0 || box[i] > 256) {
+      set_error("TMA box dim %d = %u out of range", i, box[i]);
+      return ADB_ERR_INVALID;
+    }
+  }
+  for (int i = 0; i + 1 < rank; ++i) {
+    gstr[i] = strides_bytes[i];
+    if (strides_bytes[i] % 16 != 0) {
+      set_error("TMA stride %d = %llu bytes is not a multiple of 16", i,
+                (unsigned long long)strides_bytes[i]);
+      return ADB_ERR_INVALID;
+    }
+  }
+  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)rank, const_cast<void*>(base),
+                  gdim, gstr, bx, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed with CUresult %d (rank %d dims %llu,%llu box %u,%u)",
+              (int)r, rank, (unsigned long long)dims[0], (unsigned long long)dims[1], box[0], box[1]);
+    return ADB_ERR_CUDA;
+  }
+  return ADB_OK;
+}
+
 // implemented in the kernel translation units
 int conv_block_n(int cout);
 int conv_igemm_submit(adb_plan*, const adb_conv_desc*, cudaStream_t);
 int attention_submit(adb_plan*, const void*, void*, float*, int, int, int, int, cudaStream_t);
-int attention_backward_submit(adb_plan*, const void*, const void*, const void*, const float*, float*, void*, int, int,
+int attention_backward_submit(adb_plan*, const void*, const void*, const void*, const float*, float*, void*, float*, int, int,
                               int, int, cudaStream_t);
+int attention_backward_fused_mode(int);
 int gn_backward_submit(adb_plan*, const adb_gn_bwd_desc*, cudaStream_t);
 int pool_prepare_submit(adb_plan*, const void*, const float*, void*, float*, int, int, int, cudaStream_t);
 int pool_attention_submit(adb_plan*, const float*, const void*, float*, float*, int, int, int, cudaStream_t);
@@ -245,7 +291,16 @@ int adb_attention_lse(adb_plan* plan, const void* qkv, void* out, float* lse, in
 int adb_attention_backward(adb_plan* plan, const void* qkv, const void* out, const void* dout, const float* lse,
                            float* dsum, void* dqkv, int b, int t, int heads, int legacy_order,
                            adb_stream stream) {
-  return attention_backward_submit(plan, qkv, out, dout, lse, dsum, dqkv, b, t, heads, legacy_order,
+  return attention_backward_submit(plan, qkv, out, dout, lse, dsum, dqkv, nullptr, b, t, heads, legacy_order,
+                                   static_cast<cudaStream_t>(stream));
+}
+
+int adb_set_attention_backward_fused(int on) { return attention_backward_fused_mode(on); }
+
+int adb_attention_backward_ws(adb_plan* plan, const void* qkv, const void* out, const void* dout, const float* lse,
+                              float* dsum, void* dqkv, float* dq_ws, int b, int t, int heads, int legacy_order,
+                              adb_stream stream) {
+  return attention_backward_submit(plan, qkv, out, dout, lse, dsum, dqkv, dq_ws, b, t, heads, legacy_order,
                                    static_cast<cudaStream_t>(stream));
 }
 

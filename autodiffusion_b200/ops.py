@@ -233,24 +233,38 @@ def attention(qkv: torch.Tensor, b: int, t: int, heads: int, legacy_order: bool,
 
 def attention_backward(qkv: torch.Tensor, out: torch.Tensor, dout: torch.Tensor, lse: torch.Tensor, b: int, t: int,
                        heads: int, legacy_order: bool, dqkv: Optional[torch.Tensor] = None,
-                       dsum: Optional[torch.Tensor] = None, plan: Optional[Plan] = None) -> torch.Tensor:
-    """Gradient of `attention` w.r.t. qkv. out/dout bf16 [b*t, heads*64] -> dqkv bf16 [b*t, 3*heads*64]."""
+                       dsum: Optional[torch.Tensor] = None, plan: Optional[Plan] = None,
+                       dq_ws: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Gradient of `attention` w.r.t. qkv. out/dout bf16 [b*t, heads*64] -> dqkv bf16 [b*t, 3*heads*64].
+    dq_ws: fp32 [b*t, heads*64] workspace of the single-pass kernel (allocated here when not given and t % 128 == 0)."""
     c = heads * 64
     assert qkv.numel() == b * t * 3 * c and out.numel() == b * t * c and dout.numel() == b * t * c
     if dqkv is None:
         dqkv = torch.empty((b * t, 3 * c), dtype=torch.bfloat16, device=qkv.device)
     if dsum is None:
         dsum = torch.empty((b * heads, t), dtype=torch.float32, device=qkv.device)
+    if dq_ws is None and t % 128 == 0:
+        dq_ws = torch.empty((b * t, c), dtype=torch.float32, device=qkv.device)
+    if dq_ws is not None:
+        assert dq_ws.numel() == b * t * c
     _lib.check(
-        _lib.lib().adb_attention_backward(_ph(plan), _dev(qkv, "qkv", torch.bfloat16), _dev(out, "out", torch.bfloat16),
-                                          _dev(dout, "dout", torch.bfloat16), _dev(lse, "lse", torch.float32),
-                                          _dev(dsum, "dsum", torch.float32), _dev(dqkv, "dqkv", torch.bfloat16),
-                                          b, t, heads, int(bool(legacy_order)), _stream()),
-        "adb_attention_backward",
+        _lib.lib().adb_attention_backward_ws(_ph(plan), _dev(qkv, "qkv", torch.bfloat16), _dev(out, "out", torch.bfloat16),
+                                             _dev(dout, "dout", torch.bfloat16), _dev(lse, "lse", torch.float32),
+                                             _dev(dsum, "dsum", torch.float32), _dev(dqkv, "dqkv", torch.bfloat16),
+                                             _opt(dq_ws, "dq_ws", torch.float32), b, t, heads, int(bool(legacy_order)),
+                                             _stream()),
+        "adb_attention_backward_ws",
     )
     if plan is not None:
-        plan.keep(qkv, out, dout, lse, dsum, dqkv)
+        plan.keep(qkv, out, dout, lse, dsum, dqkv, dq_ws)
     return dqkv
+
+
+def set_attention_backward_fused(on: Optional[bool]) -> bool:
+    """Choose the attention-backward form recorded from now on (include/adb200.h: adb_set_attention_backward_fused):
+    True = single-pass kernel (faster, fp32-rounding-level run-to-run differences), False = deterministic two-kernel form
+    (default). None only queries. Returns the mode in force."""
+    return bool(_lib.lib().adb_set_attention_backward_fused(-1 if on is None else int(bool(on))))
 
 
 def gn_backward(x: torch.Tensor, stats: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, dout: torch.Tensor,

@@ -216,6 +216,17 @@ int adb_attention_lse(adb_plan* plan, const void* qkv, void* out, float* lse, in
 int adb_attention_backward(adb_plan* plan, const void* qkv, const void* out, const void* dout, const float* lse,
                            float* dsum, void* dqkv, int b, int t, int heads, int legacy_order,
                            adb_stream stream);
+/* Same, with an fp32 [b*t, heads*64] workspace `dq_ws`: when t is a multiple of 128 the single-pass kernel runs (one
+ * exponential and five tile products per score instead of two and seven; dQ partials are reduced into dq_ws with
+ * TMA reductions (cp.reduce.async.bulk.tensor) and rounded into dqkv by a second kernel). dq_ws == NULL, or the
+ * deterministic mode (see adb_set_attention_backward_fused), behaves like adb_attention_backward. */
+int adb_attention_backward_ws(adb_plan* plan, const void* qkv, const void* out, const void* dout, const float* lse,
+                              float* dsum, void* dqkv, float* dq_ws, int b, int t, int heads, int legacy_order,
+                              adb_stream stream);
+/* Selects what adb_attention_backward_ws records from now on: 1 = the single-pass kernel (faster; dQ partials are summed
+ * by L2 reductions in no fixed order, so results are reproducible to fp32 rounding only), 0 = the deterministic
+ * two-kernel form (default; also ADB_ATTN_BWD_FUSED=1 in the environment). on < 0 only queries. Returns the mode in force. */
+int adb_set_attention_backward_fused(int on);
 
 /* Gradient of adb_groupnorm (single source) w.r.t. its input: GroupNorm32 (+FiLM) (+SiLU) (+2x average
  * pool) backward (nn.py:17-19, unet.py:236-258 under autograd). */

@@ -93,8 +93,19 @@ def test_gn_backward(n, res, c, variant):
 
 @pytest.mark.parametrize("b,t,heads", [(2, 64, 8), (2, 256, 6), (1, 1024, 4), (3, 64, 2), (2, 128, 3)])
 @pytest.mark.parametrize("legacy", [True, False])
-def test_attention_backward(b, t, heads, legacy):
+@pytest.mark.parametrize("fused", [False, True])
+def test_attention_backward(b, t, heads, legacy, fused):
+    """fused = the opt-in single-pass kernel (attention_bwd_fused.cu; t % 128 == 0), else the deterministic two-kernel form."""
     ops = _ops()
+    prev = ops.set_attention_backward_fused(None)
+    ops.set_attention_backward_fused(fused)
+    try:
+        _attention_backward_case(ops, b, t, heads, legacy, fused)
+    finally:
+        ops.set_attention_backward_fused(prev)
+
+
+def _attention_backward_case(ops, b, t, heads, legacy, fused):
     c = heads * 64
     qkv = _bf(_rand((b, 3 * c, t), 50 + t + heads, 1.2)).requires_grad_(True)
     out_ref = unet_ref.qkv_attention(qkv, heads, new_order=not legacy)  # [b, c, t]
@@ -109,7 +120,10 @@ def test_attention_backward(b, t, heads, legacy):
     got_out = out.float().view(b, t, c).permute(0, 2, 1).cpu()
     _check(got_out, out_ref.detach(), 2 ** -6, f"attention(lse) fwd b{b} t{t} h{heads} legacy={legacy}")
     got = dqkv.float().view(b, t, 3 * c).permute(0, 2, 1).cpu()
-    _check(got, ref, 2 ** -5, f"attention_backward b{b} t{t} h{heads} legacy={legacy}")
+    _check(got, ref, 2 ** -5, f"attention_backward b{b} t{t} h{heads} legacy={legacy} fused={fused}")
+    if not fused:  # the default form is bit-reproducible
+        again = ops.attention_backward(rows, out, drows, lse, b, t, heads, legacy)
+        assert torch.equal(again, dqkv)
 
 
 def test_conv_dgrad_weights():

@@ -158,10 +158,20 @@ def test_attention_forward_batch256(t, heads, legacy):
     _check(out.float(), ref, 2 ** -6, f"attention n{N} t{t} h{heads} legacy={legacy}")
 
 
-@pytest.mark.parametrize("t,heads", [(1024, 4), (256, 6), (64, 8)])
-def test_attention_backward_batch256(t, heads):
-    """The classifier's attention layers (legacy order, width 128: 256 / 384 / 512 channels) at batch 256."""
+@pytest.mark.parametrize("t,heads,fused", [(1024, 4, False), (256, 6, False), (64, 8, False), (1024, 4, True), (256, 6, True)])
+def test_attention_backward_batch256(t, heads, fused):
+    """The classifier's attention layers (legacy order, width 128: 256 / 384 / 512 channels) at batch 256, in the default
+    two-kernel form and in the opt-in single-pass form."""
     ops = _ops()
+    prev = ops.set_attention_backward_fused(None)
+    ops.set_attention_backward_fused(fused)
+    try:
+        _attention_backward_batch256(ops, t, heads)
+    finally:
+        ops.set_attention_backward_fused(prev)
+
+
+def _attention_backward_batch256(ops, t, heads):
     c = heads * 64
     rows = _rand((N * t, 3 * c), 50 + t, 1.2).to(torch.bfloat16)
     drows = _rand((N * t, c), 51).to(torch.bfloat16)

@@ -815,11 +815,11 @@ class Dynamic_UNetModel(nn.Module):
                 up.finalize(use_graph=os.environ.get("ADB_NO_GRAPH", "0") != "1", validate=validate)
                 up._validated = validate
             self._plans[key] = up
-            if len(self._plans) > max(2, self.max_cached_plans):
-                for k in self._plans:  # oldest first
-                    if k[3] != () and k != key:
-                        del self._plans[k]  # a SchedulePlan still holding it keeps it alive; the cache lets go
-                        break
+            while len(self._plans) > max(2, self.max_cached_plans):
+                victim = next((k for k in self._plans if k[3] != () and k != key), None)  # oldest first
+                if victim is None:
+                    break
+                del self._plans[victim]  # a SchedulePlan still holding it keeps it alive; the cache lets go
         else:
             self._plans.move_to_end(key)
         return up

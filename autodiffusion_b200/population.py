@@ -58,6 +58,10 @@ def run_population(model, diffusion, cond_fn, n_candidates: int, num_samples: in
     if warmup:  # one candidate outside the timed region: kernel attributes, NCCL communicator, allocator, pinned buffers
         ev.evaluate_population(draw_population(max(1, world), time_step, model.layer_num, max_prun, seed=seed + 991),
                                None)
+        if world > 1:  # the moment all-reduce itself (NCCL connection set-up for a 33.6 MB fp64 buffer: ~0.35 s the first time)
+            from .evaluator import MomentAccumulator
+
+            MomentAccumulator(ref_dim, dev).all_reduce()
 
     def barrier():
         if world > 1:

@@ -68,7 +68,7 @@ def parse():
                     help="skip the secondary measurements of the default line: 4-step schedule, stock-API call, same-box "
                          "torch-eager arm (N=1), population evaluation (N>1)")
     ap.add_argument("--pop-candidates", type=int, default=0,
-                    help="population_eval (N>1): number of candidates (default 6 x N + 2, i.e. BASELINE configs[2]'s 50 at N=8)")
+                    help="population_eval (N>1): number of candidates (default 6 x N + 1; BASELINE configs[2]'s 50 at N=8)")
     ap.add_argument("--sd-sampler", default="ddim", choices=["ddim", "plms", "dpm"],
                     help="sdv1 workload: searched-timestep DDIM (BASELINE configs[4]), PLMS, or DPM-Solver++(2M)")
     ap.add_argument("--workload", default="admg64", choices=["admg64", "lsun256", "sdv1"],
@@ -381,7 +381,9 @@ def run_ours(args):
         if world > 1:
             from autodiffusion_b200.population import run_population
 
-            n_c = args.pop_candidates or 6 * world + 2
+            # 8 GPUs: BASELINE configs[2]'s 50 candidates (48 whole + 2 batch-sharded); fewer ranks: 6 per rank + 1, so that
+            # the batch-sharded tail and its NCCL moment all-reduce are exercised at every N > 1 within the same ~30 s
+            n_c = args.pop_candidates or (50 if world == 8 else 6 * world + 1)
             pop = run_population(model, diffusion, None if args.unet_only else guidance, n_c, num_samples=1000, batch_size=B,
                                  fid_method="eigh")
             pop.pop("fids")

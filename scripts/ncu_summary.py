@@ -42,7 +42,8 @@ def main():
                 b = 0.0
                 for c in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
                     b += float(r[idx[c]]) * UNIT.get(units[idx[c]], 1.0)
-                conv.append((name[:40], b, float(r[idx["gpu__time_duration.sum"]])))
+                tu = {"nsecond": 1e-3, "ns": 1e-3, "usecond": 1.0, "us": 1.0, "msecond": 1e3, "ms": 1e3, "second": 1e6, "s": 1e6}
+                conv.append((name[:40], b, float(r[idx["gpu__time_duration.sum"]]) * tu.get(units[idx["gpu__time_duration.sum"]], 1.0)))
     print(f"{len(data)} launches -> {out}")
     if traffic and conv:
         json.dump({"dram_bytes_per_launch_avg": sum(b for _, b, _ in conv) / len(conv), "launches_sampled": len(conv),

@@ -56,5 +56,23 @@ for _ in range(2):
             w = ops.pack_conv_weight([(R(c, c, 3, 3) / math.sqrt(9 * c)).cpu()]).to(dev)
             st = torch.zeros(B, 32, 2, dtype=torch.float64, device=dev)
             ops.conv_igemm([(x, 9)], w, R(c), c, stats_out=st)
+    if "convset" in which and _ == 0:
+        # the distinct 3x3 convolutions of ADM-G 64 (Cin -> Cout @ resolution), the classifier's 128-wide
+        # ones, and the qkv / proj GEMMs at the three attention resolutions: what `roofline.traffic` is averaged over
+        convs = [(64, 192, 192), (64, 384, 192), (64, 576, 192), (64, 128, 128), (32, 192, 384), (32, 384, 384), (32, 576, 384),
+                 (32, 768, 384), (32, 960, 384), (32, 576, 576), (32, 256, 256), (16, 384, 576), (16, 576, 576), (16, 960, 576),
+                 (16, 1152, 576), (16, 1344, 576), (16, 768, 768), (8, 576, 768), (8, 768, 768), (8, 1344, 768), (8, 1536, 768)]
+        for (r, cin, cout) in convs:
+            x = R(B, r, r, cin).bfloat16()
+            w = ops.pack_conv_weight([(R(cout, cin, 3, 3) / math.sqrt(9 * cin)).cpu()]).to(dev)
+            st = torch.zeros(B, 32, 2, dtype=torch.float64, device=dev)
+            ops.conv_igemm([(x, 9)], w, R(cout), cout, stats_out=st)
+            del x, w
+        for (r, c) in [(32, 384), (16, 576), (8, 768)]:
+            x = R(B, r, r, c).bfloat16()
+            wq = ops.pack_conv_weight([(R(3 * c, c, 1) / math.sqrt(c)).cpu()]).to(dev)
+            wp = ops.pack_conv_weight([(R(c, c, 1) / math.sqrt(c)).cpu()]).to(dev)
+            ops.conv_igemm([(x, 1)], wq, R(3 * c), 3 * c)
+            ops.conv_igemm([(x, 1)], wp, R(c), c, residual=x, res_mode=ops.RES_SAME)
 torch.cuda.synchronize()
 print("ok")

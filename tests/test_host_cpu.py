@@ -163,3 +163,39 @@ def test_library_loads_and_exports_header_symbols():
     assert handle.adb_version() == 100
     assert handle.adb_conv_block_n(192) == 192 and handle.adb_conv_block_n(6) == 16
     assert handle.adb_plan_num_ops(None) == 0
+
+
+def test_fast_path_locates_the_modules_behind_the_reference_closures():
+    """fastpath.py (host side): the UNet / classifier behind the search script's closures are found through the closure cells
+    (`self.model`, `self.classifier` of the captured searcher, or the module captured directly); a CPU call is never fused."""
+    import types
+
+    import torch
+
+    from autodiffusion_b200 import classifier_defaults, create_classifier, create_model_and_diffusion, model_and_diffusion_defaults
+    from autodiffusion_b200.classifier import ClassifierGuidance
+    from autodiffusion_b200.fastpath import _find_modules, try_fast_path
+
+    d = model_and_diffusion_defaults()
+    d.update(attention_resolutions="32,16,8", class_cond=True, image_size=64, learn_sigma=True, num_channels=64, num_head_channels=64,
+             num_res_blocks=1, resblock_updown=True, use_new_attention_order=True, use_scale_shift_norm=True, use_dynamic_unet=True)
+    model, diffusion = create_model_and_diffusion(**d)
+    cd = classifier_defaults()
+    cd.update(classifier_depth=1, classifier_width=64)
+    clf = create_classifier(**cd)
+    self = types.SimpleNamespace(model=model, classifier=clf, active_diffusion=diffusion)
+    args = types.SimpleNamespace(classifier_scale=1.0, class_cond=True)
+
+    def cond_fn(x, t, y=None, skip_layers=None, timesteps=None):
+        return self.classifier(x, t) * args.classifier_scale
+
+    def model_fn(x, t, y=None, skip_layers=None, timesteps=None):
+        return self.model(x, t, y if args.class_cond else None, skip_layer=skip_layers[self.active_diffusion.timestep_map.index(t[0])])
+
+    direct = lambda x, t, y=None: model(x, t, y)
+    assert _find_modules(model_fn)[0] == [model] and _find_modules(cond_fn)[1] == [clf]
+    assert _find_modules(direct)[0] == [model] and _find_modules(model)[0] == [model]
+    assert _find_modules(ClassifierGuidance(clf, 2.0))[1] == [clf]
+    assert _find_modules(lambda x, t: x) == ([], [])
+    noise = torch.zeros(2, 3, 64, 64)
+    assert try_fast_path(diffusion, model_fn, (2, 3, 64, 64), noise, True, cond_fn, {"y": torch.zeros(2, dtype=torch.long)}, "cpu") is None

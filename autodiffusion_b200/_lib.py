@@ -108,6 +108,15 @@ class ConvDesc(C.Structure):
         ("stats2_choff", C.c_int),
         ("bias_stride", C.c_int),
         ("seg_stride", C.c_int * 3),
+        ("gnb_x", C.c_void_p),
+        ("gnb_stats", C.c_void_p),
+        ("gnb_gamma", C.c_void_p),
+        ("gnb_beta", C.c_void_p),
+        ("gnb_scale_shift", C.c_void_p),
+        ("gnb_ss_stride", C.c_int),
+        ("gnb_eps", C.c_float),
+        ("gnb_silu", C.c_int),
+        ("gnb_bstats", C.c_void_p),
     ]
 
 
@@ -163,6 +172,7 @@ class GnBwdDesc(C.Structure):
         ("add_mode", C.c_int),
         ("dx", C.c_void_p),
         ("bstats", C.c_void_p),
+        ("bstats_ready", C.c_int),
     ]
 
 
@@ -184,6 +194,7 @@ SYMBOLS = {
     "adb_plan_op_info": (_I, [_P, _I, C.POINTER(C.c_char_p), C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     "adb_plan_run_profiled": (_I, [_P, _P, C.POINTER(C.c_float), _I]),
     "adb_conv_block_n": (_I, [_I]),
+    "adb_conv_gnb_supported": (_I, [_I, _I, _I, _I]),
     "adb_conv_igemm": (_I, [_P, C.POINTER(ConvDesc), _P]),
     "adb_attention": (_I, [_P, _P, _P, _I, _I, _I, _I, _P]),
     "adb_groupnorm": (_I, [_P, C.POINTER(GnDesc), _P]),

@@ -404,6 +404,15 @@ class EncoderUNetModel(nn.Module):
                 return {}
             return {"stats_out": new_slot(t)}
 
+        fuse_gnb = os.environ.get("ADB_NO_GNB_FUSE", "0") != "1"
+
+        def gnb_of(x: th.Tensor, st: th.Tensor, gamma, beta, silu: bool, **kw) -> Optional[dict]:
+            """`conv_igemm(gnb=...)` descriptor: the data-gradient conv producing d(GroupNorm(x) output) also reduces the
+            two sums of that GroupNorm's backward (into `bscratch`), which then reads x and the gradient once."""
+            if not fuse_gnb or not ops.conv_gnb_supported(*x.shape):
+                return None
+            return dict(x=x, stats=st, gamma=gamma, beta=beta, silu=silu, bstats=bscratch, **kw)
+
         def gn(x, gamma, beta, out_t, **kw) -> th.Tensor:
             """GroupNorm of x; returns the [B,32,2] sums it normalised with (kept for the backward pass)."""
             st = stats_of.get(x.data_ptr())
@@ -447,14 +456,17 @@ class EncoderUNetModel(nn.Module):
 
             def bwd(dout: th.Tensor) -> th.Tensor:
                 dg2 = ctx.alloc((n, ho, wo, cout))
-                ops.conv_igemm([(dout, 9)], pk.w2t, None, cout, out=dg2, plan=plan)
+                fz = gnb_of(c1, st_c1, pk.g2, pk.be2, True, scale_shift=(ss_all, pk.ss_off), ss_stride=ss_total)
+                ops.conv_igemm([(dout, 9)], pk.w2t, None, cout, out=dg2, plan=plan, gnb=fz)
                 dc1 = ctx.alloc((n, ho, wo, cout))
                 ops.gn_backward(c1, st_c1, pk.g2, pk.be2, dg2, scale_shift=(ss_all, pk.ss_off),
-                                ss_stride=ss_total, silu=True, dx=dc1, bstats=bscratch, plan=plan)
+                                ss_stride=ss_total, silu=True, dx=dc1, bstats=bscratch, plan=plan,
+                                bstats_ready=fz is not None)
                 ctx.release(dg2)
                 ctx.release(c1)
                 dg1 = ctx.alloc((n, ho, wo, cin))
-                ops.conv_igemm([(dc1, 9)], pk.w1t, None, cin, out=dg1, plan=plan)
+                fz = None if down else gnb_of(x, st_x, pk.g1, pk.be1, True)
+                ops.conv_igemm([(dc1, 9)], pk.w1t, None, cin, out=dg1, plan=plan, gnb=fz)
                 ctx.release(dc1)
                 if pk.wst is not None:  # skip path: x -> 1x1 conv
                     add = ctx.alloc((n, h, w, cin))
@@ -466,7 +478,7 @@ class EncoderUNetModel(nn.Module):
                     add_mode = ops.RES_AVGPOOL2 if down else ops.RES_SAME
                 dx = ctx.alloc((n, h, w, cin))
                 ops.gn_backward(x, st_x, pk.g1, pk.be1, dg1, silu=True, resample=mode, add=add,
-                                add_mode=add_mode, dx=dx, bstats=bscratch, plan=plan)
+                                add_mode=add_mode, dx=dx, bstats=bscratch, plan=plan, bstats_ready=fz is not None)
                 ctx.release(dg1)
                 ctx.release(add)
                 ctx.release(x)
@@ -505,11 +517,12 @@ class EncoderUNetModel(nn.Module):
                 for tns in (da, dsum, a, qkv, lse) + ((ws,) if ws is not None else ()):
                     ctx.release(tns)
                 dg = ctx.alloc((n, h, w, c))
-                ops.conv_igemm([(dqkv, 1)], pk.wqkvt, None, c, out=dg, plan=plan)
+                fz = gnb_of(x, st_x, pk.g, pk.be, False)
+                ops.conv_igemm([(dqkv, 1)], pk.wqkvt, None, c, out=dg, plan=plan, gnb=fz)
                 ctx.release(dqkv)
                 dx = ctx.alloc((n, h, w, c))
                 ops.gn_backward(x, st_x, pk.g, pk.be, dg, silu=False, add=dout, add_mode=ops.RES_SAME,
-                                dx=dx, bstats=bscratch, plan=plan)
+                                dx=dx, bstats=bscratch, plan=plan, bstats_ready=fz is not None)
                 ctx.release(dg)
                 ctx.release(x)
                 return dx

@@ -440,9 +440,15 @@ int gn_backward_submit(adb_plan* plan, const adb_gn_bwd_desc* d, cudaStream_t st
   // below execute 1.5x that (x and dout are read by both): a cluster-per-sample single-launch form that re-reads its slice
   // from L2 was measured SLOWER (0.36-0.40 ms vs 0.31 ms at 256 x 64x64x128; profiles/README.md) and is not kept.
   const double bytes = 2.0 * elems * (1.0 + dscale + (d->add_mode == ADB_RES_NONE ? 0.0 : (d->add_mode == ADB_RES_AVGPOOL2 ? 0.25 : 1.0)) + 1.0);
-  return submit(plan, stream, "groupnorm_bwd", 0.0, bytes, [p](cudaStream_t s) -> int {
+  const int ready = d->bstats_ready ? 1 : 0;
+  return submit(plan, stream, "groupnorm_bwd", 0.0, bytes, [p, ready](cudaStream_t s) -> int {
     dim3 grid(p.splits, p.n);
     const size_t smem = 6 * (size_t)p.C * sizeof(float);
+    if (ready) {  // the two sums came out of the producing data-gradient conv's epilogue (adb_conv_desc.gnb_*)
+      gn_bwd_kernel<true, 4><<<grid, GB_THREADS, smem, s>>>(p);
+      ADB_CUDA(cudaGetLastError());
+      return 1;
+    }
     ADB_CUDA(cudaMemsetAsync(p.bstats, 0, (size_t)p.n * GN_GROUPS * 2 * sizeof(double), s));
     // 4 channels per thread (80 registers, 3 blocks/SM) measured 3.9 TB/s vs 3.5 TB/s for 8 channels per thread
     // (128 registers, 2 blocks/SM) and 2.9 TB/s for the first version (157 registers, 1 block/SM)

@@ -67,6 +67,17 @@ struct ConvKParams {
   int choff2;
   // x / cpg == (x * magic) >> 32 for the column indices that occur (x * cpg < 2^32)
   unsigned long long cpg_magic, cpg2_magic;
+  // GroupNorm-backward sums mode (adb_conv_desc.gnb_*): this conv is a data gradient dY; tmRes then maps the consumer
+  // GroupNorm's forward input x, `stats` is the target of sum dxh / sum dxh*xh, and nothing is added to the output.
+  int gnb;
+  double gnb_inv_cnt;  // 1 / (channels per group * pixels per image)
+  const double* gnb_stats;
+  const float* gnb_gamma;
+  const float* gnb_beta;
+  const float* gnb_ss;
+  int gnb_ss_stride;
+  float gnb_eps;
+  int gnb_silu;
 };
 
 __device__ __forceinline__ int fast_div(int x, unsigned long long magic) {
@@ -90,7 +101,9 @@ struct Cfg {
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_BYTES + 1024 /*align slack*/;
 };
 
-template <int BLOCK_N, int NCTA>
+// GNB: the epilogue also reduces the consumer GroupNorm's backward sums (ConvKParams::gnb); a separate instantiation so
+// that the plain kernel's register allocation is untouched.
+template <int BLOCK_N, int NCTA, bool GNB>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 conv_igemm_kernel(const __grid_constant__ ConvKParams p) {
   using C = Cfg<BLOCK_N, NCTA>;
@@ -316,6 +329,23 @@ conv_igemm_kernel(const __grid_constant__ ConvKParams p) {
           tma_load_2d(epi_base + 2048u * b, &p.tmRes, res_bar0 + 8u * b, n0 + cbeg + ci * CHUNK_COLS, row0f);
         }
       }
+      // gnb: per-column coefficients of the consumer GroupNorm (lane j <-> channel col + j of image imgw), fetched one chunk
+      // ahead of their use so that the L2 latency never sits in front of the column walk
+      struct { double sum, sq; float ga, be, sc, sh; } gn = {0.0, 0.0, 0.f, 0.f, 0.f, 0.f};
+      const int imgw = GNB ? row0f / P : 0;  // the image this warp's 32 rows belong to (h*w % 32 == 0)
+      auto gnb_fetch = [&](int col) {
+        const int ch = col + lane;
+        const double* sp = p.gnb_stats + ((size_t)imgw * 32 + fast_div(ch, p.cpg_magic)) * 2;
+        gn.sum = __ldg(sp);
+        gn.sq = __ldg(sp + 1);
+        gn.ga = __ldg(p.gnb_gamma + ch);
+        gn.be = __ldg(p.gnb_beta + ch);
+        if (p.gnb_ss != nullptr) {
+          gn.sc = __ldg(p.gnb_ss + (size_t)imgw * p.gnb_ss_stride + ch);
+          gn.sh = __ldg(p.gnb_ss + (size_t)imgw * p.gnb_ss_stride + p.cout + ch);
+        }
+      };
+      if (GNB && fast) gnb_fetch(n0 + cbeg);
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
       const bool row_ok = m < p.M;
@@ -360,6 +390,10 @@ conv_igemm_kernel(const __grid_constant__ ConvKParams p) {
         for (int ci = 0; ci < nch; ++ci) {
           const int c = cbeg + ci * CHUNK_COLS;
           const int col0 = n0 + c;
+          // gnb: this chunk's column coefficients were requested one chunk ago; request the next chunk's now
+          const double g_sum = gn.sum, g_sq = gn.sq;
+          const float g_ga = gn.ga, g_be = gn.be, g_sc = gn.sc, g_sh = gn.sh;
+          if (GNB && ci + 1 < nch) gnb_fetch(col0 + CHUNK_COLS);
           uint32_t v[32];
           tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * BLOCK_N + c, v);
           float4 bv[8];
@@ -385,15 +419,17 @@ conv_igemm_kernel(const __grid_constant__ ConvKParams p) {
             res_phase ^= 1u << res_buf;
             const uint8_t* rrow = epi_gen + 2048 * res_buf + lane * 64;
             uint4 rc[4];
+            if (!GNB)
 #pragma unroll
             for (int g = 0; g < 4; ++g) rc[g] = *reinterpret_cast<const uint4*>(rrow + ((g ^ ((lane >> 1) & 3)) << 4));
             __syncwarp();
-            if (ci + 2 < nch && lane == 0) {  // this buffer is free again: request the chunk after next
+            if (!GNB && ci + 2 < nch && lane == 0) {  // this buffer is free again: request the chunk after next
               fence_proxy_async_smem();
               mbar_arrive_expect_tx(res_bar0 + 8u * res_buf, 2048);
               tma_load_2d(epi_base + 2048u * res_buf, &p.tmRes, res_bar0 + 8u * res_buf, col0 + 2 * CHUNK_COLS, row0f);
             }
             res_buf ^= 1;
+            if (!GNB)
 #pragma unroll
             for (int g = 0; g < 4; ++g) {
               f[g * 8 + 0] += bf16_lo(rc[g].x);
@@ -426,6 +462,55 @@ conv_igemm_kernel(const __grid_constant__ ConvKParams p) {
             // column sums of the STORED values: lane j walks column j down the staged tile's 32 rows
             float cs = 0.f, cq = 0.f;
             const uint32_t cch = (uint32_t)lane >> 3, cin8 = ((uint32_t)lane & 7u) * 2u;
+            if (GNB) {
+              // GroupNorm-backward sums: the stored values are dY; the matching 32 x 32 tile of the GroupNorm's input x sits
+              // in the residual buffer waited for above (res_buf was flipped since). Lane j owns channel col0 + j.
+              // With hz = z / 2 = x * a + b: silu'(z) = (1 + th)(1 + hz (1 - th)) / 2, th = tanh(hz); the sums are taken
+              // against raw x and turned into sums against xh = x * rstd + m0 once per column.
+              const double mean = g_sum * p.gnb_inv_cnt;
+              const float varf = fmaxf((float)fma(g_sq, p.gnb_inv_cnt, -mean * mean), 0.f) + p.gnb_eps;
+              float rstd = rsqrtf(varf);
+              rstd *= fmaf(-0.5f * varf * rstd, rstd, 1.5f);  // one Newton step: within an ulp of 1 / sqrt
+              const float m0 = -(float)mean * rstd;
+              const float sc = 1.0f + g_sc;
+              const float A = g_ga * sc;
+              const float Bc = fmaf(g_be, sc, g_sh);
+              const uint8_t* xt = epi_gen + 2048 * (res_buf ^ 1);
+              float sx = 0.f;
+              if (p.gnb_silu) {
+                const float hA = 0.5f * A, a = hA * rstd, b = fmaf(hA, m0, 0.5f * Bc);
+#pragma unroll
+                for (int r = 0; r < 32; ++r) {
+                  const uint32_t off = r * 64 + (((cch ^ ((uint32_t)(r >> 1) & 3u)) << 4) + cin8);
+                  const float dy = __uint_as_float((uint32_t)(*reinterpret_cast<const uint16_t*>(epi_out_gen + off)) << 16);
+                  const float xv = __uint_as_float((uint32_t)(*reinterpret_cast<const uint16_t*>(xt + off)) << 16);
+                  const float hz = fmaf(xv, a, b);
+                  float th;
+                  asm("tanh.approx.f32 %0, %1;" : "=f"(th) : "f"(hz));
+                  const float dxh = dy * (fmaf(hA, th, hA) * fmaf(hz, 1.0f - th, 1.0f));
+                  cs += dxh;
+                  sx = fmaf(dxh, xv, sx);
+                }
+              } else {
+#pragma unroll
+                for (int r = 0; r < 32; ++r) {
+                  const uint32_t off = r * 64 + (((cch ^ ((uint32_t)(r >> 1) & 3u)) << 4) + cin8);
+                  const float dy = __uint_as_float((uint32_t)(*reinterpret_cast<const uint16_t*>(epi_out_gen + off)) << 16);
+                  const float xv = __uint_as_float((uint32_t)(*reinterpret_cast<const uint16_t*>(xt + off)) << 16);
+                  cs += dy;
+                  sx = fmaf(dy, xv, sx);
+                }
+                cs *= A;
+                sx *= A;
+              }
+              cq = fmaf(rstd, sx, m0 * cs);
+              __syncwarp();
+              if (ci + 2 < nch && lane == 0) {  // the x buffer is free now: request the chunk after next
+                fence_proxy_async_smem();
+                mbar_arrive_expect_tx(res_bar0 + 8u * (res_buf ^ 1), 2048);
+                tma_load_2d(epi_base + 2048u * (res_buf ^ 1), &p.tmRes, res_bar0 + 8u * (res_buf ^ 1), col0 + 2 * CHUNK_COLS, row0f);
+              }
+            } else {
 #pragma unroll
             for (int r = 0; r < 32; ++r) {
               const uint16_t hv = *reinterpret_cast<const uint16_t*>(
@@ -433,6 +518,7 @@ conv_igemm_kernel(const __grid_constant__ ConvKParams p) {
               const float val = __uint_as_float((uint32_t)hv << 16);
               cs += val;
               cq = fmaf(val, val, cq);
+            }
             }
             // groups are runs of consecutive lanes: segmented inclusive scan, the last lane of a run owns its bin
             {
@@ -747,12 +833,12 @@ conv_igemm_kernel(const __grid_constant__ ConvKParams p) {
   }
 }
 
-template <int BLOCK_N, int NCTA>
+template <int BLOCK_N, int NCTA, bool GNB = false>
 int launch(const ConvKParams& kp, cudaStream_t stream) {
   using C = Cfg<BLOCK_N, NCTA>;
   static bool attr_set = false;
   if (!attr_set) {
-    ADB_CUDA(cudaFuncSetAttribute(conv_igemm_kernel<BLOCK_N, NCTA>,
+    ADB_CUDA(cudaFuncSetAttribute(conv_igemm_kernel<BLOCK_N, NCTA, GNB>,
                                   cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
     attr_set = true;
   }
@@ -772,7 +858,7 @@ int launch(const ConvKParams& kp, cudaStream_t stream) {
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  ADB_CUDA(cudaLaunchKernelEx(&cfg, conv_igemm_kernel<BLOCK_N, NCTA>, kp));
+  ADB_CUDA(cudaLaunchKernelEx(&cfg, conv_igemm_kernel<BLOCK_N, NCTA, GNB>, kp));
   return 1;
 }
 
@@ -819,6 +905,24 @@ int conv_ncta(int block_n) {
 bool is_pow2(int v) { return v > 0 && (v & (v - 1)) == 0; }
 
 }  // namespace
+
+// the N tile conv_igemm_submit ends up with for an [M, cout_pad] output
+static int effective_block_n(long long M, int cout, int cout_pad) {
+  int block_n = conv_block_n(cout);
+  // the 256-wide pair tile pays once there is at least one wave of them; small problems keep the 128-wide tile
+  // (cout_pad is a multiple of 256, hence of 128 as well)
+  if (block_n == 256 && ((M + 2 * BLOCK_M - 1) / (2 * BLOCK_M)) * (cout_pad / 256) < num_sms() / 2) block_n = 128;
+  return block_n;
+}
+
+int conv_gnb_supported(int n, int h, int w, int cout) {
+  const long long P = (long long)h * w, M = P * n;
+  if (n <= 0 || h <= 0 || w <= 0 || cout <= 0 || cout % 32 != 0 || P % 32 != 0 || M % BLOCK_M != 0) return 0;
+  const int bn = conv_block_n(cout);
+  if (cout % bn != 0) return 0;  // cout_pad == cout
+  const int be = effective_block_n(M, cout, cout);
+  return (be >= 64 && cout % be == 0) ? 1 : 0;
+}
 
 int conv_igemm_submit(adb_plan* plan, const adb_conv_desc* d, cudaStream_t stream) {
   ADB_REQUIRE(d != nullptr, "conv_igemm: null descriptor");
@@ -874,10 +978,7 @@ int conv_igemm_submit(adb_plan* plan, const adb_conv_desc* d, cudaStream_t strea
     }
     if (r != ADB_OK) return r;
   }
-  int block_n = conv_block_n(d->cout);
-  // the 256-wide pair tile pays once there is at least one wave of them; small problems keep the 128-wide tile
-  // (cout_pad is a multiple of 256, hence of 128 as well)
-  if (block_n == 256 && ((M + 2 * BLOCK_M - 1) / (2 * BLOCK_M)) * (d->cout_pad / 256) < num_sms() / 2) block_n = 128;
+  const int block_n = effective_block_n(M, d->cout, d->cout_pad);
   const int ncta = conv_ncta(block_n);
   ADB_REQUIRE(d->cout_pad % block_n == 0, "conv_igemm: cout_pad (%d) must be a multiple of the N tile %d (adb_conv_block_n)", d->cout_pad, block_n);
   {
@@ -939,8 +1040,45 @@ int conv_igemm_submit(adb_plan* plan, const adb_conv_desc* d, cudaStream_t strea
                 "conv_igemm: stats_out needs bf16 output, cout %% 32 == 0 and h*w %% 32 == 0");
   }
 
+  if (d->gnb_bstats != nullptr) {
+    // GroupNorm-backward sums in the epilogue: only on the all-TMA epilogue path (full tiles, one image per 32-row slab)
+    ADB_REQUIRE(d->gnb_x && d->gnb_stats && d->gnb_gamma && d->gnb_beta, "conv_igemm: gnb needs x, stats, gamma and beta");
+    ADB_REQUIRE(kp.tma_epi && d->res_mode == ADB_RES_NONE && d->stats_out == nullptr && d->stats2_out == nullptr &&
+                    M % BLOCK_M == 0 && P % 32 == 0 && d->cout % 32 == 0 && d->cout_pad == d->cout && d->cout % block_n == 0 &&
+                    block_n >= 64,
+                "conv_igemm: gnb needs bf16 output without residual or forward statistics, full tiles (n*h*w %% 128 == 0, "
+                "cout %% N tile == 0) and h*w %% 32 == 0");
+    const uint64_t dims[2] = {(uint64_t)d->cout, (uint64_t)M};
+    const uint64_t strides[1] = {(uint64_t)d->cout * 2};
+    const uint32_t box[2] = {32u, 32u};
+    int r = make_tmap_bf16(&kp.tmRes, d->gnb_x, 2, dims, strides, box, 64);
+    if (r != ADB_OK) return r;
+    kp.res_mode = ADB_RES_SAME;
+    kp.gnb = 1;
+    kp.gnb_inv_cnt = 1.0 / ((double)(d->cout / 32) * (double)P);
+    kp.stats = d->gnb_bstats;
+    kp.gnb_stats = d->gnb_stats;
+    kp.gnb_gamma = d->gnb_gamma;
+    kp.gnb_beta = d->gnb_beta;
+    kp.gnb_ss = d->gnb_scale_shift;
+    kp.gnb_ss_stride = d->gnb_ss_stride;
+    kp.gnb_eps = d->gnb_eps;
+    kp.gnb_silu = d->gnb_silu;
+  }
+
   const double flops = 2.0 * (double)M * (double)d->cout * (double)ktot;
-  return submit(plan, stream, "conv_igemm", flops, 0.0, [kp, block_n, ncta](cudaStream_t s) -> int {
+  const size_t gnb_bytes = kp.gnb ? (size_t)d->n * 32 * 2 * sizeof(double) : 0;
+  return submit(plan, stream, "conv_igemm", flops, 0.0, [kp, block_n, ncta, gnb_bytes](cudaStream_t s) -> int {
+    if (gnb_bytes) {
+      ADB_CUDA(cudaMemsetAsync(kp.stats, 0, gnb_bytes, s));
+      switch (block_n) {
+        case 256: return launch<256, 2, true>(kp, s);
+        case 192: return ncta == 2 ? launch<192, 2, true>(kp, s) : launch<192, 1, true>(kp, s);
+        case 160: return launch<160, 2, true>(kp, s);
+        case 128: return launch<128, 1, true>(kp, s);
+        default: return launch<64, 1, true>(kp, s);
+      }
+    }
     switch (block_n) {
       case 256: return launch<256, 2>(kp, s);
       case 192: return ncta == 2 ? launch<192, 2>(kp, s) : launch<192, 1>(kp, s);

@@ -141,6 +141,7 @@ int make_tmap_f32(CUtensorMap* out, const void* base, int rank, const uint64_t* 
 
 // implemented in the kernel translation units
 int conv_block_n(int cout);
+int conv_gnb_supported(int n, int h, int w, int cout);
 int conv_igemm_submit(adb_plan*, const adb_conv_desc*, cudaStream_t);
 int attention_submit(adb_plan*, const void*, void*, float*, int, int, int, int, cudaStream_t);
 int attention_backward_submit(adb_plan*, const void*, const void*, const void*, const float*, float*, void*, float*, int, int,
@@ -269,6 +270,7 @@ int adb_plan_run_profiled(adb_plan* plan, adb_stream stream, float* ms_out, int 
 }
 
 int adb_conv_block_n(int cout) { return conv_block_n(cout); }
+int adb_conv_gnb_supported(int n, int h, int w, int cout) { return conv_gnb_supported(n, h, w, cout); }
 
 int adb_conv_igemm(adb_plan* plan, const adb_conv_desc* d, adb_stream stream) {
   return conv_igemm_submit(plan, d, static_cast<cudaStream_t>(stream));

@@ -153,10 +153,14 @@ def conv_igemm(
     plan: Optional[Plan] = None,
     stats_out: Optional[torch.Tensor] = None,
     stats2: Optional[tuple] = None,
+    gnb: Optional[dict] = None,
 ) -> torch.Tensor:
     """segs: [(act[n,h,w,cin] bf16, taps), ...]; weight from `pack_conv_weight`.
     stats_out: optional zeroed fp64 [n,32,2]; the epilogue adds the output's GroupNorm sums to it.
-    stats2: optional (fp64 [n,32,2], cpg, channel offset) - sums for a consumer GroupNorm over a concat."""
+    stats2: optional (fp64 [n,32,2], cpg, channel offset) - sums for a consumer GroupNorm over a concat.
+    gnb: this conv is a data gradient consumed by `gn_backward` of the GroupNorm described by the dict (keys x, stats,
+      gamma, beta, bstats and optionally scale_shift, ss_stride, eps, silu - the arguments of `gn_backward`): the epilogue
+      reduces that backward's two per-(image, group) sums into `bstats`; call `gn_backward(..., bstats_ready=True)`."""
     act0 = segs[0][0]
     s0 = segs[0][2] if len(segs[0]) > 2 else 1  # a third tuple entry is the segment's stride (1 or 2)
     n, h, w = act0.shape[0], act0.shape[1] // s0, act0.shape[2] // s0
@@ -198,10 +202,34 @@ def conv_igemm(
     if stats2 is not None:
         d.stats2_out = _dev(stats2[0], "stats2", torch.float64)
         d.stats2_cpg, d.stats2_choff = int(stats2[1]), int(stats2[2])
+    gnb_keep = ()
+    if gnb is not None:
+        gx = gnb["x"]
+        assert tuple(gx.shape) == (n, h, w, cout), f"gnb x shape {tuple(gx.shape)} != {(n, h, w, cout)}"
+        d.gnb_x = _dev(gx, "gnb.x", torch.bfloat16)
+        d.gnb_stats = _dev(gnb["stats"], "gnb.stats", torch.float64)
+        d.gnb_gamma = _dev(gnb["gamma"], "gnb.gamma", torch.float32)
+        d.gnb_beta = _dev(gnb["beta"], "gnb.beta", torch.float32)
+        ss = gnb.get("scale_shift")
+        if isinstance(ss, tuple):
+            d.gnb_scale_shift = _dev(ss[0], "gnb.scale_shift", torch.float32) + 4 * int(ss[1])
+            ss = ss[0]
+        else:
+            d.gnb_scale_shift = _opt(ss, "gnb.scale_shift", torch.float32)
+        d.gnb_ss_stride = int(gnb.get("ss_stride", 0))
+        d.gnb_eps = float(gnb.get("eps", 1e-5))
+        d.gnb_silu = int(bool(gnb.get("silu", True)))
+        d.gnb_bstats = _dev(gnb["bstats"], "gnb.bstats", torch.float64)
+        gnb_keep = (gx, gnb["stats"], gnb["gamma"], gnb["beta"], ss, gnb["bstats"])
     _lib.check(_lib.lib().adb_conv_igemm(_ph(plan), C.byref(d), _stream()), "adb_conv_igemm")
     if plan is not None:
-        plan.keep(*[s[0] for s in segs], weight, bias, residual, out, stats_out, stats2[0] if stats2 else None)
+        plan.keep(*[s[0] for s in segs], weight, bias, residual, out, stats_out, stats2[0] if stats2 else None, *gnb_keep)
     return out
+
+
+def conv_gnb_supported(n: int, h: int, w: int, cout: int) -> bool:
+    """Whether `conv_igemm(..., gnb=...)` accepts an [n,h,w,cout] output (full tiles on the all-TMA epilogue)."""
+    return bool(_lib.lib().adb_conv_gnb_supported(int(n), int(h), int(w), int(cout)))
 
 
 def attention(qkv: torch.Tensor, b: int, t: int, heads: int, legacy_order: bool,
@@ -271,8 +299,10 @@ def gn_backward(x: torch.Tensor, stats: torch.Tensor, gamma: torch.Tensor, beta:
                 scale_shift=None, ss_stride: int = 0, silu: bool = True, resample: int = RESAMPLE_NONE,
                 add: Optional[torch.Tensor] = None, add_mode: int = RES_NONE, eps: float = 1e-5,
                 dx: Optional[torch.Tensor] = None, bstats: Optional[torch.Tensor] = None,
-                plan: Optional[Plan] = None) -> torch.Tensor:
-    """Gradient of `groupnorm` (single source) w.r.t. its input x [n,h,w,c]; `stats` are the forward sums of x."""
+                plan: Optional[Plan] = None, bstats_ready: bool = False) -> torch.Tensor:
+    """Gradient of `groupnorm` (single source) w.r.t. its input x [n,h,w,c]; `stats` are the forward sums of x.
+    bstats_ready: `bstats` already holds the two backward sums (`conv_igemm(..., gnb=...)` produced `dout`), so x and
+    dout are read once instead of twice."""
     n, h, w, c = x.shape
     if dx is None:
         dx = torch.empty_like(x)
@@ -305,6 +335,9 @@ def gn_backward(x: torch.Tensor, stats: torch.Tensor, gamma: torch.Tensor, beta:
         assert tuple(add.shape) == exp, f"add shape {tuple(add.shape)} != {exp}"
     d.dx = _dev(dx, "dx", torch.bfloat16)
     d.bstats = _dev(bstats, "bstats", torch.float64)
+    d.bstats_ready = int(bool(bstats_ready))
+    if bstats_ready and resample != RESAMPLE_NONE:
+        raise ValueError("gn_backward: bstats_ready needs dout at x's resolution")
     _lib.check(_lib.lib().adb_gn_backward(_ph(plan), C.byref(d), _stream()), "adb_gn_backward")
     if plan is not None:
         plan.keep(x, stats, gamma, beta, ss_base, dout, add, dx, bstats)

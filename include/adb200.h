@@ -101,10 +101,26 @@ typedef struct {
   int seg_stride[3];    /* 0 or 1: unit stride. 2: segment s is a 3x3 stride-2 pad-1 convolution (Downsample.op,
                            openaimodel.py:147-149): its `act` is [n, 2h, 2w, cin], output pixel (y, x) reads input
                            rows 2y-1..2y+1, columns 2x-1..2x+1 */
+  /* ---- appended for classifier guidance: this conv is a DATA GRADIENT whose output dY feeds adb_gn_backward of a
+   * GroupNorm with forward input gnb_x [n,h,w,cout]. With gnb_x != NULL the epilogue also reduces that backward's two
+   * sums per (image, group) - sum dxh and sum dxh*xh with xh = (x - mean) rstd, dxh = dY act'(z) gamma (1+scale) - into
+   * gnb_bstats (zeroed here), so that adb_gn_backward (bstats_ready = 1) reads x and dY once instead of twice.
+   * Requires bf16 output, no residual, n*h*w % 128 == 0, h*w % 32 == 0, cout % adb_conv_block_n(cout) == 0. ---- */
+  const void* gnb_x;           /* bf16 NHWC [n,h,w,cout] or NULL */
+  const double* gnb_stats;     /* forward sums of gnb_x [n,32,2] */
+  const float* gnb_gamma;      /* [cout] */
+  const float* gnb_beta;       /* [cout] */
+  const float* gnb_scale_shift; /* optional FiLM rows (scale | shift), row stride gnb_ss_stride floats */
+  int gnb_ss_stride;
+  float gnb_eps;
+  int gnb_silu;
+  double* gnb_bstats;          /* out [n,32,2] */
 } adb_conv_desc;
 
 /* N tile the kernel uses for `cout` output channels; `cout_pad` must be a multiple of it. */
 int adb_conv_block_n(int cout);
+/* 1 when adb_conv_igemm accepts gnb_* for an [n,h,w,cout] output (full tiles on the all-TMA epilogue), else 0 */
+int adb_conv_gnb_supported(int n, int h, int w, int cout);
 int adb_conv_igemm(adb_plan* plan, const adb_conv_desc* d, adb_stream stream);
 
 /* ---- fused softmax attention, head dim 64 ----
@@ -246,7 +262,8 @@ typedef struct {
   int add_mode;             /* ADB_RES_NONE; ADB_RES_SAME: add is [n,h,w,c]; ADB_RES_AVGPOOL2: the skip path
                                average-pooled x, add is [n,h/2,w/2,c] and contributes add/4 */
   void* dx;                 /* bf16 NHWC [n,h,w,c] */
-  double* bstats;           /* scratch [n,32,2] */
+  double* bstats;           /* scratch [n,32,2]; with bstats_ready: the sums, already reduced by the producing conv */
+  int bstats_ready;         /* 1: bstats was filled by adb_conv_igemm (gnb_*): only the apply pass runs */
 } adb_gn_bwd_desc;
 int adb_gn_backward(adb_plan* plan, const adb_gn_bwd_desc* d, adb_stream stream);
 

@@ -91,6 +91,61 @@ def test_gn_backward(n, res, c, variant):
     _check(_nchw(dx), ref, 2 ** -6, f"gn_backward {variant} n{n} r{res} c{c}")
 
 
+@pytest.mark.parametrize("n,res,cin,cout,taps,variant", [
+    (4, 16, 128, 256, 9, "film"),     # two-CTA 256-wide tile or its 128-wide fallback
+    (2, 8, 512, 512, 9, "silu"),      # 64-pixel images: two images per 128-row tile
+    (2, 32, 192, 192, 1, "plain"),    # attention block: 1x1 data gradient, no SiLU
+    (3, 32, 256, 128, 9, "silu"),     # odd image count (n*h*w % 128 == 0 still)
+    (8, 16, 384, 384, 9, "film"),
+])
+def test_conv_fused_gn_backward_sums(n, res, cin, cout, taps, variant):
+    """conv_igemm(gnb=...): the data-gradient conv's epilogue reduces sum(dxh) and sum(dxh * xh) of the consumer
+    GroupNorm's backward; they must equal the sums gn_backward's own first pass computes from the stored bf16 gradient,
+    and dx from the single-pass form (bstats_ready) must match the two-pass one."""
+    ops = _ops()
+    assert ops.conv_gnb_supported(n, res, res, cout)
+    x = _nhwc(_bf(_rand((n, cout, res, res), 60, 2.0) + 0.5))
+    g = (1 + 0.1 * _rand((cout,), 61)).to(DEV)
+    bt = (0.1 * _rand((cout,), 62)).to(DEV)
+    kw = dict(silu=variant != "plain")
+    if variant == "film":
+        kw.update(scale_shift=(0.3 * _rand((n, 2 * cout + 8), 63)).to(DEV), ss_stride=2 * cout + 8)
+    stats = torch.empty((n, 32, 2), dtype=torch.float64, device=DEV)
+    ops.groupnorm(x, g, bt, stats=stats, **kw)
+    k = 3 if taps == 9 else 1
+    w = _rand((cout, cin, k, k), 64, 1.0 / math.sqrt(cin * taps))
+    wp = ops.pack_conv_weight([w], DEV)
+    dy_in = _nhwc(_bf(_rand((n, cin, res, res), 65)))
+    # reference: plain conv, then the two-pass backward (its first pass leaves the sums in bstats)
+    dg_ref = ops.conv_igemm([(dy_in, taps)], wp, None, cout)
+    b_ref = torch.empty((n, 32, 2), dtype=torch.float64, device=DEV)
+    dx_ref = ops.gn_backward(x, stats, g, bt, dg_ref, bstats=b_ref, **kw)
+    # fused
+    b_f = torch.full((n, 32, 2), 123.0, dtype=torch.float64, device=DEV)  # the conv zeroes it itself
+    dg = ops.conv_igemm([(dy_in, taps)], wp, None, cout, gnb=dict(x=x, stats=stats, gamma=g, beta=bt, bstats=b_f, **kw))
+    dx = ops.gn_backward(x, stats, g, bt, dg, bstats=b_f, bstats_ready=True, **kw)
+    torch.cuda.synchronize()
+    assert torch.equal(dg, dg_ref), "gnb must not change the conv's output"
+    scale = b_ref.abs().max().item()
+    err = (b_f - b_ref).abs().max().item()
+    assert err <= 2e-5 * max(scale, 1.0), f"fused GroupNorm-backward sums off by {err} (scale {scale})"
+    d = (dx.float() - dx_ref.float()).abs().max().item()
+    assert d <= 2 ** -7 * dx_ref.float().abs().max().item(), f"dx differs by {d}"
+    # every argument check the header states
+    with pytest.raises(Exception):
+        ops.conv_igemm([(dy_in, taps)], wp, None, cout, residual=x, res_mode=ops.RES_SAME,
+                       gnb=dict(x=x, stats=stats, gamma=g, beta=bt, bstats=b_f, **kw))
+
+
+def test_conv_gnb_supported_shapes():
+    ops = _ops()
+    assert not ops.conv_gnb_supported(1, 8, 8, 512)      # 64 rows: not a full tile
+    assert not ops.conv_gnb_supported(2, 4, 4, 512)      # 16 pixels per image
+    assert not ops.conv_gnb_supported(4, 16, 16, 48)     # cout % 32
+    assert ops.conv_gnb_supported(256, 64, 64, 128)
+    assert ops.conv_gnb_supported(256, 8, 8, 512)
+
+
 @pytest.mark.parametrize("b,t,heads", [(2, 64, 8), (2, 256, 6), (1, 1024, 4), (3, 64, 2), (2, 128, 3)])
 @pytest.mark.parametrize("legacy", [True, False])
 @pytest.mark.parametrize("fused", [False, True])

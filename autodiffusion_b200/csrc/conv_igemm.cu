@@ -1068,7 +1068,8 @@ int conv_igemm_submit(adb_plan* plan, const adb_conv_desc* d, cudaStream_t strea
 
   const double flops = 2.0 * (double)M * (double)d->cout * (double)ktot;
   const size_t gnb_bytes = kp.gnb ? (size_t)d->n * 32 * 2 * sizeof(double) : 0;
-  return submit(plan, stream, "conv_igemm", flops, 0.0, [kp, block_n, ncta, gnb_bytes](cudaStream_t s) -> int {
+  // the GNB instantiation is reported under its own name: its epilogue carries the consumer GroupNorm's backward sums
+  return submit(plan, stream, kp.gnb ? "conv_igemm_gnb" : "conv_igemm", flops, 0.0, [kp, block_n, ncta, gnb_bytes](cudaStream_t s) -> int {
     if (gnb_bytes) {
       ADB_CUDA(cudaMemsetAsync(kp.stats, 0, gnb_bytes, s));
       switch (block_n) {

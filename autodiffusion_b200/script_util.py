@@ -2,6 +2,11 @@
 
 Same defaults dicts, same keyword names, same channel_mult / attention_ds derivation
 (script_util.py:43-66, 75-211, 415-481); the objects returned are the B200-native ones.
+
+Provenance: the flag schema below (the `*_defaults()` dictionaries, the keyword names and order of the `create_*`
+factories, `add_dict_to_argparser` / `args_to_dict` / `str2bool`) is the public interface of OpenAI's guided-diffusion
+`script_util.py` (MIT licence), which the reference vendors; a drop-in has to reproduce it name for name, so those
+parts necessarily read like the original. Everything the factories construct is this repository's own code.
 """
 import argparse
 

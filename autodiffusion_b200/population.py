@@ -84,14 +84,28 @@ def run_population(model, diffusion, cond_fn, n_candidates: int, num_samples: in
         assert th.equal(f, f0), "ranks disagree on the population's FIDs"
         ar = th.tensor([max(info["allreduce_ms"]) if info["allreduce_ms"] else 0.0], device=dev, dtype=th.float64)
         dist.all_reduce(ar, op=dist.ReduceOp.MAX)
-        info["allreduce_ms"] = float(ar.item())
+        info["allreduce_ms"] = float(ar.item())  # the first tail all-reduce also absorbs the ranks' arrival skew
+        # the collective alone: the same 33.6 MB fp64 buffer, every rank released by a barrier just before
+        from .evaluator import MomentAccumulator
+
+        probe = MomentAccumulator(ref_dim, dev)
+        barrier()
+        e0, e1 = th.cuda.Event(enable_timing=True), th.cuda.Event(enable_timing=True)
+        e0.record()
+        probe.all_reduce()
+        e1.record()
+        th.cuda.synchronize()
+        pure = th.tensor([e0.elapsed_time(e1)], device=dev, dtype=th.float64)
+        dist.all_reduce(pure, op=dist.ReduceOp.MAX)
+        info["allreduce_alone_ms"] = float(pure.item())
     else:
         info["allreduce_ms"] = 0.0
+        info["allreduce_alone_ms"] = 0.0
     n = len(population)
     return {
         "candidates": n, "num_samples": num_samples, "batch_size": batch_size, "n_gpus": world,
         "candidates_per_s": n / wall, "images_per_s": n * num_samples / wall, "wall_s": wall,
-        "allreduce_ms": info["allreduce_ms"], "plan_build_s": {"first": round(info["plan_build_first_s"], 3),
+        "allreduce_ms": info["allreduce_ms"], "allreduce_alone_ms": round(info["allreduce_alone_ms"], 3), "plan_build_s": {"first": round(info["plan_build_first_s"], 3),
                                                                "overlapped_total_max_rank": round(info["plan_build_overlapped_s"], 3)},
         "schedule": {"whole_per_rank": info["whole_per_rank"], "batch_sharded_tail": info["shared"]},
         "fid_method": fid_method, "feature_dim": ref_dim, "guided": cond_fn is not None,

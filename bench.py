@@ -384,7 +384,9 @@ def run_ours(args):
             # 8 GPUs: BASELINE configs[2]'s 50 candidates (48 whole + 2 batch-sharded); fewer ranks: 6 per rank + 1, so that
             # the batch-sharded tail and its NCCL moment all-reduce are exercised at every N > 1 within the same ~30 s
             n_c = args.pop_candidates or (50 if world == 8 else 6 * world + 1)
-            pop = run_population(model, diffusion, None if args.unet_only else guidance, n_c, num_samples=1000, batch_size=B,
+            # batches that divide the 1000 samples (250 at the default 256): no partly used last batch
+            pb = max(b for b in range(1, B + 1) if 1000 % b == 0)
+            pop = run_population(model, diffusion, None if args.unet_only else guidance, n_c, num_samples=1000, batch_size=pb,
                                  fid_method="eigh")
             pop.pop("fids")
             pop["vs_sampling_rate"] = pop["images_per_s"] / (B * world * args.steps / (ms * 1e-3))

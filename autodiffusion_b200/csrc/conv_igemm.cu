@@ -390,10 +390,10 @@ conv_igemm_kernel(const __grid_constant__ ConvKParams p) {
         for (int ci = 0; ci < nch; ++ci) {
           const int c = cbeg + ci * CHUNK_COLS;
           const int col0 = n0 + c;
-          // gnb: this chunk's column coefficients were requested one chunk ago; request the next chunk's now
+          // gnb: this chunk's column coefficients were requested one chunk ago (the next chunk's are requested after the
+          // staging fence below - a membar would wait for them)
           const double g_sum = gn.sum, g_sq = gn.sq;
           const float g_ga = gn.ga, g_be = gn.be, g_sc = gn.sc, g_sh = gn.sh;
-          if (GNB && ci + 1 < nch) gnb_fetch(col0 + CHUNK_COLS);
           uint32_t v[32];
           tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * BLOCK_N + c, v);
           float4 bv[8];
@@ -458,6 +458,7 @@ conv_igemm_kernel(const __grid_constant__ ConvKParams p) {
             tma_store_2d(&p.tmOut, epi_out, col0, row0f);
             tma_store_commit();
           }
+          if (GNB && ci + 1 < nch) gnb_fetch(col0 + CHUNK_COLS);
           if (p.stats != nullptr) {
             // column sums of the STORED values: lane j walks column j down the staged tile's 32 rows
             float cs = 0.f, cq = 0.f;

@@ -132,3 +132,18 @@ def test_config1_full_admg64_with_native_classifier():
           f"{d8.max()} LSB, within 1 LSB: {(d8 <= 1).mean() * 100:.1f}%; kernels per candidate: {plan.launches}")
     assert p >= 44.0  # measured 47.1 dB
     assert d8.mean() <= 0.45 and (d8 <= 1).mean() >= 0.90  # measured 93.7 % within 1 LSB
+    # the plan above runs the guidance on a second stream beside the UNet forward (sampler._run_chain); the single-stream
+    # order must give the same bits
+    import os
+
+    prev = os.environ.get("ADB_CONCURRENT_GUIDANCE")
+    os.environ["ADB_CONCURRENT_GUIDANCE"] = "0"
+    try:
+        seq = SchedulePlan(model, active, per_step, 8, cond_fn=ClassifierGuidance(clf, 1.0), pack_uint8=True)
+        out_seq = seq.run(noise, y).clone().cpu()
+    finally:
+        if prev is None:
+            os.environ.pop("ADB_CONCURRENT_GUIDANCE")
+        else:
+            os.environ["ADB_CONCURRENT_GUIDANCE"] = prev
+    assert torch.equal(out, out_seq), "two-stream and single-stream schedules differ"

@@ -202,17 +202,24 @@ __global__ void __launch_bounds__(AT_THREADS, 2) attention2_kernel(const __grid_
         }
       }
       // p = exp2(s*sc - m_new) (one FFMA + one MUFU per element), row sum; bf16 P packed in place
-      float ps[8];
+      // The scale-subtract and the eight row-sum chains run on packed pairs (FFMA2 / FADD2: one issue slot per two
+      // scores); same roundings and the same summation order as the scalar form.
+      const uint64_t sc2 = f32x2_pack(sc, sc), nm2 = f32x2_pack(-m_new, -m_new);
+      uint64_t ps2[4];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) ps[i] = 0.f;
+      for (int i = 0; i < 4; ++i) ps2[i] = f32x2_pack(0.f, 0.f);
 #pragma unroll
       for (int i = 0; i < KT / 2; ++i) {
-        const float p0 = ex2_approx(fmaf(__uint_as_float(sr[2 * i]), sc, -m_new));
-        const float p1 = ex2_approx(fmaf(__uint_as_float(sr[2 * i + 1]), sc, -m_new));
-        ps[(2 * i) & 7] += p0;
-        ps[(2 * i + 1) & 7] += p1;
+        float x0, x1;
+        f32x2_unpack(f32x2_fma(f32x2_pack(__uint_as_float(sr[2 * i]), __uint_as_float(sr[2 * i + 1])), sc2, nm2), x0, x1);
+        const float p0 = ex2_approx(x0);
+        const float p1 = ex2_approx(x1);
+        ps2[i & 3] = f32x2_add(ps2[i & 3], f32x2_pack(p0, p1));
         sr[i] = pack_bf16x2(p0, p1);
       }
+      float ps[8];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) f32x2_unpack(ps2[i], ps[2 * i], ps[2 * i + 1]);
       const float ps0 = (ps[0] + ps[1]) + (ps[2] + ps[3]);
       const float ps1 = (ps[4] + ps[5]) + (ps[6] + ps[7]);
       // P_j overwrites the head of S_j (all of S_j is in registers by now)

@@ -166,6 +166,7 @@ __global__ void __launch_bounds__(BW_THREADS, 2) attn_bwd_dq_kernel(const __grid
     // dS carries the s^2 = 1/8 of d(scores)/d(q.k): folded into the exponent (2^-3)
     const float L = ok ? (p.lse[(size_t)bh * p.T + q0 + row] + 3.0f) : 0.f;
     const float Dr = ok ? p.dsum[(size_t)bh * p.T + q0 + row] : 0.f;
+    const uint64_t sc2 = f32x2_pack(sc, sc), nL2 = f32x2_pack(-L, -L), nD2 = f32x2_pack(-Dr, -Dr);
     for (int j = 0; j < nt; ++j) {
       mbar_wait(bar(B_SP), (uint32_t)j & 1u);
       tc_fence_after();
@@ -176,11 +177,16 @@ __global__ void __launch_bounds__(BW_THREADS, 2) attn_bwd_dq_kernel(const __grid
         tmem_ld_32x32b_x32(lane_addr + hf * 32, sv);
         tmem_ld_32x32b_x32(lane_addr + TN + hf * 32, dp);
         tmem_wait_ld();
+        // packed pairs (FFMA2 / FADD2 / FMUL2: one issue slot per two scores), same roundings as the scalar form
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
-          const float p0 = ex2_approx(fmaf(__uint_as_float(sv[2 * i]), sc, -L));
-          const float p1 = ex2_approx(fmaf(__uint_as_float(sv[2 * i + 1]), sc, -L));
-          ds[hf * 16 + i] = pack_bf16x2(p0 * (__uint_as_float(dp[2 * i]) - Dr), p1 * (__uint_as_float(dp[2 * i + 1]) - Dr));
+          float x0, x1, d0, d1;
+          f32x2_unpack(f32x2_fma(f32x2_pack(__uint_as_float(sv[2 * i]), __uint_as_float(sv[2 * i + 1])), sc2, nL2), x0, x1);
+          const float p0 = ex2_approx(x0);
+          const float p1 = ex2_approx(x1);
+          const uint64_t e2 = f32x2_add(f32x2_pack(__uint_as_float(dp[2 * i]), __uint_as_float(dp[2 * i + 1])), nD2);
+          f32x2_unpack(f32x2_mul(f32x2_pack(p0, p1), e2), d0, d1);
+          ds[hf * 16 + i] = pack_bf16x2(d0, d1);
         }
       }
       tmem_st_32x32b_x32(lane_addr, ds);
@@ -322,6 +328,7 @@ __global__ void __launch_bounds__(BW_THREADS, 2) attn_bwd_dkv_kernel(const __gri
     const bool ok = (k0 + row) < p.T;
     const uint32_t lane_addr = tmem_base + ((uint32_t)(quarter * 32) << 16);
     const float sc = 0.125f * 1.4426950408889634f;
+    const uint64_t sc2 = f32x2_pack(sc, sc), eighth2 = f32x2_pack(0.125f, 0.125f);
     for (int i = 0; i < nt; ++i) {
       const int st = i % STAGES;
       mbar_wait(bar(B_FULL + st), (uint32_t)(i / STAGES) & 1u);  // lse / D of tile i visible to this thread
@@ -338,11 +345,17 @@ __global__ void __launch_bounds__(BW_THREADS, 2) attn_bwd_dkv_kernel(const __gri
         for (int c = 0; c < 16; ++c) {
           const float2 l2 = *reinterpret_cast<const float2*>(&lse_s[st][hf * 32 + 2 * c]);
           const float2 d2 = *reinterpret_cast<const float2*>(&dsum_s[st][hf * 32 + 2 * c]);
-          const float p0 = ex2_approx(fmaf(__uint_as_float(sv[2 * c]), sc, -l2.x));
-          const float p1 = ex2_approx(fmaf(__uint_as_float(sv[2 * c + 1]), sc, -l2.y));
+          // packed pairs (FFMA2 / FADD2 / FMUL2), same roundings as the scalar form (the 1/8 is exact)
+          float x0, x1, d0, d1;
+          f32x2_unpack(f32x2_fma(f32x2_pack(__uint_as_float(sv[2 * c]), __uint_as_float(sv[2 * c + 1])), sc2,
+                                 f32x2_pack(-l2.x, -l2.y)), x0, x1);
+          const float p0 = ex2_approx(x0);
+          const float p1 = ex2_approx(x1);
           pt[hf * 16 + c] = pack_bf16x2(p0, p1);
-          ds[hf * 16 + c] = pack_bf16x2(0.125f * p0 * (__uint_as_float(dp[2 * c]) - d2.x),
-                                        0.125f * p1 * (__uint_as_float(dp[2 * c + 1]) - d2.y));
+          const uint64_t e2 = f32x2_add(f32x2_pack(__uint_as_float(dp[2 * c]), __uint_as_float(dp[2 * c + 1])),
+                                        f32x2_pack(-d2.x, -d2.y));
+          f32x2_unpack(f32x2_mul(f32x2_mul(f32x2_pack(p0, p1), eighth2), e2), d0, d1);
+          ds[hf * 16 + c] = pack_bf16x2(d0, d1);
         }
       }
       tmem_st_32x32b_x32(lane_addr, pt);

@@ -266,11 +266,17 @@ __global__ void __launch_bounds__(FB_THREADS, 1) attn_bwd_fused_kernel(const __g
         for (int c = 0; c < 16; ++c) {
           const float2 l2 = *reinterpret_cast<const float2*>(&lse_s[st][hf * 32 + 2 * c]);
           const float2 d2 = *reinterpret_cast<const float2*>(&dsum_s[st][hf * 32 + 2 * c]);
-          const float p0 = ex2_approx(fmaf(__uint_as_float(sv[2 * c]), sc, -l2.x));
-          const float p1 = ex2_approx(fmaf(__uint_as_float(sv[2 * c + 1]), sc, -l2.y));
+          // packed pairs (FFMA2 / FADD2 / FMUL2), same roundings as the scalar form (the 1/8 is exact)
+          float x0, x1, d0, d1;
+          f32x2_unpack(f32x2_fma(f32x2_pack(__uint_as_float(sv[2 * c]), __uint_as_float(sv[2 * c + 1])), f32x2_pack(sc, sc),
+                                 f32x2_pack(-l2.x, -l2.y)), x0, x1);
+          const float p0 = ex2_approx(x0);
+          const float p1 = ex2_approx(x1);
           pt[hf * 16 + c] = pack_bf16x2(p0, p1);
-          ds[hf * 16 + c] = pack_bf16x2(0.125f * p0 * (__uint_as_float(dp[2 * c]) - d2.x),
-                                        0.125f * p1 * (__uint_as_float(dp[2 * c + 1]) - d2.y));
+          const uint64_t e2 = f32x2_add(f32x2_pack(__uint_as_float(dp[2 * c]), __uint_as_float(dp[2 * c + 1])),
+                                        f32x2_pack(-d2.x, -d2.y));
+          f32x2_unpack(f32x2_mul(f32x2_mul(f32x2_pack(p0, p1), f32x2_pack(0.125f, 0.125f)), e2), d0, d1);
+          ds[hf * 16 + c] = pack_bf16x2(d0, d1);
         }
       }
       tmem_st_32x32b_x32(buf_addr + C_S, pt);

@@ -69,6 +69,7 @@ struct ConvKParams {
   unsigned long long cpg_magic, cpg2_magic;
   // GroupNorm-backward sums mode (adb_conv_desc.gnb_*): this conv is a data gradient dY; tmRes then maps the consumer
   // GroupNorm's forward input x, `stats` is the target of sum dxh / sum dxh*xh, and nothing is added to the output.
+  int b_one_box;  // 256-wide pair tile: the CTA's 128 weight rows are ONE TMA box (default; ADB_CONV_B128BOX=0: two 64-row boxes)
   int gnb;
   double gnb_inv_cnt;  // 1 / (channels per group * pixels per image)
   const double* gnb_stats;
@@ -214,7 +215,7 @@ conv_igemm_kernel(const __grid_constant__ ConvKParams p) {
                 else mbar_arrive_cluster(lead_full);
                 if (S2) tma_load_5d_2sm(a_dst, &p.tmA[s], lead_full, pxc + ch * BLOCK_K, x0 + sx, py, y0 + sy, img);
                 else tma_load_4d_2sm(a_dst, &p.tmA[s], lead_full, ch * BLOCK_K, x0 + dx, y0 + dy, img);
-                if (BLOCK_N == 256) {  // two 64-row boxes
+                if (BLOCK_N == 256 && !p.b_one_box) {  // two 64-row boxes
                   tma_load_2d_2sm(b_dst, &p.tmW, lead_full, kb + ch * BLOCK_K, n_tile * BLOCK_N + (int)cta_rank * 128);
                   tma_load_2d_2sm(b_dst + 8192, &p.tmW, lead_full, kb + ch * BLOCK_K, n_tile * BLOCK_N + (int)cta_rank * 128 + 64);
                 } else {
@@ -890,9 +891,12 @@ namespace {
 
 // CTA pairs (cta_group::2) for the 192- and 256-wide N tiles unless ADB_CONV_1CTA=1 (A/B testing).
 // Measured: a 128-wide pair tile is ~18 % SLOWER than the single-CTA 128 tile (the pair's handshakes buy only
-// 8 KB less B traffic per stage). The 256-wide pair tile needs its B half (128 weight rows) fetched as TWO
-// 64-row boxes: a single cta_group::2 TMA box of 112 or 128 rows never completed its mbarrier transaction once a
-// second stage or cluster was in flight (96 rows, the 192-wide tile, is fine) - independent of the barrier protocol.
+// 8 KB less B traffic per stage). Round 1 fetched the 256-wide pair tile's B half (128 weight rows) as TWO
+// 64-row boxes because a single cta_group::2 box of 112 or 128 rows "never completed its mbarrier transaction" in the
+// kernel of that time. Chased in round 2: scripts/microbench/tma_2sm_box_rows.cu runs the same ring protocol stand-alone
+// (64 / 96 / 112 / 128-row boxes, 1-4 stages, 1 or 74 clusters) and every load completes; with the present kernel the
+// single box passes the parity tests and is 3 % faster (1490 -> 1531 TFLOP/s at 32x32 256 -> 256), so it is the default now
+// (ADB_CONV_B128BOX=0 restores the two boxes). The round-1 stall came from that version's barrier protocol, not from TMA.
 int conv_ncta(int block_n) {
   static int force1 = -1;
   if (force1 < 0) {
@@ -985,7 +989,13 @@ int conv_igemm_submit(adb_plan* plan, const adb_conv_desc* d, cudaStream_t strea
   {
     const uint64_t dims[2] = {(uint64_t)ktot, (uint64_t)d->cout_pad};
     const uint64_t strides[1] = {(uint64_t)ktot * 2};
-    const uint32_t box[2] = {(uint32_t)BLOCK_K, (uint32_t)(block_n == 256 ? 64 : block_n / ncta)};
+    static int b128 = -1;
+    if (b128 < 0) {
+      const char* e = getenv("ADB_CONV_B128BOX");
+      b128 = (e && e[0] == '0') ? 0 : 1;
+    }
+    kp.b_one_box = b128;
+    const uint32_t box[2] = {(uint32_t)BLOCK_K, (uint32_t)(block_n == 256 && !b128 ? 64 : block_n / ncta)};
     int r = make_tmap_bf16(&kp.tmW, d->weight, 2, dims, strides, box);
     if (r != ADB_OK) return r;
   }

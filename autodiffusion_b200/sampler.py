@@ -117,6 +117,8 @@ class SchedulePlan:
                 self.y = th.zeros((batch,), dtype=th.int64, device=dev)
             self.guidance = cond_fn.shared_plan(self.x, self.t_in, self.y, self.grad)
             self._count_launches()
+        # second stream for the guidance branch of each step (created here, outside any capture)
+        self._side = th.cuda.Stream(device=dev) if self.guidance is not None else None
         self.graph: Optional[th.cuda.CUDAGraph] = None
         if (cond_fn is None or self.guidance is not None) and use_graph:
             g = th.cuda.CUDAGraph()
@@ -161,8 +163,6 @@ class SchedulePlan:
         # +2 % images/s, bit-identical samples. Inside a capture the fork / join become graph edges.
         # ADB_CONCURRENT_GUIDANCE=0 restores the single-stream order (A/B testing).
         conc = self.guidance is not None and os.environ.get("ADB_CONCURRENT_GUIDANCE", "1") != "0"
-        if conc and getattr(self, "_side", None) is None:
-            self._side = th.cuda.Stream(device=self.x.device)
         for n in range(self.K):
             if conc:
                 main = th.cuda.current_stream()

@@ -163,6 +163,11 @@ def test_library_loads_and_exports_header_symbols():
     assert handle.adb_version() == 100
     assert handle.adb_conv_block_n(192) == 192 and handle.adb_conv_block_n(6) == 16
     assert handle.adb_plan_num_ops(None) == 0
+    # host-only predicate of the conv epilogue's GroupNorm-backward sums (full tiles on the all-TMA path, include/adb200.h)
+    assert handle.adb_conv_gnb_supported(256, 64, 64, 128) == 1 and handle.adb_conv_gnb_supported(256, 8, 8, 512) == 1
+    assert handle.adb_conv_gnb_supported(1, 8, 8, 512) == 0    # 64 rows: not a full 128-row tile
+    assert handle.adb_conv_gnb_supported(2, 4, 4, 512) == 0    # 16 pixels per image: a 32-row slab would span images
+    assert handle.adb_conv_gnb_supported(4, 16, 16, 48) == 0   # channels must divide into 32 groups
 
 
 def test_fast_path_locates_the_modules_behind_the_reference_closures():
